@@ -1,0 +1,139 @@
+"""Synthetic multi-sample single-cell datasets shaped like the reference's demo.
+
+There is no scanpy/umap/anndata in this image and no network for real datasets, so the parity tests
+and ``bench.py`` build their own AnnData-like inputs: a latent Gaussian mixture whose cluster
+proportions differ between cases and controls, an exact kNN graph and UMAP's fuzzy-simplicial-set
+weights symmetrised as ``A = P + P^T - P o P^T`` — i.e. what ``scanpy.pp.neighbors`` would leave in
+``.obsp['connectivities']`` (float64 CSR, sorted indices, zero diagonal, weights in (0, 1]).
+
+The kNN search uses scikit-learn on the CPU for test-sized inputs and the library's brute-force
+CUDA kernel (``cna_knn_bruteforce``) for benchmark-sized inputs when a GPU is present; the weight
+construction runs in torch on whichever device is available.  None of this is on the timed path.
+"""
+import math
+
+import numpy as np
+import pandas as pd
+import scipy.sparse as sp
+import torch
+
+
+class AnnDataLike:
+    """Duck-typed AnnData: the hot path only touches ``.obs`` and ``.obsp['connectivities']``
+    (reference ``_nam.py:19,51``; ``_association.py:228-237``)."""
+
+    def __init__(self, obs, connectivities):
+        self.obs = obs
+        self.obsp = {"connectivities": connectivities}
+
+    @property
+    def n_obs(self):
+        return len(self.obs)
+
+    def __repr__(self):
+        a = self.obsp["connectivities"]
+        return f"AnnDataLike(n_obs={self.n_obs}, nnz={a.nnz}, obs={list(self.obs.columns)})"
+
+
+def _knn_cpu(points, k):
+    from sklearn.neighbors import NearestNeighbors
+    nn = NearestNeighbors(n_neighbors=k, algorithm="auto").fit(points)
+    dist, idx = nn.kneighbors(points)
+    # drop self (first hit; duplicates are vanishingly unlikely with continuous data)
+    return idx[:, 1:].astype(np.int64), dist[:, 1:].astype(np.float64)
+
+
+def _knn_gpu(points, k):
+    from . import _lib
+    pts = torch.as_tensor(points, dtype=torch.float32, device="cuda").contiguous()
+    idx, d2 = _lib.knn_bruteforce(pts, k - 1)
+    return idx, d2.double().sqrt_()
+
+
+def fuzzy_simplicial_set(idx, dist, n_iter=64):
+    """UMAP's smooth-kNN-distance weights, symmetrised by probabilistic t-conorm.
+
+    idx/dist: [N, k-1] neighbour indices / distances (self excluded), torch tensors (any device) or
+    numpy arrays.  Returns scipy CSR float64 with sorted indices."""
+    idx = torch.as_tensor(idx)
+    dist = torch.as_tensor(dist, dtype=torch.float64, device=idx.device)
+    idx = idx.long()
+    N, km1 = idx.shape
+    target = math.log2(km1 + 1)
+    rho = dist[:, :1]
+    gap = (dist - rho).clamp_(min=0)
+    lo = torch.zeros(N, 1, dtype=torch.float64, device=idx.device)
+    hi = torch.full((N, 1), float("inf"), dtype=torch.float64, device=idx.device)
+    mid = torch.ones(N, 1, dtype=torch.float64, device=idx.device)
+    for _ in range(n_iter):
+        psum = torch.exp(-gap / mid).sum(dim=1, keepdim=True)
+        too_big = psum > target
+        hi = torch.where(too_big, mid, hi)
+        lo = torch.where(too_big, lo, mid)
+        mid = torch.where(torch.isinf(hi), mid * 2, (lo + hi) / 2)
+    p = torch.exp(-gap / mid).reshape(-1)
+    i = torch.arange(N, device=idx.device).repeat_interleave(km1)
+    j = idx.reshape(-1)
+    key = torch.cat([i * N + j, j * N + i])
+    val = torch.cat([p, p])
+    key, order = torch.sort(key)
+    val = val[order]
+    ukey, inv = torch.unique_consecutive(key, return_inverse=True)
+    s1 = torch.zeros(len(ukey), dtype=torch.float64, device=idx.device).index_add_(0, inv, val)
+    s2 = torch.zeros(len(ukey), dtype=torch.float64, device=idx.device).index_add_(0, inv, val * val)
+    w = s1 - (s1 * s1 - s2) / 2  # p + q - p.q for mutual pairs, p otherwise
+    rows = (ukey // N).cpu().numpy()
+    cols = (ukey % N).cpu().numpy().astype(np.int32)
+    indptr = np.zeros(N + 1, dtype=np.int64)
+    np.cumsum(np.bincount(rows, minlength=N), out=indptr[1:])
+    return sp.csr_matrix((w.cpu().numpy(), cols, indptr.astype(np.int32)), shape=(N, N))
+
+
+def make_dataset(n_cells=10000, n_samples=50, k=15, dim=None, seed=0, n_clusters=12, n_batches=4,
+                 ragged=False, knn="auto", device=None):
+    """Returns (AnnDataLike, sample_meta DataFrame with columns case / batch / age).
+
+    Cells are stored sample-contiguous like the reference's demo; ``ragged`` draws unequal cells
+    per sample.  ``obs`` has the column ``id`` (sample id per cell)."""
+    rng = np.random.default_rng(seed)
+    if dim is None:
+        dim = 20 if n_cells <= 200_000 else 6
+    if ragged:
+        w = rng.uniform(0.5, 1.5, n_samples)
+        counts = np.maximum((w / w.sum() * n_cells).astype(np.int64), 2)
+        counts[-1] += n_cells - counts.sum()
+    else:
+        counts = np.full(n_samples, n_cells // n_samples, dtype=np.int64)
+        counts[: n_cells - counts.sum()] += 1
+    sid = np.repeat(np.arange(n_samples), counts)
+    case = (np.arange(n_samples) >= n_samples / 2).astype(np.float64)
+    centres = rng.normal(0, 4.0, (n_clusters, dim))
+    logits = rng.normal(0, 0.3, (n_samples, n_clusters))
+    logits[:, 0] += 0.8 * case
+    probs = np.exp(logits)
+    probs /= probs.sum(axis=1, keepdims=True)
+    cum = np.cumsum(probs, axis=1)
+    u = rng.random(n_cells)
+    cluster = (u[:, None] > cum[sid]).sum(axis=1).clip(max=n_clusters - 1)
+    points = centres[cluster] + rng.normal(0, 1.0, (n_cells, dim))
+
+    use_gpu = torch.cuda.is_available() if knn == "auto" else knn == "gpu"
+    if use_gpu and n_cells >= 50_000:
+        idx, dist = _knn_gpu(points, k)
+    else:
+        idx, dist = _knn_cpu(points, k)
+        if device is None and torch.cuda.is_available():
+            device = "cuda"
+        idx = torch.as_tensor(idx, device=device or "cpu")
+        dist = torch.as_tensor(dist, device=device or "cpu")
+    A = fuzzy_simplicial_set(idx, dist)
+
+    index = (pd.Index([f"c{i}" for i in range(n_cells)]) if n_cells <= 200_000
+             else pd.RangeIndex(n_cells))
+    obs = pd.DataFrame({"id": sid}, index=index)
+    meta = pd.DataFrame({
+        "case": case,
+        "batch": np.tile(np.arange(n_batches), n_samples // n_batches + 1)[:n_samples],
+        "age": np.random.default_rng(seed + 1).normal(0, 1, n_samples),
+    }, index=pd.Index(np.arange(n_samples), name="id"))
+    return AnnDataLike(obs, A), meta

@@ -1,0 +1,106 @@
+"""Shared comparison helpers for the parity tests."""
+import json
+import os
+import warnings
+
+import numpy as np
+
+from tests.golden import cases
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load_golden(stem):
+    arrays = dict(np.load(os.path.join(GOLD, stem + ".npz")))
+    scalars = json.load(open(os.path.join(GOLD, stem + ".json")))
+    return arrays, scalars
+
+
+def synth_raw(arrays, name):
+    pre = name + "/raw_"
+    return {k[len(pre):]: v for k, v in arrays.items() if k.startswith(pre)}
+
+
+def run_association(fn, data, kwargs, np_seed=None, **extra):
+    """Call an ``association`` implementation the way the golden cases do; returns (res, warnings)."""
+    if np_seed is not None:
+        np.random.seed(np_seed)
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        res = fn(data, return_full=True, **kwargs, **extra)
+    warns = sorted({str(x.message)[:60] for x in w if issubclass(x.category, UserWarning)})
+    return res, warns
+
+
+def sign_align(a, b):
+    """Flip the columns of ``a`` to the sign of the matching columns of ``b``."""
+    s = np.sign((a * b).sum(axis=0))
+    s[s == 0] = 1
+    return a * s
+
+
+def assert_matches_golden(res, data, key, arrays, scalars, name, warns=None, rtol=1e-9, atol=1e-12,
+                          exact_sets=True, check_full=True):
+    """Compare a result Namespace + obs columns with the reference outputs stored for ``name``.
+
+    ``rtol`` is the relative tolerance for floating-point outputs (1e-9 for the float64 oracle,
+    1e-5 — the north-star tolerance — for the fp32 CUDA path); integer / index outputs are exact.
+    """
+    sc = scalars[name]
+    g = lambda f: arrays[name + "/" + f]  # noqa: E731
+    # ---- integer / index outputs: exact ----
+    assert list(map(int, res.ks)) == sc["ks"]
+    assert int(res.k) == int(sc["k"])
+    assert int(res.r) == int(sc["r"])
+    np.testing.assert_array_equal(np.asarray(res.kept), g("kept"))
+    assert float(res.p) == sc["p"], (res.p, sc["p"])  # a count ratio
+    if warns is not None:
+        assert warns == sc["warnings"]
+    coef_fdr = data.obs[key + "_fdr"].to_numpy()
+    if exact_sets:
+        assert int((coef_fdr <= 0.05).sum()) == sc["n_fdr05"]
+        assert int((coef_fdr <= 0.10).sum()) == sc["n_fdr10"]
+        np.testing.assert_array_equal(coef_fdr <= 0.05, g("coef_fdr") <= 0.05)
+        nt = min(len(g("fdrs")), len(res.fdrs))
+        np.testing.assert_array_equal(g("fdrs")[:nt, 2], res.fdrs["num_detected"].to_numpy()[:nt])
+    # ---- floating-point outputs ----
+    close = lambda a, b, **kw: np.testing.assert_allclose(  # noqa: E731
+        np.asarray(a, dtype=np.float64), b, rtol=kw.get("rtol", rtol), atol=kw.get("atol", atol))
+    close(res.ncorrs.to_numpy(), g("ncorrs"), atol=max(atol, rtol * np.abs(g("ncorrs")).max()))
+    close(data.obs[key].to_numpy(), g("coef"), atol=max(atol, rtol * np.nanmax(np.abs(g("coef")))))
+    svs = g("svs")
+    close(res.namresid_svs.to_numpy(), svs, atol=max(atol, rtol * 1e-3 * svs.max()))
+    close(res.r2, sc["r2"])
+    kk = int(sc["k"])
+    close(np.abs(res.beta), np.abs(g("beta")), atol=max(atol, rtol * np.abs(g("beta")).max()))
+    close(res.r2_perpc, g("r2_perpc"), atol=max(atol, rtol))
+    close(res.yresid.to_numpy(), g("yresid"), atol=max(atol, rtol))
+    close(res.yresid_hat, g("yresid_hat"), atol=max(atol, rtol))
+    close(res.nullminps, g("nullminps"), rtol=max(rtol, 1e-9) * 50, atol=1e-300)
+    close(res.nullr2_mean, sc["nullr2_mean"], rtol=max(rtol, 1e-9) * 10)
+    close(res.nullr2_std, sc["nullr2_std"], rtol=max(rtol, 1e-9) * 10)
+    # len(np.arange(m/4, m, m/400)) (_association.py:102) is 300 or 301 depending on the last
+    # bit of m = max|ncorrs| — a floating-point knife-edge of the reference itself (its own result
+    # changes with the BLAS summation order).  The common 300 rows must agree.
+    fd = g("fdrs")
+    assert len(fd) in (300, 301) and len(res.fdrs) in (300, 301)
+    nt = min(len(fd), len(res.fdrs))
+    close(res.fdrs["threshold"].to_numpy()[:nt], fd[:nt, 0])
+    close(res.fdrs["fdr"].to_numpy()[:nt], fd[:nt, 1], rtol=max(rtol, 1e-9), atol=max(atol, rtol))
+    for f in ("fdr_5p_t", "fdr_10p_t"):
+        if sc[f] is None:
+            assert getattr(res, f) is None
+        else:
+            close(getattr(res, f), sc[f])
+    close(coef_fdr, g("coef_fdr"), atol=max(atol, rtol))
+    close(res.M.to_numpy(), g("M"), atol=max(atol, rtol))
+    if check_full:
+        n_top = max(kk, 4)
+        U = sign_align(res.namresid_sampleXpc.to_numpy()[:, :n_top], g("U")[:, :n_top])
+        close(U, g("U")[:, :n_top], atol=max(1e-9, rtol * 20))
+        close(res.namresid_varexp.to_numpy()[:n_top], g("varexp")[:n_top])
+        close(res.namresid.to_numpy()[:, :64], g("namresid_head"), atol=max(atol, rtol * 10))
+        nh = g("nam_head")
+        close(res.nam.to_numpy()[:, :64], nh, atol=max(atol, rtol * np.abs(nh).max()))
+        V = sign_align(res.namresid_nbhdXpc.to_numpy()[:64, :n_top], g("V_head")[:, :n_top])
+        close(V, g("V_head")[:, :n_top], atol=max(1e-9, rtol * 20 * np.abs(g("V_head")).max()))
