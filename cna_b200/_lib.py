@@ -1,0 +1,274 @@
+"""ctypes binding of ``libcna_b200.so`` (the C-ABI declared in ``include/cna_b200.h``).
+
+torch is used here only to own device memory and streams: every wrapper takes torch CUDA tensors,
+checks dtype / contiguity, and passes raw device pointers plus the current CUDA stream to the
+library.  There is no fallback: if the shared library is missing, or a tensor is not on a CUDA
+device, the call raises.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_build", "libcna_b200.so")
+
+_lib = None
+
+
+class CnaError(RuntimeError):
+    pass
+
+
+def load():
+    """Load (building first if the sources are newer and nvcc is present) the shared library."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        from . import build as _build
+        try:
+            _build.build()
+        except Exception as exc:  # no nvcc on this machine and no prebuilt library
+            raise ImportError(
+                f"cna_b200: {LIB_PATH} is missing and could not be built ({exc}). "
+                "Run `python -m cna_b200.build` on a machine with nvcc 12.9.") from exc
+    lib = ctypes.CDLL(LIB_PATH)
+    _declare(lib)
+    if lib.cna_abi_version() != 1:
+        raise ImportError("cna_b200: ABI version mismatch between _lib.py and libcna_b200.so")
+    _lib = lib
+    return lib
+
+
+_I32P = ctypes.c_void_p
+_VP = ctypes.c_void_p
+_I64 = ctypes.c_int64
+_INT = ctypes.c_int
+_DBL = ctypes.c_double
+
+
+class ResidArgs(ctypes.Structure):
+    _fields_ = [
+        ("s", _VP), ("ld_s", _I64), ("n_rows", _I64), ("inv_count", _VP),
+        ("colmap", _VP), ("n", _INT),
+        ("row_keep", _VP),
+        ("C", _VP), ("Wt", _VP), ("r", _INT),
+        ("seg_order", _VP), ("seg_off", _VP), ("n_batches", _INT),
+        ("y", _VP),
+        ("x_out", _VP), ("ld_x", _I64), ("kurt", _VP), ("ncorr", _VP), ("row_valid", _VP),
+    ]
+
+
+# name -> argtypes; every function returns int except the three bookkeeping calls
+_SIGNATURES = {
+    "cna_graph_colsum": [_VP, _VP, _VP, _INT, _I64, _VP, _VP],
+    "cna_graph_scale": [_VP, _VP, _VP, _INT, _I64, _VP, _DBL, _VP, _VP, _INT, _VP],
+    "cna_diffuse_onehot": [_VP, _VP, _VP, _VP, _VP, _I64, _INT, _VP, _I64, _VP],
+    "cna_diffuse_step_f32": [_VP, _VP, _VP, _VP, _VP, _VP, _I64, _INT, _I64, _VP],
+    "cna_diffuse_step_f64": [_VP, _VP, _VP, _VP, _VP, _VP, _I64, _INT, _I64, _VP],
+    "cna_row_kurtosis": [_VP, _I64, _I64, _INT, _VP, _VP, _VP],
+    "cna_batch_kurtosis": [_VP, _I64, _I64, _VP, _VP, _VP, _INT, _INT, _VP, _VP],
+    "cna_resid_pass": [ctypes.POINTER(ResidArgs), _VP],
+    "cna_gram": [_VP, _I64, _I64, _INT, _VP, _VP],
+    "cna_gram_simt": [_VP, _I64, _I64, _INT, _VP, _VP],
+    "cna_right_multiply": [_VP, _I64, _I64, _INT, _VP, _I64, _INT, _VP, _I64, _VP],
+    "cna_perm_stats": [_VP, _VP, _I64, _INT, _VP, _VP, _INT, _VP, _INT, _VP, _INT, _VP, _VP, _VP,
+                       _I64, _INT, _VP],
+    "cna_null_hist": [_VP, _I64, _I64, _INT, _VP, _I64, _INT, _VP, _INT, _DBL, _VP, _VP],
+    "cna_obs_hist": [_VP, _VP, _I64, _VP, _VP, _INT, _VP, _VP, _VP],
+    "cna_absmax": [_VP, _VP, _I64, _VP, _VP],
+    "cna_cell_fdr": [_VP, _VP, _I64, _VP, _VP, _INT, _VP, _VP, _VP],
+    "cna_knn_bruteforce": [_VP, _I64, _INT, _INT, _VP, _VP, _VP],
+}
+EXPORTS = sorted(list(_SIGNATURES) + ["cna_abi_version", "cna_last_error", "cna_launch_count"])
+
+
+def _declare(lib):
+    lib.cna_abi_version.restype = ctypes.c_int
+    lib.cna_abi_version.argtypes = []
+    lib.cna_last_error.restype = ctypes.c_char_p
+    lib.cna_last_error.argtypes = []
+    lib.cna_launch_count.restype = ctypes.c_int64
+    lib.cna_launch_count.argtypes = []
+    for name, args in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = ctypes.c_int
+        fn.argtypes = args
+
+
+def _check(rc, name):
+    if rc != 0:
+        raise CnaError(f"{name} failed ({rc}): {load().cna_last_error().decode()}")
+
+
+def _ptr(t, dtype, name, allow_none=False):
+    if t is None:
+        if allow_none:
+            return None
+        raise CnaError(f"{name}: tensor required")
+    if not t.is_cuda:
+        raise CnaError(f"{name}: expected a CUDA tensor (cna_b200 has no CPU path)")
+    if t.dtype != dtype:
+        raise CnaError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise CnaError(f"{name}: tensor must be contiguous")
+    return t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def launch_count():
+    return int(load().cna_launch_count())
+
+
+# ---------------------------------------------------------------------------------------------
+# thin typed wrappers
+# ---------------------------------------------------------------------------------------------
+def graph_colsum(indptr, indices, data, colsum):
+    is64 = data.dtype == torch.float64
+    _check(load().cna_graph_colsum(_ptr(indptr, torch.int32, "indptr"), _ptr(indices, torch.int32, "indices"),
+                                   _ptr(data, data.dtype, "data"), int(is64), indptr.numel() - 1,
+                                   _ptr(colsum, torch.float64, "colsum"), _stream()), "cna_graph_colsum")
+
+
+def graph_scale(indptr, indices, data, colsum, self_weight, vals, diag):
+    is64 = data.dtype == torch.float64
+    out64 = vals.dtype == torch.float64
+    _check(load().cna_graph_scale(_ptr(indptr, torch.int32, "indptr"), _ptr(indices, torch.int32, "indices"),
+                                  _ptr(data, data.dtype, "data"), int(is64), indptr.numel() - 1,
+                                  _ptr(colsum, torch.float64, "colsum"), float(self_weight),
+                                  _ptr(vals, vals.dtype, "vals"), _ptr(diag, vals.dtype, "diag"),
+                                  int(out64), _stream()), "cna_graph_scale")
+
+
+def diffuse_onehot(indptr, indices, vals, diag, code, n_samples, out):
+    _check(load().cna_diffuse_onehot(_ptr(indptr, torch.int32, "indptr"), _ptr(indices, torch.int32, "indices"),
+                                     _ptr(vals, torch.float32, "vals"), _ptr(diag, torch.float32, "diag"),
+                                     _ptr(code, torch.int32, "code"), out.shape[0], int(n_samples),
+                                     _ptr(out, torch.float32, "out"), out.shape[1], _stream()),
+           "cna_diffuse_onehot")
+
+
+def diffuse_step(indptr, indices, vals, diag, src, dst, n_cols):
+    if src.dtype == torch.float32:
+        fn, name, dt = load().cna_diffuse_step_f32, "cna_diffuse_step_f32", torch.float32
+    else:
+        fn, name, dt = load().cna_diffuse_step_f64, "cna_diffuse_step_f64", torch.float64
+    _check(fn(_ptr(indptr, torch.int32, "indptr"), _ptr(indices, torch.int32, "indices"),
+              _ptr(vals, dt, "vals"), _ptr(diag, dt, "diag"), _ptr(src, dt, "src"), _ptr(dst, dt, "dst"),
+              src.shape[0], int(n_cols), src.shape[1], _stream()), name)
+
+
+def row_kurtosis(s, n_samples, inv_count, kurt):
+    _check(load().cna_row_kurtosis(_ptr(s, torch.float32, "s"), s.shape[1], s.shape[0], int(n_samples),
+                                   _ptr(inv_count, torch.float64, "inv_count"),
+                                   _ptr(kurt, torch.float64, "kurt"), _stream()), "cna_row_kurtosis")
+
+
+def batch_kurtosis(s, inv_count, seg_order, seg_off, kurt):
+    nb = seg_off.numel() - 1
+    _check(load().cna_batch_kurtosis(_ptr(s, torch.float32, "s"), s.shape[1], s.shape[0],
+                                     _ptr(inv_count, torch.float64, "inv_count"),
+                                     _ptr(seg_order, torch.int32, "seg_order"),
+                                     _ptr(seg_off, torch.int32, "seg_off"), nb, seg_order.numel(),
+                                     _ptr(kurt, torch.float64, "kurt"), _stream()), "cna_batch_kurtosis")
+
+
+def resid_pass(s, inv_count, colmap, row_keep, C, Wt, seg_order, seg_off, y, x_out, kurt, ncorr, row_valid):
+    a = ResidArgs()
+    a.s = _ptr(s, torch.float32, "s"); a.ld_s = s.shape[1]; a.n_rows = s.shape[0]
+    a.inv_count = _ptr(inv_count, torch.float64, "inv_count")
+    a.colmap = _ptr(colmap, torch.int32, "colmap"); a.n = colmap.numel()
+    a.row_keep = _ptr(row_keep, torch.uint8, "row_keep", allow_none=True)
+    r = 0 if C is None else C.shape[1]
+    a.C = _ptr(C, torch.float64, "C") if r else None
+    a.Wt = _ptr(Wt, torch.float64, "Wt") if r else None
+    a.r = r
+    if seg_off is not None and seg_off.numel() > 2:
+        a.seg_order = _ptr(seg_order, torch.int32, "seg_order")
+        a.seg_off = _ptr(seg_off, torch.int32, "seg_off")
+        a.n_batches = seg_off.numel() - 1
+    else:
+        a.seg_order = None; a.seg_off = None; a.n_batches = 1
+    a.y = _ptr(y, torch.float64, "y")
+    a.x_out = _ptr(x_out, torch.float32, "x_out"); a.ld_x = x_out.shape[1]
+    a.kurt = _ptr(kurt, torch.float64, "kurt", allow_none=True)
+    a.ncorr = _ptr(ncorr, torch.float64, "ncorr")
+    a.row_valid = _ptr(row_valid, torch.uint8, "row_valid")
+    _check(load().cna_resid_pass(ctypes.byref(a), _stream()), "cna_resid_pass")
+
+
+def gram(x, n, out, simt=False):
+    fn = load().cna_gram_simt if simt else load().cna_gram
+    _check(fn(_ptr(x, torch.float32, "x"), x.shape[1], x.shape[0], int(n), _ptr(out, torch.float64, "gram"),
+              _stream()), "cna_gram")
+
+
+def right_multiply(x, n, b, n_out, out):
+    _check(load().cna_right_multiply(_ptr(x, torch.float32, "x"), x.shape[1], x.shape[0], int(n),
+                                     _ptr(b, torch.float32, "b"), b.shape[1], int(n_out),
+                                     _ptr(out, torch.float32, "out"), out.shape[1], _stream()),
+           "cna_right_multiply")
+
+
+def perm_stats(y, perm, C, W, Ut, ks, ssered, ssefull, ycond, n_local):
+    K, n = perm.shape
+    r = 0 if C is None else C.shape[1]
+    _check(load().cna_perm_stats(_ptr(y, torch.float64, "y"), _ptr(perm, torch.int32, "perm"), K, n,
+                                 _ptr(C, torch.float64, "C") if r else None,
+                                 _ptr(W, torch.float64, "W") if r else None, r,
+                                 _ptr(Ut, torch.float64, "Ut"), Ut.shape[0], _ptr(ks, torch.int32, "ks"),
+                                 ks.numel(), _ptr(ssered, torch.float64, "ssered"),
+                                 _ptr(ssefull, torch.float64, "ssefull"),
+                                 _ptr(ycond, torch.float32, "ycond", allow_none=True),
+                                 0 if ycond is None else ycond.shape[1], int(n_local), _stream()),
+           "cna_perm_stats")
+
+
+def null_hist(x, n, ycond, n_null, edges, edge0, hist):
+    _check(load().cna_null_hist(_ptr(x, torch.float32, "x"), x.shape[1], x.shape[0], int(n),
+                                _ptr(ycond, torch.float32, "ycond"), ycond.shape[1], int(n_null),
+                                _ptr(edges, torch.float64, "edges"), edges.numel(), float(edge0),
+                                _ptr(hist, torch.int32, "hist"), _stream()), "cna_null_hist")
+
+
+def obs_hist(ncorr, row_valid, edges, thresholds, rank_hist, det_hist):
+    _check(load().cna_obs_hist(_ptr(ncorr, torch.float64, "ncorr"),
+                               _ptr(row_valid, torch.uint8, "row_valid", allow_none=True), ncorr.numel(),
+                               _ptr(edges, torch.float64, "edges"), _ptr(thresholds, torch.float64, "thresholds"),
+                               edges.numel(), _ptr(rank_hist, torch.int32, "rank_hist"),
+                               _ptr(det_hist, torch.int32, "det_hist"), _stream()), "cna_obs_hist")
+
+
+def absmax(v, row_valid, out):
+    _check(load().cna_absmax(_ptr(v, torch.float64, "v"), _ptr(row_valid, torch.uint8, "row_valid", allow_none=True),
+                             v.numel(), _ptr(out, torch.float64, "out"), _stream()), "cna_absmax")
+
+
+def cell_fdr(ncorr, row_valid, thresholds, prefix_min_fdr, coef, fdr):
+    _check(load().cna_cell_fdr(_ptr(ncorr, torch.float64, "ncorr"),
+                               _ptr(row_valid, torch.uint8, "row_valid", allow_none=True), ncorr.numel(),
+                               _ptr(thresholds, torch.float64, "thresholds"),
+                               _ptr(prefix_min_fdr, torch.float64, "prefix_min_fdr"), thresholds.numel(),
+                               _ptr(coef, torch.float64, "coef"), _ptr(fdr, torch.float64, "fdr"), _stream()),
+           "cna_cell_fdr")
+
+
+def knn_bruteforce(points, k):
+    """points: [n, dim] float32 CUDA tensor.  Returns (idx int64 [n, k], dist2 float32 [n, k])."""
+    n, dim = points.shape
+    pad = next(d for d in (4, 8, 16, 32) if d >= dim) if dim <= 32 else None
+    if pad is None:
+        raise CnaError("knn_bruteforce: at most 32 dimensions")
+    if pad != dim:
+        points = torch.nn.functional.pad(points, (0, pad - dim))
+    points = points.contiguous()
+    idx = torch.empty((n, k), dtype=torch.int32, device=points.device)
+    d2 = torch.empty((n, k), dtype=torch.float32, device=points.device)
+    _check(load().cna_knn_bruteforce(_ptr(points, torch.float32, "points"), n, pad, int(k),
+                                     _ptr(idx, torch.int32, "idx"), _ptr(d2, torch.float32, "dist2"),
+                                     _stream()), "cna_knn_bruteforce")
+    return idx.long(), d2

@@ -1,0 +1,297 @@
+// Kernel (ii): everything between the diffusion and the Gram matrix that is local to one cell.
+//
+// In the cells x samples layout each neighbourhood is one row, so QC (batch kurtosis), the
+// sample reindex/filter, centring, the ridge residualisation, the ddof=1 standardisation and the
+// neighbourhood coefficient are all row-local: one read of the fp32 state, one write of the
+// fp32 residualised NAM.  Arithmetic inside a row is fp64 (the reference is fp64 throughout and
+// the per-row work is tiny: ~2 n (r+3) flops).
+//
+// Reference: src/cna/tools/_nam.py:78-99 (QC), :118-159 (_resid_nam), _association.py:175-185
+// (reindex, filter, zero-variance drop), :77 (ncorrs).
+#include "common.cuh"
+
+namespace cna {
+
+// Pearson kurtosis across the per-batch means of the values in `rowbuf` (per-warp shared memory).
+// Batch b owns positions seg_order[seg_off[b] .. seg_off[b+1]).  `means` is per-warp scratch [nb].
+// Every lane returns the result.  (_nam.py:78-82)
+__device__ __forceinline__ double batch_kurtosis_of_row(const double *rowbuf, double *means,
+                                                        const int *seg_order, const int *seg_off,
+                                                        int nb, int lane) {
+    int G = 1;  // lanes cooperating on one batch
+    while (G * 2 * nb <= 32) G *= 2;
+    int groups = 32 / G, g = lane / G, u = lane % G;
+    int iters = (nb + groups - 1) / groups;
+    for (int it = 0; it < iters; ++it) {
+        int b = g + it * groups;
+        bool active = b < nb;
+        double acc = 0.0;
+        int t0 = 0, t1 = 0;
+        if (active) {
+            t0 = seg_off[b];
+            t1 = seg_off[b + 1];
+            for (int t = t0 + u; t < t1; t += G) acc += rowbuf[seg_order[t]];
+        }
+        for (int o = G >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(kFull, acc, o);
+        if (active && u == 0) means[b] = acc / double(t1 - t0);
+    }
+    __syncwarp();
+    double tot = 0.0;
+    for (int b = lane; b < nb; b += 32) tot += means[b];
+    double mm = warp_sum(tot) / nb;
+    double s2 = 0.0, s4 = 0.0;
+    for (int b = lane; b < nb; b += 32) {
+        double d = means[b] - mm;
+        double d2 = d * d;
+        s2 += d2;
+        s4 += d2 * d2;
+    }
+    s2 = warp_sum(s2) / nb;
+    s4 = warp_sum(s4) / nb;
+    __syncwarp();
+    return kurtosis_from_moments(mm, s2, s4, false);
+}
+
+// ---------------------------------------------------------------------------------------------
+// QC: batch kurtosis of the raw NAM over all samples
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+batch_kurtosis_kernel(const float *__restrict__ s, int64_t ld, int64_t n_rows,
+                      const double *__restrict__ inv_count, const int32_t *__restrict__ seg_order_g,
+                      const int32_t *__restrict__ seg_off_g, int nb, int n_sel,
+                      double *__restrict__ kurt) {
+    extern __shared__ double sm[];
+    const int warps = blockDim.x >> 5;
+    double *invc = sm;                       // [n_sel] scaling of the selected columns
+    double *rowbuf = invc + n_sel;           // [warps][n_sel]
+    double *means = rowbuf + warps * n_sel;  // [warps][nb]
+    int *seg_col = reinterpret_cast<int *>(means + warps * nb);  // [n_sel] state column ids
+    int *seg_pos = seg_col + n_sel;          // [n_sel] identity positions
+    int *seg_off = seg_pos + n_sel;          // [nb + 1]
+    for (int t = threadIdx.x; t < n_sel; t += blockDim.x) {
+        int c = seg_order_g[t];
+        seg_col[t] = c;
+        seg_pos[t] = t;
+        invc[t] = inv_count[c];
+    }
+    for (int t = threadIdx.x; t <= nb; t += blockDim.x) seg_off[t] = seg_off_g[t];
+    __syncthreads();
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    double *rb = rowbuf + w * n_sel, *mb = means + w * nb;
+    int64_t stride = int64_t(gridDim.x) * warps;
+    for (int64_t row = int64_t(blockIdx.x) * warps + w; row < n_rows; row += stride) {
+        const float *p = s + row * ld;
+        for (int t = lane; t < n_sel; t += 32) rb[t] = double(__ldg(p + seg_col[t])) * invc[t];
+        __syncwarp();
+        double k = batch_kurtosis_of_row(rb, mb, seg_pos, seg_off, nb, lane);
+        if (lane == 0) kurt[row] = k;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// fused select / centre / residualise / standardise / ncorr pass
+// ---------------------------------------------------------------------------------------------
+template <int NQ>
+__global__ void __launch_bounds__(256) resid_kernel(cna_resid_args a) {
+    extern __shared__ double sm[];
+    const int warps = blockDim.x >> 5;
+    const int n = a.n, r = a.r, nb = a.n_batches;
+    const bool want_kurt = (a.kurt != nullptr) && nb > 1;
+    double *Wt = sm;                         // [r][n]
+    double *Ct = Wt + r * n;                 // [r][n]  (transposed copy of C [n x r])
+    double *ys = Ct + r * n;                 // [n]
+    double *invc = ys + n;                   // [n]
+    double *proj = invc + n;                 // [warps][r]
+    double *rowbuf = proj + warps * r;       // [warps][n]   (only when want_kurt)
+    double *means = rowbuf + (want_kurt ? warps * n : 0);  // [warps][nb]
+    int *colmap = reinterpret_cast<int *>(means + (want_kurt ? warps * nb : 0));  // [n]
+    int *seg_order = colmap + n;             // [n]
+    int *seg_off = seg_order + n;            // [nb + 1]
+    for (int t = threadIdx.x; t < r * n; t += blockDim.x) {
+        Wt[t] = a.Wt[t];
+        int rr = t / n, m = t % n;
+        Ct[t] = a.C[m * r + rr];
+    }
+    for (int t = threadIdx.x; t < n; t += blockDim.x) {
+        int c = a.colmap[t];
+        colmap[t] = c;
+        ys[t] = a.y[t];
+        invc[t] = a.inv_count[c];
+        if (want_kurt) seg_order[t] = a.seg_order[t];
+    }
+    if (want_kurt)
+        for (int t = threadIdx.x; t <= nb; t += blockDim.x) seg_off[t] = a.seg_off[t];
+    __syncthreads();
+
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    double *pw = proj + w * r;
+    double *rb = rowbuf + w * n, *mb = means + w * nb;
+    const double dn = double(n);
+    int64_t stride = int64_t(gridDim.x) * warps;
+    for (int64_t row = int64_t(blockIdx.x) * warps + w; row < a.n_rows; row += stride) {
+        const float *p = a.s + row * a.ld_s;
+        float *o = a.x_out + row * a.ld_x;
+        double x[NQ];
+        double sum = 0.0;
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            int m = lane + 32 * q;
+            x[q] = (m < n) ? double(__ldg(p + colmap[m])) * invc[m] : 0.0;
+            sum += x[q];
+        }
+        double mean = warp_sum(sum) / dn;
+        double ss = 0.0;
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            int m = lane + 32 * q;
+            x[q] = (m < n) ? x[q] - mean : 0.0;  // _nam.py:122
+            ss += x[q] * x[q];
+        }
+        double var0 = warp_sum(ss) / (dn - 1.0);
+        bool keep = a.row_keep ? (a.row_keep[row] != 0) : true;
+        bool valid = keep && !(var0 == 0.0);  // _association.py:182-185
+        if (!valid) {
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                int m = lane + 32 * q;
+                if (m < a.ld_x) o[m] = 0.f;
+            }
+            if (lane == 0) {
+                if (a.kurt) a.kurt[row] = nan("");
+                a.ncorr[row] = 0.0;
+                a.row_valid[row] = 0;
+            }
+            continue;
+        }
+        // rank-r update X <- X - (X Wt^T) C^T   (_nam.py:133-135 / :146-148 with M = I - C.W)
+        for (int rr = 0; rr < r; ++rr) {
+            double acc = 0.0;
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                int m = lane + 32 * q;
+                if (m < n) acc += x[q] * Wt[rr * n + m];
+            }
+            acc = warp_sum(acc);
+            if (lane == 0) pw[rr] = acc;
+        }
+        __syncwarp();
+        for (int rr = 0; rr < r; ++rr) {
+            double pr = pw[rr];
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                int m = lane + 32 * q;
+                if (m < n) x[q] -= pr * Ct[rr * n + m];
+            }
+        }
+        __syncwarp();
+        if (want_kurt) {  // _nam.py:150-155
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                int m = lane + 32 * q;
+                if (m < n) rb[m] = x[q];
+            }
+            __syncwarp();
+            double k = batch_kurtosis_of_row(rb, mb, seg_order, seg_off, nb, lane);
+            if (lane == 0) a.kurt[row] = k;
+        } else if (a.kurt && lane == 0) {
+            a.kurt[row] = nan("");
+        }
+        // ddof=1 standardisation (_nam.py:159; pandas std recomputes the mean)
+        double s1 = 0.0;
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) s1 += x[q];
+        double mean2 = warp_sum(s1) / dn;
+        double s2 = 0.0;
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            int m = lane + 32 * q;
+            double d = (m < n) ? x[q] - mean2 : 0.0;
+            s2 += d * d;
+        }
+        double sd = sqrt(warp_sum(s2) / (dn - 1.0));
+        double dot = 0.0;
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            int m = lane + 32 * q;
+            double v = x[q] / sd;
+            if (m < n) {
+                dot += v * ys[m];
+                o[m] = float(v);
+            } else if (m < a.ld_x) {
+                o[m] = 0.f;
+            }
+        }
+        dot = warp_sum(dot);
+        if (lane == 0) {
+            a.ncorr[row] = dot / dn;  // _association.py:77
+            a.row_valid[row] = 1;
+        }
+    }
+}
+
+}  // namespace cna
+
+using namespace cna;
+
+extern "C" {
+
+int cna_batch_kurtosis(const float *s, int64_t ld, int64_t n_rows, const double *inv_count,
+                       const int32_t *seg_order, const int32_t *seg_off, int n_batches, int n_sel,
+                       double *kurt, void *stream) {
+    CNA_REQUIRE(n_rows >= 0 && n_batches >= 2, "cna_batch_kurtosis: need at least two batches");
+    if (n_rows == 0) return CNA_OK;
+    CNA_REQUIRE(n_sel > 0 && n_sel <= ld, "cna_batch_kurtosis: bad segment table (n_sel=%d)", n_sel);
+    const int threads = 256, warps = threads / 32;
+    size_t smem = sizeof(double) * (size_t(n_sel) + size_t(warps) * n_sel + size_t(warps) * n_batches) +
+                  sizeof(int) * (2 * size_t(n_sel) + n_batches + 1);
+    CNA_REQUIRE(smem <= 200 * 1024, "cna_batch_kurtosis: %zu bytes of shared memory needed", smem);
+    CNA_CUDA(cudaFuncSetAttribute(batch_kurtosis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  int(smem)));
+    int64_t blocks_needed = (n_rows + warps - 1) / warps;
+    unsigned grid = unsigned(blocks_needed < int64_t(num_sms()) * 8 ? blocks_needed : int64_t(num_sms()) * 8);
+    batch_kurtosis_kernel<<<grid, threads, smem, as_stream(stream)>>>(
+        s, ld, n_rows, inv_count, seg_order, seg_off, n_batches, n_sel, kurt);
+    CNA_LAUNCHED("batch_kurtosis_kernel");
+    return CNA_OK;
+}
+
+int cna_resid_pass(const cna_resid_args *args, void *stream) {
+    CNA_REQUIRE(args != nullptr, "cna_resid_pass: null args");
+    const cna_resid_args &a = *args;
+    CNA_REQUIRE(a.n_rows >= 0 && a.n >= 2 && a.n <= 1024, "cna_resid_pass: n must be in [2, 1024] (got %d)", a.n);
+    CNA_REQUIRE(a.r >= 0 && a.ld_x >= a.n && a.ld_x <= ((a.n + 31) / 32) * 32,
+                "cna_resid_pass: bad r/ld_x (r=%d ld_x=%lld n=%d)", a.r, (long long)a.ld_x, a.n);
+    CNA_REQUIRE(a.s && a.inv_count && a.colmap && a.y && a.x_out && a.ncorr && a.row_valid,
+                "cna_resid_pass: null pointer");
+    CNA_REQUIRE(a.r == 0 || (a.C && a.Wt), "cna_resid_pass: C/Wt missing");
+    if (a.n_rows == 0) return CNA_OK;
+    const int threads = 256, warps = threads / 32;
+    const bool want_kurt = a.kurt && a.n_batches > 1;
+    CNA_REQUIRE(!want_kurt || (a.seg_order && a.seg_off), "cna_resid_pass: batch segments missing");
+    size_t smem = sizeof(double) * (2 * size_t(a.r) * a.n + 2 * size_t(a.n) + size_t(warps) * a.r +
+                                    (want_kurt ? size_t(warps) * (a.n + a.n_batches) : 0)) +
+                  sizeof(int) * (2 * size_t(a.n) + a.n_batches + 2);
+    CNA_REQUIRE(smem <= 200 * 1024,
+                "cna_resid_pass: n=%d, r=%d needs %zu bytes of shared memory (limit 200 KiB)", a.n, a.r, smem);
+    int64_t blocks_needed = (a.n_rows + warps - 1) / warps;
+    int64_t cap = int64_t(num_sms()) * 4;
+    unsigned grid = unsigned(blocks_needed < cap ? blocks_needed : cap);
+    int nq = (a.n + 31) / 32;
+    cudaStream_t st = as_stream(stream);
+#define CNA_RESID(NQ)                                                                              \
+    do {                                                                                           \
+        CNA_CUDA(cudaFuncSetAttribute(resid_kernel<NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                      int(smem)));                                                 \
+        resid_kernel<NQ><<<grid, threads, smem, st>>>(a);                                          \
+    } while (0)
+    if (nq <= 2) CNA_RESID(2);
+    else if (nq <= 4) CNA_RESID(4);
+    else if (nq <= 8) CNA_RESID(8);
+    else if (nq <= 16) CNA_RESID(16);
+    else CNA_RESID(32);
+#undef CNA_RESID
+    CNA_LAUNCHED("resid_kernel");
+    return CNA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,157 @@
+// Permutation engine: all Nnull shuffled-phenotype fits against the top NAM-PCs, one warp per
+// permutation, fp64 throughout (1 - r^2 cancels to ~1e-4, so fp32 is not an option here).
+//
+// Reference: src/cna/tools/_association.py:35-61 (_reg / _stats / _minp_stats) called once per
+// permutation from the Python loop at :84, and :94-97 (conditioned null phenotypes for the
+// neighbourhood-level test).  The F survival function (scipy.special.fdtrc, :46) and the argmin over
+// ks stay with the caller: they are O(Nnull * len(ks)) scalar work.
+#include "common.cuh"
+
+namespace cna {
+
+template <int NQ>
+__global__ void __launch_bounds__(256)
+perm_stats_kernel(const double *__restrict__ y, const int32_t *__restrict__ perm, int64_t K, int n,
+                  const double *__restrict__ C, const double *__restrict__ W, int r,
+                  const double *__restrict__ Ut, int kmax, const int32_t *__restrict__ ks, int nks,
+                  double *__restrict__ ssered, double *__restrict__ ssefull,
+                  float *__restrict__ ycond, int64_t ld_y, int n_local) {
+    extern __shared__ double sm[];
+    double *ys = sm;               // [n]
+    double *Ws = ys + n;           // [r][n]
+    double *Cs = Ws + r * n;       // [r][n] (transposed)
+    double *Us = Cs + r * n;       // [kmax][n]
+    double *proj = Us + kmax * n;  // [warps][r]
+    int *kss = reinterpret_cast<int *>(proj + (blockDim.x >> 5) * r);  // [nks]
+    for (int t = threadIdx.x; t < n; t += blockDim.x) ys[t] = y[t];
+    for (int t = threadIdx.x; t < r * n; t += blockDim.x) {
+        Ws[t] = W[t];
+        Cs[t] = C[(t % n) * r + t / n];
+    }
+    for (int t = threadIdx.x; t < kmax * n; t += blockDim.x) Us[t] = Ut[t];
+    for (int t = threadIdx.x; t < nks; t += blockDim.x) kss[t] = ks[t];
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, warps = blockDim.x >> 5;
+    double *pw = proj + w * r;
+    const double dn = double(n);
+    for (int64_t k = int64_t(blockIdx.x) * warps + w; k < K; k += int64_t(gridDim.x) * warps) {
+        double z[NQ];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            int m = lane + 32 * q;
+            z[q] = (m < n) ? ys[perm[k * n + m]] : 0.0;  // _stats.py:18  Y[bix]
+        }
+        // zc = M z with M = I - C.W  (_association.py:51)
+        for (int rr = 0; rr < r; ++rr) {
+            double acc = 0.0;
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                int m = lane + 32 * q;
+                if (m < n) acc += Ws[rr * n + m] * z[q];
+            }
+            acc = warp_sum(acc);
+            if (lane == 0) pw[rr] = acc;
+        }
+        __syncwarp();
+        for (int rr = 0; rr < r; ++rr) {
+            double pr = pw[rr];
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                int m = lane + 32 * q;
+                if (m < n) z[q] -= Cs[rr * n + m] * pr;
+            }
+        }
+        __syncwarp();
+        // zc /= zc.std(ddof=1)  (_association.py:52 — a pandas Series, hence ddof=1)
+        double s1 = 0.0;
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) s1 += z[q];
+        double mean = warp_sum(s1) / dn;
+        double s2 = 0.0;
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            int m = lane + 32 * q;
+            double d = (m < n) ? z[q] - mean : 0.0;
+            s2 += d * d;
+        }
+        double sd = sqrt(warp_sum(s2) / (dn - 1.0));
+        double sr = 0.0;
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            z[q] = z[q] / sd;
+            int m = lane + 32 * q;
+            if (m < n) {
+                sr += z[q] * z[q];
+                if (k < n_local) ycond[int64_t(m) * ld_y + k] = float(z[q]);
+            } else {
+                z[q] = 0.0;
+            }
+        }
+        sr = warp_sum(sr);  // ssered = zc.zc  (_association.py:43)
+        if (lane == 0) ssered[k] = sr;
+        // residual after regressing on the first j PCs, evaluated at j in ks (_association.py:35-42)
+        int next = 0;
+        for (int j = 0; j < kmax && next < nks; ++j) {
+            double b = 0.0;
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                int m = lane + 32 * q;
+                if (m < n) b += Us[j * n + m] * z[q];
+            }
+            b = warp_sum(b);  // beta_j = U[:, j] . zc  (U orthonormal: independent of the residual)
+            double ss = 0.0;
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                int m = lane + 32 * q;
+                if (m < n) {
+                    z[q] -= b * Us[j * n + m];
+                    ss += z[q] * z[q];
+                }
+            }
+            if (j + 1 == kss[next]) {
+                ss = warp_sum(ss);
+                if (lane == 0) ssefull[k * nks + next] = ss;
+                ++next;
+            }
+        }
+    }
+}
+
+}  // namespace cna
+
+using namespace cna;
+
+extern "C" int cna_perm_stats(const double *y, const int32_t *perm, int64_t K, int n, const double *C,
+                              const double *W, int r, const double *Ut, int kmax, const int32_t *ks,
+                              int nks, double *ssered, double *ssefull, float *ycond, int64_t ld_y,
+                              int n_local, void *stream) {
+    CNA_REQUIRE(K >= 0 && n >= 2 && n <= 1024 && r >= 0 && kmax >= 1 && kmax <= n && nks >= 1,
+                "cna_perm_stats: bad shape (K=%lld n=%d r=%d kmax=%d nks=%d)", (long long)K, n, r, kmax, nks);
+    CNA_REQUIRE(n_local == 0 || (ycond && ld_y >= n_local), "cna_perm_stats: ycond buffer too small");
+    if (K == 0) return CNA_OK;
+    const int threads = 256, warps = threads / 32;
+    size_t smem = sizeof(double) * (size_t(n) + 2 * size_t(r) * n + size_t(kmax) * n + size_t(warps) * r) +
+                  sizeof(int) * size_t(nks);
+    CNA_REQUIRE(smem <= 200 * 1024, "cna_perm_stats: n=%d r=%d kmax=%d needs %zu bytes of shared memory", n, r, kmax, smem);
+    int64_t blocks = (K + warps - 1) / warps;
+    int64_t cap = int64_t(num_sms()) * 2;
+    unsigned grid = unsigned(blocks < cap ? blocks : cap);
+    int nq = (n + 31) / 32;
+    cudaStream_t st = as_stream(stream);
+#define CNA_PERM(NQ)                                                                                  \
+    do {                                                                                              \
+        CNA_CUDA(cudaFuncSetAttribute(perm_stats_kernel<NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                      int(smem)));                                                    \
+        perm_stats_kernel<NQ><<<grid, threads, smem, st>>>(y, perm, K, n, C, W, r, Ut, kmax, ks, nks, \
+                                                            ssered, ssefull, ycond, ld_y, n_local);   \
+    } while (0)
+    if (nq <= 2) CNA_PERM(2);
+    else if (nq <= 4) CNA_PERM(4);
+    else if (nq <= 8) CNA_PERM(8);
+    else if (nq <= 16) CNA_PERM(16);
+    else CNA_PERM(32);
+#undef CNA_PERM
+    CNA_LAUNCHED("perm_stats_kernel");
+    return CNA_OK;
+}

@@ -1,0 +1,263 @@
+"""Association driver: global permutation test + neighbourhood-level FDRs.
+
+Mirrors ``src/cna/tools/_association.py`` of the reference: same signature, side effects on
+``data.obs``, exceptions, warnings and result Namespace.  The NAM never leaves the GPU unless
+``return_full=True`` asks for the big matrices.
+"""
+import warnings
+from argparse import Namespace
+
+import numpy as np
+import pandas as pd
+import scipy.stats as st
+import torch
+
+from .. import _lib
+from . import _nam, _stats
+from ._graph import _to_dev
+from ._out import select_output
+
+
+def check_inputs(data, y, sid_name, batches, covs, donorids, allow_low_sample_size):
+    """``_association.py:131-173`` — same checks, exception types and messages."""
+    if not isinstance(y, pd.Series):
+        raise TypeError(f"'y' must be a pandas Series, but got {type(y)}")
+    if batches is not None and not isinstance(batches, pd.Series):
+        raise TypeError(f"'batches' must be a pandas Series, but got {type(batches)}")
+    if covs is not None and not isinstance(covs, pd.DataFrame):
+        raise TypeError(f"'covs' must be a pandas DataFrame, but got {type(covs)}")
+    if donorids is not None and not isinstance(donorids, pd.Series):
+        raise TypeError(f"'donorids' must be a pandas Series, but got {type(donorids)}")
+    present = data.obs[sid_name].unique()
+    if not y.index.isin(present).all():
+        print("WARNING: index of 'y' contains values not present in 'data[sid_name]'. "
+              "These samples will be ignored.")
+    if not pd.Index(present).isin(y.index).all():
+        raise ValueError("'data[sid_name]' contains values not present in the index of 'y'.")
+    if batches is not None and donorids is not None:
+        raise ValueError("We do not currently support conditioning on batch "
+                         "while also accounting for multiple samples per donor")
+    if batches is None:
+        batches = pd.Series(np.ones(len(y)), index=y.index)
+    if covs is not None:
+        filter_samples = ~(y.isna() | covs.isna().any(axis=1)) & y.index.isin(present)
+        if donorids is not None:
+            print("WARNING: We currently do not account for multiple samples per donor "
+                  "when conditioning on covariates. This conditioning may therefore account "
+                  "only incompletely for the covariates of interest. We expect this to make "
+                  "only minor differences in most cases, but we have not investigated it formally")
+    else:
+        filter_samples = ~np.isnan(y) & y.index.isin(present)
+    if filter_samples.sum() < 10 and not allow_low_sample_size:
+        raise ValueError(
+            "You are supplying phenotype information on fewer than 10 samples. This may lead to "
+            "poor power at low sample sizes because our null distribution is one in which each "
+            "sample's single-cell profile is unchanged but the sample labels are randomly "
+            "assigned. If you want to run an analysis at this sample size despite the possibility of low "
+            "power, you can do so by invoking the association(...) function with the argument "
+            "allow_low_sample_size=True.")
+    return batches, filter_samples
+
+
+def default_ks(n):
+    """``_association.py:25-28``."""
+    incr = max(int(0.02 * n), 1)
+    maxnpcs = max(min(4 * incr, int(n / 5)), 1)
+    return np.arange(incr, maxnpcs + 1, incr)
+
+
+def _f_pvalues(ssered, ssefull, ks, n, r):
+    """``_association.py:41-48`` vectorised over permutations: returns (p, r2), each [K x len(ks)]."""
+    ks = np.asarray(ks, dtype=np.float64)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        f = ((ssered[:, None] - ssefull) / ks) / (ssefull / n)  # :45 (divides by n, not dof)
+        p = st.f.sf(f, ks, n - (1 + r + ks))  # :46
+        r2 = 1 - ssefull / ssered[:, None]  # :47
+    return p, r2
+
+
+def _pick(p, r2, ks):
+    """``_association.py:60``: k_ = nanargmin(ps) per permutation."""
+    with np.errstate(invalid="ignore"):
+        pick = np.nanargmin(p, axis=1)
+    rows = np.arange(p.shape[0])
+    return np.asarray(ks)[pick], p[rows, pick], r2[rows, pick]
+
+
+def _association(st_nam, res, y, batches, donorids, ks=None, Nnull=1000, force_permute_all=False,
+                 local_test=True, seed=None, show_progress=False):
+    """``_association.py:10-129``.  ``res`` carries the device-resident residualised NAM (``res.x``),
+    U, M, r; ``y`` / ``batches`` / ``donorids`` are length-n arrays in the order of res.x's columns."""
+    out = select_output(show_progress)
+    if seed is not None:
+        np.random.seed(seed)  # :15-16
+    if force_permute_all:
+        batches = np.ones(len(y))  # :17-18
+    U, M, r, n = res.U, res.M, res.r, res.n
+    dev = res.x.device
+    y = res.y_std
+    ks = res.ks
+    kmax = int(max(ks))
+
+    # ---- observed phenotype (:64-74): n-sized host arithmetic in float64 -----------------
+    ycond = M.dot(y)
+    ycond = ycond / ycond.std(ddof=1)  # a pandas Series in the reference -> ddof=1
+    ssered = np.array([ycond.dot(ycond)])
+    ssefull = np.array([[np.sum((U[:, :k].dot(U[:, :k].T.dot(ycond)) - ycond) ** 2) for k in ks]])
+    p_all, r2_all = _f_pvalues(ssered, ssefull, ks, n, r)
+    k, p, r2 = (a[0] for a in _pick(p_all, r2_all, ks))
+    if k == max(ks):  # :65-67
+        warnings.warn(("data supported use of {} NAM PCs, which is the maximum considered. "
+                       'Consider allowing more PCs by using the "ks" argument.').format(k))
+    beta = U[:, :k].T.dot(ycond)  # :72
+    yhat = U[:, :k].dot(beta)
+    r2_perpc = (beta / np.sqrt(ycond.dot(ycond))) ** 2  # :74
+
+    # ---- permutations: indices on the host (bit-exact RNG), everything else on the device ----
+    if donorids is not None:  # :80-83
+        bix = _stats.grouplevel_permutation_indices(donorids, y, Nnull)
+        if bix is None:
+            raise TypeError("'NoneType' object is not subscriptable")  # what the reference dies with
+    else:
+        bix = _stats.conditional_permutation_indices(batches, Nnull)
+    Kl = min(1000, Nnull) if local_test else 0
+    perm_d = _to_dev(np.ascontiguousarray(bix.T, dtype=np.int32))
+    ld_y = _nam._round_up(max(Kl, 1), 4)
+    ycond_d = torch.zeros((res.x.shape[1], ld_y), dtype=torch.float32, device=dev) if Kl else None
+    ssered_d = torch.empty(Nnull, dtype=torch.float64, device=dev)
+    ssefull_d = torch.empty((Nnull, len(ks)), dtype=torch.float64, device=dev)
+    y_d = _to_dev(y)
+    C_d = _to_dev(res.C) if r else None
+    W_d = _to_dev(np.ascontiguousarray(res.W_last)) if r else None
+    Ut_d = _to_dev(np.ascontiguousarray(U[:, :kmax].T))
+    ks_d = _to_dev(np.asarray(ks, dtype=np.int32))
+    _lib.perm_stats(y_d, perm_d, C_d, W_d, Ut_d, ks_d, ssered_d, ssefull_d, ycond_d, Kl)
+
+    # ---- neighbourhood-level null: launch before the host-side F tests so they overlap ----
+    fdrs, fdr_5p_t, fdr_10p_t = None, None, None
+    if local_test:
+        print("computing neighborhood-level FDRs", file=out)
+        mx = torch.zeros(1, dtype=torch.float64, device=dev)
+        _lib.absmax(res.ncorr, res.valid, mx)
+        maxcorr = max(float(mx.item()), 0.001)  # :101
+        thresholds = np.arange(maxcorr / 4, maxcorr, maxcorr / 400)  # :102
+        edges = _stats.threshold_edges(thresholds)
+        T = len(thresholds)
+        edges_d, thr_d = _to_dev(edges), _to_dev(thresholds)
+        hist = torch.zeros((Kl, T), dtype=torch.int32, device=dev)
+        obs = torch.zeros((2, T), dtype=torch.int32, device=dev)
+        _lib.null_hist(res.x, n, ycond_d, Kl, edges_d, float(edges[0]), hist)
+        _lib.obs_hist(res.ncorr, res.valid, edges_d, thr_d, obs[0], obs[1])
+
+    # ---- global p-value (:84-88) ----
+    nullp, nullr2 = _f_pvalues(ssered_d.cpu().numpy(), ssefull_d.cpu().numpy(), ks, n, r)
+    _, nullminps, nullr2s = _pick(nullp, nullr2, ks)
+    nhit = int((nullminps <= p + 1e-8).sum())
+    pfinal = (nhit + 1) / (Nnull + 1)
+    if nhit == 0:
+        warnings.warn("global association p-value attained minimal possible value. "
+                      "Consider increasing Nnull")
+
+    if local_test:
+        obs_h = obs.cpu().numpy()
+        fdr_vals = _stats.fdr_from_counts(hist.cpu().numpy(), obs_h[0])  # _stats.py:64-83
+        num_detected = _stats.tails_from_hist(obs_h[1].astype(np.int64))  # :105-108
+        fdrs = pd.DataFrame({"threshold": thresholds, "fdr": fdr_vals, "num_detected": num_detected})
+        if not np.min(fdrs.fdr) > 0.05:  # :111-114
+            fdr_5p_t = fdrs[fdrs.fdr <= 0.05].iloc[0].threshold
+        if not np.min(fdrs.fdr) > 0.1:  # :115-118
+            fdr_10p_t = fdrs[fdrs.fdr <= 0.1].iloc[0].threshold
+
+    return Namespace(p=pfinal, nullminps=nullminps, k=k, ncorrs=None, fdrs=fdrs,
+                     fdr_5p_t=fdr_5p_t, fdr_10p_t=fdr_10p_t, yresid_hat=yhat, yresid=ycond,
+                     ks=ks, beta=beta, r2=r2, r2_perpc=r2_perpc,
+                     nullr2_mean=nullr2s.mean(), nullr2_std=nullr2s.std())
+
+
+def association(data, y, sid_name, batches=None, covs=None, donorids=None, ks=None, key_added="coef",
+                max_frac_pcs=0.15, nsteps=None, show_progress=False, allow_low_sample_size=False,
+                return_full=False, ridges=None, **kwargs):
+    """``_association.py:193-242``.  Returns the global p-value, or the full result Namespace when
+    ``return_full``; writes ``data.obs[key_added]`` and ``data.obs[key_added + '_fdr']``."""
+    out = select_output(show_progress)
+    bad = set(kwargs) - {"Nnull", "force_permute_all", "local_test", "seed"}
+    if bad:  # the reference forwards **kwargs to _association(), which rejects anything else
+        raise TypeError(f"_association() got an unexpected keyword argument '{sorted(bad)[0]}'")
+    batches, filter_samples = check_inputs(data, y, sid_name, batches, covs, donorids,
+                                           allow_low_sample_size)
+
+    # ---- NAM (compute_nam_and_reindex, :175-191): diffusion + QC on the device ----
+    print("computing NAM", file=out)
+    stn = _nam._nam_device(data, sid_name, nsteps=nsteps, show_progress=show_progress)
+    _nam._qc_device(stn, batches, show_progress=show_progress)
+
+    fs = np.asarray(filter_samples, dtype=bool)
+    sids = y.index[fs]
+    colmap = stn.labels.get_indexer(sids)  # NAM.reindex(y.index)[filter_samples], :178-181
+    n = int(fs.sum())
+    batches_f = batches.reindex(y.index).to_numpy()[fs]
+    covs_f = covs.reindex(y.index).to_numpy()[fs] if covs is not None else None
+    donor_f = donorids.reindex(y.index).to_numpy()[fs] if donorids is not None else None
+    y_f = np.asarray(y.to_numpy()[fs], dtype=np.float64)
+    y_std = (y_f - y_f.mean()) / y_f.std()  # :22 (ndarray -> ddof=0)
+
+    npcs = min(n, max([10] + [int(max_frac_pcs * n)] + [ks if ks is not None else []][0]))  # :207
+    res = _nam.resid_nam_device(stn, colmap, covs_f, batches_f, y_std, ridges=ridges,
+                                show_progress=show_progress)
+    res.y_std = y_std
+    res.ks = default_ks(n) if ks is None else ks
+    if max(res.ks) + res.r >= n:  # :29-33
+        raise ValueError(
+            "Maximum number of PCs plus number of covariates must be less than n-1. "
+            f"Currently it is {max(res.ks) + res.r} while n is {n}. Either reduce the number of covariates "
+            "or reduce the number of PCs to consider using the optional argument ks=[...].")
+    res.U, svs, res.G = _nam.gram_svd(res.x, n)  # _nam.py:163
+
+    print("performing association test", file=out)
+    core = _association(stn, res, y_f, batches_f, donor_f, ks=ks, show_progress=show_progress, **kwargs)
+
+    # ---- neighbourhood-level outputs (:228-237) ----
+    N = stn.N
+    dev = res.x.device
+    coef_d = torch.empty(N, dtype=torch.float64, device=dev)
+    fdr_d = torch.empty(N, dtype=torch.float64, device=dev)
+    if key_added in data.obs:
+        warnings.warn(f"Key '{key_added}' already exists in data.obs. Overwriting.")
+    if core.fdrs is None:
+        # local_test=False: the reference writes the coefficients and then crashes looking up FDRs
+        # (res.fdrs is None at :235); here the FDR column is simply not written.
+        thr, pmin = np.array([np.inf]), np.array([1.0])
+    else:
+        thr = core.fdrs.threshold.to_numpy()
+        pmin = np.fmin.accumulate(core.fdrs.fdr.to_numpy())  # Series.min() skips NaN
+    _lib.cell_fdr(res.ncorr, res.valid, _to_dev(thr), _to_dev(pmin), coef_d, fdr_d)
+    both = torch.stack([coef_d, fdr_d]).cpu().numpy()
+    data.obs[key_added] = both[0]
+    if core.fdrs is not None:
+        data.obs[f"{key_added}_fdr"] = both[1]
+    if not return_full:
+        return core.p
+
+    # ---- full result surface (_nam.py:168-175, _association.py:223-225) ----
+    kept = res.valid.bool().cpu().numpy()
+    cells = data.obs.index[kept]
+    pcs = ["PC" + str(i) for i in range(1, n + 1)]
+    full = Namespace()
+    full.M = pd.DataFrame(res.M, index=sids, columns=sids)
+    full.r = res.r
+    vmask = res.valid.bool()
+    xk = res.x[vmask][:, :n]
+    full.namresid = pd.DataFrame(xk.t().double().cpu().numpy(), index=sids, columns=cells)
+    full.namresid_sampleXpc = pd.DataFrame(res.U, index=sids, columns=pcs)
+    V = _nam.nbhd_loadings(res.x, n, res.U, svs, rows=vmask)
+    full.namresid_nbhdXpc = pd.DataFrame(V, index=cells, columns=pcs)
+    full.namresid_svs = pd.Series(svs, index=pcs)[:npcs]
+    full.namresid_varexp = pd.Series(svs / n / len(cells), index=pcs)
+    full.__dict__.update(vars(core))
+    full.ncorrs = pd.Series(both[0][kept], index=cells)
+    full.yresid = pd.Series(core.yresid, index=sids)
+    cm = torch.as_tensor(colmap, device=dev, dtype=torch.long)
+    nam_sel = (stn.s[vmask][:, cm].double() * stn.inv_count[cm])
+    full.nam = pd.DataFrame(nam_sel.t().cpu().numpy(), index=sids, columns=cells)
+    full.kept = kept
+    return full

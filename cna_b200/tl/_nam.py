@@ -1,0 +1,350 @@
+"""NAM construction, QC, residualisation and SVD — host side of kernels (i), (ii), (iii).
+
+Mirrors ``src/cna/tools/_nam.py`` of the reference (same public names, arguments, defaults and
+return types) with the arithmetic running on the GPU through the C-ABI in ``include/cna_b200.h``.
+The device state is CELLS x SAMPLES (the transpose of the reference's DataFrames) in fp32.
+"""
+from argparse import Namespace
+
+import numpy as np
+import pandas as pd
+import torch
+
+from .. import _lib
+from ._graph import get_connectivity, graph_of, sample_codes, device, _to_dev  # noqa: F401
+from ._out import select_output
+
+DEFAULT_RIDGES = [1e5, 1e4, 1e3, 1e2, 1e1, 1e0, 1e-1, 1e-2, 1e-3, 1e-4, 0]
+
+
+def _round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+def device_median(t):
+    """``np.median`` of a 1-D device tensor: mean of the two middle order statistics, NaN if any
+    element is NaN.  One device sort and one 24-byte copy back."""
+    n = t.numel()
+    if n == 0:
+        return float("nan")
+    v, _ = torch.sort(t)  # NaNs sort last
+    lo, hi, last = torch.stack([v[(n - 1) // 2], v[n // 2], v[-1]]).tolist()
+    if last != last:
+        return float("nan")
+    return (lo + hi) / 2
+
+
+# ---------------------------------------------------------------------------------------------
+# diffusion
+# ---------------------------------------------------------------------------------------------
+def diffuse_stepwise(data, s, maxnsteps=15, show_progress=False, self_weight=1):
+    """``_nam.py:21-34``.  Generator over the state after each step.  ``s`` may be a numpy array or
+    DataFrame (cells x k, float64 arithmetic on the GPU, numpy arrays are yielded) or a CUDA tensor
+    (float32 or float64, CUDA tensors are yielded)."""
+    out = select_output(show_progress)
+    g = graph_of(data)
+    on_device = torch.is_tensor(s)
+    if on_device:
+        cur = s if s.is_cuda else s.to(device())
+        dtype = cur.dtype if cur.dtype in (torch.float32, torch.float64) else torch.float64
+        cur = cur.to(dtype)
+    else:
+        frame = s if isinstance(s, pd.DataFrame) else None
+        arr = np.asarray(s, dtype=np.float64)
+        cur = _to_dev(arr)
+        dtype = torch.float64
+    if cur.dim() != 2 or cur.shape[0] != g.n:
+        raise ValueError("s must be a 2-D array with one row per cell")  # colsums[:,None] needs 2-D
+    cur = cur.contiguous()
+    vals, diag = g.scaled(self_weight, dtype)
+    for i in range(maxnsteps):
+        print("\ttaking step", i + 1, file=out)
+        nxt = torch.empty_like(cur)
+        _lib.diffuse_step(g.indptr, g.indices, vals, diag, cur, nxt, cur.shape[1])
+        cur = nxt
+        if on_device:
+            yield cur
+        else:
+            res = cur.cpu().numpy()
+            yield pd.DataFrame(res, index=frame.index, columns=frame.columns) if frame is not None else res
+
+
+def diffuse(data, s, nsteps, show_progress=False, self_weight=1):
+    """``_nam.py:36-41``."""
+    for s in diffuse_stepwise(data, s, maxnsteps=nsteps, show_progress=show_progress,
+                              self_weight=self_weight):
+        pass
+    return s
+
+
+class NamState:
+    """Device-resident raw NAM: ``s`` [N x ld] fp32 (un-normalised diffusion state), the per-sample
+    scaling 1/C (``_nam.py:73``), sample labels, the QC keep mask and step diagnostics."""
+
+    def __init__(self, s, n_samples, labels, counts, cell_index):
+        self.s = s
+        self.S = n_samples
+        self.labels = labels
+        self.counts = counts
+        with np.errstate(divide="ignore"):
+            self.inv_count = _to_dev(1.0 / counts)
+        self.cell_index = cell_index
+        self.keep = None  # None = all cells kept
+        self.qc_threshold = None
+        self.medkurt = []
+        self.nsteps = 0
+
+    @property
+    def N(self):
+        return self.s.shape[0]
+
+
+def _r2_p20(s, old, S):
+    # print-only diagnostic of _nam.py:47-49,60,63 (runs only under show_progress)
+    a, b = s[:, :S].double(), old[:, :S].double()
+    r = ((a - a.mean(0)) * (b - b.mean(0))).mean(0) / a.std(0, unbiased=False) / b.std(0, unbiased=False)
+    r2 = (r ** 2).cpu().numpy()
+    return np.percentile(r2, 20)
+
+
+def _nam_device(data, sid_name, nsteps=None, maxnsteps=15, self_weight=1, show_progress=False):
+    """``_nam.py:44-76`` on the device.  The first step never materialises the one-hot matrix."""
+    out = select_output(show_progress)
+    g = graph_of(data)
+    labels, codes, counts = sample_codes(data, sid_name)
+    if codes.numel() != g.n:
+        raise ValueError("data.obs and the connectivities graph disagree on the number of cells")
+    S = len(labels)
+    ld = _round_up(S, 8)
+    dev = codes.device
+    vals, diag = g.scaled(self_weight, torch.float32)
+    cur = torch.empty((g.n, ld), dtype=torch.float32, device=dev)
+    nxt = torch.zeros((g.n, ld), dtype=torch.float32, device=dev)
+    st = NamState(cur, S, labels, counts, data.obs.index)
+    need_stats = nsteps is None or show_progress
+    kurt = torch.empty(g.n, dtype=torch.float64, device=dev) if need_stats else None
+    old = None
+    prevmedkurt = np.inf
+    i = 0
+    for i in range(maxnsteps):
+        print("\ttaking step", i + 1, file=out)
+        if i == 0:
+            _lib.diffuse_onehot(g.indptr, g.indices, vals, diag, codes, S, cur)
+        else:
+            if show_progress:
+                old = cur.clone()
+            _lib.diffuse_step(g.indptr, g.indices, vals, diag, cur, nxt, S)
+            cur, nxt = nxt, cur
+        if need_stats:
+            _lib.row_kurtosis(cur, S, st.inv_count, kurt)
+            medkurt = device_median(kurt)  # _nam.py:59
+            st.medkurt.append(medkurt + 3)
+            print("\tmedian kurtosis:", medkurt + 3, file=out)
+            if show_progress:
+                r2 = _r2_p20(cur, old, S) if old is not None else float("nan")
+                print("\t20th percentile R2(t,t-1):", r2, file=out)
+        if nsteps is None:
+            if prevmedkurt - medkurt < 3 and i + 1 >= 3:  # _nam.py:65
+                print("stopping after", i + 1, "steps", file=out)
+                break
+            prevmedkurt = medkurt
+        elif i + 1 == nsteps:  # _nam.py:69
+            break
+    st.s = cur
+    st.nsteps = i + 1
+    return st
+
+
+def _batch_segments(batch_values):
+    """Group positions 0..len-1 by batch value (sorted unique order, like ``np.unique`` at
+    ``_nam.py:81``).  Returns (unique values, order int32, offsets int32)."""
+    b = np.asarray(batch_values)
+    ub, inv = np.unique(b, return_inverse=True)
+    order = np.argsort(inv, kind="stable").astype(np.int32)
+    off = np.zeros(len(ub) + 1, dtype=np.int32)
+    np.cumsum(np.bincount(inv, minlength=len(ub)), out=off[1:])
+    return ub, order, off
+
+
+def _qc_device(st, batches, show_progress=False):
+    """``_nam.py:85-99``.  Sets ``st.keep`` (uint8 device mask, or None when every cell is kept)."""
+    out = select_output(show_progress)
+    if len(np.unique(batches)) == 1:  # _nam.py:89
+        st.keep = None
+        return
+    b = batches.reindex(st.labels)  # _nam.py:79
+    ub, order, off = _batch_segments(b.to_numpy())
+    dev = st.s.device
+    kurt = torch.empty(st.N, dtype=torch.float64, device=dev)
+    _lib.batch_kurtosis(st.s, st.inv_count, _to_dev(order), _to_dev(off), kurt)
+    med = device_median(kurt)
+    threshold = max(6, 2 * med)  # _nam.py:94 (python max: a NaN median gives 6)
+    print("throwing out neighborhoods with batch kurtosis >=", threshold, file=out)
+    keep = kurt < threshold  # NaN -> dropped, _nam.py:96
+    print("keeping", int(keep.sum()), "neighborhoods", file=out)
+    st.keep = keep.to(torch.uint8)
+    st.qc_threshold = threshold
+
+
+def nam(data, sid_name, batches=None, nsteps=None, self_weight=1, max_frac_pcs=0.15, suffix="",
+        ks=None, show_progress=False, **kwargs):
+    """``_nam.py:179-193``.  Returns (DataFrame samples x kept cells float64, keep mask bool[N])."""
+    out = select_output(show_progress)
+    if batches is None:  # _nam.py:185-186
+        u = data.obs[sid_name].unique()
+        batches = pd.Series(np.ones(len(u)), index=u)
+    print("computing NAM", file=out)
+    st = _nam_device(data, sid_name, nsteps=nsteps, self_weight=self_weight, show_progress=show_progress)
+    _qc_device(st, batches, show_progress=show_progress)
+    return nam_frame(st, sid_name), keep_mask(st)
+
+
+def keep_mask(st):
+    if st.keep is None:
+        return np.repeat(True, st.N)
+    return st.keep.bool().cpu().numpy()
+
+
+def nam_frame(st, sid_name, rows=None, cols=None):
+    """Materialise (a part of) the QC'd NAM as the reference's samples x cells DataFrame."""
+    x = st.s[:, :st.S].double() * st.inv_count  # _nam.py:73
+    keep = keep_mask(st)
+    if st.keep is not None:
+        x = x[st.keep.bool()]
+    arr = x.t().contiguous().cpu().numpy()
+    df = pd.DataFrame(arr, index=st.labels, columns=st.cell_index[keep], dtype=float)
+    df.index.name = sid_name  # _nam.py:74
+    return df
+
+
+# ---------------------------------------------------------------------------------------------
+# SVD of a NAM given on the host (public helper)
+# ---------------------------------------------------------------------------------------------
+def svd_nam(NAM):
+    """``_nam.py:102-115``.  ``NAM`` is the reference's samples x cells DataFrame; the centring /
+    standardisation and the Gram contraction run on the GPU, the n x n SVD on the host."""
+    idx, cols = NAM.index, NAM.columns
+    x64 = _to_dev(NAM.to_numpy(dtype=np.float64)).t().contiguous()  # cells x samples
+    n = x64.shape[1]
+    x64 = x64 - x64.mean(dim=1, keepdim=True)  # :103
+    x64 = x64 / x64.std(dim=1, unbiased=True, keepdim=True)  # :104 pandas ddof=1
+    ld = _round_up(n, 8)
+    x = torch.zeros((x64.shape[0], ld), dtype=torch.float32, device=x64.device)
+    x[:, :n] = x64
+    del x64
+    U, svs, _ = gram_svd(x, n)
+    pcs = ["PC" + str(i) for i in range(1, n + 1)]
+    V = nbhd_loadings(x, n, U, svs)
+    return (pd.DataFrame(U, index=idx, columns=pcs), pd.Series(svs, index=pcs),
+            pd.DataFrame(V, index=cols, columns=pcs))
+
+
+def gram_svd(x, n):
+    """``_nam.py:105``: U, svs, _ = svd(NAM.NAM^T) with the Gram matrix contracted on the GPU."""
+    G = torch.zeros((n, n), dtype=torch.float64, device=x.device)
+    _lib.gram(x, n, G)
+    Gh = G.cpu().numpy()
+    Gh = (Gh + Gh.T) / 2  # the kernel fills both triangles from the same products; keep it exact
+    U, svs, _ = np.linalg.svd(Gh)
+    return U, svs, Gh
+
+
+def nbhd_loadings(x, n, U, svs, rows=None):
+    """``_nam.py:106``: V = NAM^T U / sqrt(svs) (cells x n).  The trailing ~null-space columns divide
+    by ~0 exactly like the reference."""
+    with np.errstate(divide="ignore", invalid="ignore"):
+        B = U / np.sqrt(svs)
+    ldb = _round_up(n, 4)
+    b = np.zeros((x.shape[1], ldb), dtype=np.float32)
+    b[:n, :n] = np.nan_to_num(B, nan=0.0, posinf=3e38, neginf=-3e38)
+    out = torch.empty((x.shape[0], ldb), dtype=torch.float32, device=x.device)
+    _lib.right_multiply(x, n, _to_dev(b), n, out)
+    V = out[:, :n]
+    if rows is not None:
+        V = V[rows]
+    return V.double().cpu().numpy()
+
+
+# ---------------------------------------------------------------------------------------------
+# residualisation (host part: the small design-matrix algebra)
+# ---------------------------------------------------------------------------------------------
+def design_matrix(covs, batches, n):
+    """``_nam.py:123-139``.  Returns (C [n x r] float64, number of batch columns).  pandas ``.std``
+    is ddof=1."""
+    if covs is None:
+        cov = np.ones((n, 0))
+    else:
+        cov = np.asarray(covs, dtype=np.float64).reshape(n, -1)
+        cov = (cov - cov.mean(axis=0)) / cov.std(axis=0, ddof=1)  # :126
+    if batches is None or len(np.unique(batches)) == 1:  # :128
+        return cov, 0
+    ub = np.unique(batches)  # get_dummies column order, :137
+    B = (np.asarray(batches)[:, None] == ub[None, :]).astype(np.float64)
+    B = (B - B.mean(axis=0)) / B.std(axis=0, ddof=1)  # :138
+    return np.concatenate([B, cov], axis=1), B.shape[1]
+
+
+def projector(C, nb, ridge):
+    """``_nam.py:145-146`` (or ``:133`` when there are no batch columns): W [r x n], M = I - C.W."""
+    n, r = C.shape
+    CtC = C.T.dot(C)
+    if nb > 0:
+        L = np.diag([1.0] * nb + [0.0] * (r - nb))
+        CtC = CtC + ridge * n * L
+    return np.linalg.solve(CtC, C.T)
+
+
+def resid_nam_device(st, colmap, covs, batches, y_std, ridges=None, show_progress=False):
+    """``_nam.py:118-177`` + ``_association.py:178-185`` + ``:77`` on the device.
+
+    colmap : int array, state column of each of the n selected samples (phenotype order)
+    covs   : [n x c] array or None;  batches : length-n array;  y_std : standardised phenotype.
+    Returns a Namespace with the device tensors ``x`` [N x ld] (rows of dropped cells are zero),
+    ``ncorr`` [N], ``valid`` [N] and the host matrices M, C, W_last, W_cum, r, ridge log."""
+    out = select_output(show_progress)
+    n = len(colmap)
+    dev = st.s.device
+    C, nb = design_matrix(covs, batches, n)
+    r = C.shape[1]
+    ld = _round_up(n, 8)
+    x = torch.empty((st.N, ld), dtype=torch.float32, device=dev)
+    ncorr = torch.empty(st.N, dtype=torch.float64, device=dev)
+    valid = torch.empty(st.N, dtype=torch.uint8, device=dev)
+    colmap_d = _to_dev(np.asarray(colmap, dtype=np.int32))
+    y_d = _to_dev(np.asarray(y_std, dtype=np.float64))
+    res = Namespace(x=x, ncorr=ncorr, valid=valid, n=n, r=r, C=C, ridge_log=[])
+
+    def run(Wcum, seg=None, kurt=None):
+        C_d = _to_dev(C) if r else None
+        W_d = _to_dev(np.ascontiguousarray(Wcum)) if r else None
+        _lib.resid_pass(st.s, st.inv_count, colmap_d, st.keep, C_d, W_d,
+                        seg[0] if seg else None, seg[1] if seg else None, y_d, x, kurt, ncorr, valid)
+
+    if nb == 0:
+        if r > 0:  # _nam.py:133
+            W = projector(C, 0, 0.0)
+            res.M = np.eye(n) - C.dot(W)
+        else:  # :131
+            W = np.zeros((0, n))
+            res.M = np.eye(n)
+        res.W_last = W
+        run(W)
+    else:
+        _, order, off = _batch_segments(batches)
+        seg = (_to_dev(order), _to_dev(off))
+        kurt = torch.empty(st.N, dtype=torch.float64, device=dev)
+        Wcum = np.zeros((r, n))
+        for ridge in (DEFAULT_RIDGES if ridges is None else ridges):  # :141-144
+            W = projector(C, nb, ridge)
+            # the reference applies M = I - C.W cumulatively (:148); the product of such
+            # projectors is again I - C.W' with W' = W_prev + W - (W C) W_prev
+            Wcum = Wcum + W - W.dot(C).dot(Wcum)
+            run(Wcum, seg, kurt)
+            med = device_median(kurt[valid.bool()])  # :150-155
+            res.ridge_log.append((ridge, med))
+            print("\twith ridge", ridge, "median batch kurtosis = ", med, file=out)
+            if med <= 6:
+                break
+        res.W_last = W
+        res.M = np.eye(n) - C.dot(W)  # only the last M survives (:169)
+    return res

@@ -1,0 +1,67 @@
+"""Permutation generators and empirical-FDR bookkeeping — host side.
+
+Mirrors ``src/cna/tools/_stats.py`` of the reference.  Permutation *indices* are drawn on the host
+with exactly the reference's sequence of legacy numpy RNG calls (``np.random.randn`` +
+``np.argsort(axis=0)``), because the legacy MT19937 / polar-Gaussian stream cannot be reproduced by a
+device generator and the permutations must be bit-identical.  The gather ``Y[bix]`` and everything
+after it happen on the device (``cna_perm_stats``).
+"""
+import numpy as np
+
+
+def conditional_permutation_indices(B, num):
+    """``_stats.py:4-16``: permutation index matrix (n x num) of samples within batches.  Consumes the
+    global numpy RNG exactly like the reference: one ``randn(len(batch), num)`` block per batch, in
+    sorted batch order."""
+    B = np.asarray(B)
+    batchind = [np.where(B == b)[0] for b in np.unique(B)]
+    ix = np.concatenate([bi[np.argsort(np.random.randn(len(bi), num), axis=0)] for bi in batchind])
+    bix = np.zeros((len(B), num), dtype=np.int64)
+    bix[np.concatenate(batchind)] = ix
+    return bix
+
+
+def conditional_permutation(B, Y, num):
+    """``_stats.py:4-18``."""
+    return np.asarray(Y)[conditional_permutation_indices(B, num)]
+
+
+def grouplevel_permutation_indices(G, Y, num):
+    """``_stats.py:20-32`` as sample indices: entry (m, k) is a sample whose phenotype equals the
+    value donor-permutation k assigns to sample m.  Returns None (after printing the reference's
+    message) when Y is not constant within a donor."""
+    G = np.asarray(G)
+    Y = np.asarray(Y)
+    Gu = np.unique(G)
+    rep = np.array([np.where(G == g)[0][0] for g in Gu])  # first sample of each donor
+    Yg = Y[rep]
+    Gind = np.searchsorted(Gu, G)
+    if (Yg[Gind] != Y).any():
+        print("ERROR: the value of Y is not identical within each group of samples")
+        return None
+    ix = np.argsort(np.random.randn(len(Yg), num), axis=0)
+    return rep[ix][Gind]
+
+
+def grouplevel_permutation(G, Y, num):
+    ix = grouplevel_permutation_indices(G, Y, num)
+    return None if ix is None else np.asarray(Y)[ix]
+
+
+def threshold_edges(t, atol=1e-8, rtol=1e-5):
+    """``_stats.py:51``: histogram edges for ascending thresholds t: t^2 - atol - rtol * t^2."""
+    t2 = np.asarray(t, dtype=np.float64) ** 2
+    return t2 - atol - rtol * t2
+
+
+def tails_from_hist(hist):
+    """``_stats.py:57-59``: reverse cumulative sum, tails[k, i] = #{cells: z^2 >= edge_i}."""
+    return np.flip(np.cumsum(np.flip(hist, axis=-1), axis=-1), axis=-1)
+
+
+def fdr_from_counts(null_hist, rank_hist):
+    """``_stats.py:64-83`` from binned counts: fdr_i = mean_k(tails[k, i] / ranks[i])."""
+    tails = tails_from_hist(np.asarray(null_hist, dtype=np.int64))
+    ranks = tails_from_hist(np.asarray(rank_hist, dtype=np.int64))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return (tails / ranks).mean(axis=0)

@@ -1,0 +1,205 @@
+/*
+ * cna_b200 — C-ABI of the B200-native CNA hot path (NAM construction + permutation association).
+ *
+ * The reference (immunogenomics/cna v0.2.3) is pure Python: it has no FFI of its own, its hot
+ * arithmetic lives in scipy/numpy/OpenBLAS calls made from src/cna/tools/_nam.py,
+ * _association.py and _stats.py.  Each entry point below replaces one of those call sites; the
+ * citation after "replaces:" is the reference file:line whose arithmetic the kernel reproduces.
+ * INTEGRATION.md shows the ctypes stub a reference maintainer would add at each site.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer (cudaMalloc / torch storage) unless its name ends in _h;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); every launch is
+ *     asynchronous on that stream, no entry point synchronises unless documented;
+ *   - matrices are row-major with an explicit leading dimension `ld*` counted in elements;
+ *   - the diffusion state / NAM is CELLS x SAMPLES (the transpose of the reference's DataFrames),
+ *     fp32, leading dimension a multiple of 8 floats (32-byte sectors), padding columns zero;
+ *   - return value 0 = success, otherwise an error code; cna_last_error() returns the message of
+ *     the last failing call on the calling thread.
+ */
+#ifndef CNA_B200_H
+#define CNA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CNA_B200_ABI_VERSION 1
+
+enum {
+    CNA_OK = 0,
+    CNA_ERR_INVALID = 1,  /* bad argument (shape, alignment, unsupported size) */
+    CNA_ERR_CUDA = 2      /* a CUDA runtime call or kernel launch failed */
+};
+
+int cna_abi_version(void);
+const char *cna_last_error(void);
+/* number of kernels launched by this library since load (bench.py reports it as gpu_launches) */
+int64_t cna_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * kernel (i): random-walk diffusion over the kNN graph
+ * ------------------------------------------------------------------------------------------ */
+
+/* Column sums of the CSR adjacency.  replaces: _nam.py:28 `a.sum(axis=0)`.
+ * colsum[n_rows] (fp64) must be zeroed by the caller; data is fp64 (is_f64 != 0) or fp32. */
+int cna_graph_colsum(const int32_t *indptr, const int32_t *indices, const void *data, int is_f64,
+                     int64_t n_rows, double *colsum, void *stream);
+
+/* Fold the input-side normalisation into the edges: vals[e] = A[i,j] / (colsum[j] + w),
+ * diag[i] = w / (colsum[i] + w).  replaces: _nam.py:28,33 `s/colsums[:,None]`, `self_weight*s/colsums`.
+ * out_f64 selects double outputs (used by cna.tl.diffuse on user vectors) or float. */
+int cna_graph_scale(const int32_t *indptr, const int32_t *indices, const void *data, int is_f64,
+                    int64_t n_rows, const double *colsum, double self_weight, void *vals,
+                    void *diag, int out_f64, void *stream);
+
+/* First diffusion step when the state is the one-hot sample indicator (never materialised):
+ * out[i, c] = sum_{j: code[j]=c} vals[i,j] + diag[i]*[code[i]=c].
+ * replaces: _nam.py:51 `pd.get_dummies` + the first iteration of _nam.py:33. */
+int cna_diffuse_onehot(const int32_t *indptr, const int32_t *indices, const float *vals,
+                       const float *diag, const int32_t *code, int64_t n_rows, int n_samples,
+                       float *out, int64_t ld, void *stream);
+
+/* One diffusion step on a dense fp32 state: out = A'.in + diag*in  (CSR SpMM).
+ * replaces: _nam.py:33 `a.dot(s/colsums[:,None]) + self_weight*s/colsums[:,None]`
+ * (scipy _sparsetools.csr_matvecs).  n_cols <= ld, ld % 4 == 0, in != out. */
+int cna_diffuse_step_f32(const int32_t *indptr, const int32_t *indices, const float *vals,
+                         const float *diag, const float *in, float *out, int64_t n_rows,
+                         int n_cols, int64_t ld, void *stream);
+
+/* Same, fp64 state with any number of columns (cna.tl.diffuse / diffuse_stepwise on user input). */
+int cna_diffuse_step_f64(const int32_t *indptr, const int32_t *indices, const double *vals,
+                         const double *diag, const double *in, double *out, int64_t n_rows,
+                         int n_cols, int64_t ld, void *stream);
+
+/* Per-cell excess kurtosis (biased, Fisher) across samples of s[i,:]*inv_count[:].
+ * replaces: _nam.py:59 `st.kurtosis(s/C, axis=1)`.  kurt[n_rows] fp64 (NaN where scipy gives NaN). */
+int cna_row_kurtosis(const float *s, int64_t ld, int64_t n_rows, int n_samples,
+                     const double *inv_count, double *kurt, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * kernel (ii): QC, sample selection, residualisation, standardisation — one HBM pass
+ * ------------------------------------------------------------------------------------------ */
+
+/* Per-cell Pearson kurtosis across the per-batch means of s[i,:]*inv_count[:].
+ * replaces: _nam.py:78-82 `_batch_kurtosis` inside `_qc_nam` (_nam.py:85-99).
+ * Samples are grouped by batch through seg_order[n_sel] (column ids into the state, grouped so
+ * that batch b owns seg_order[seg_off[b]..seg_off[b+1])), seg_off[n_batches] = n_sel; n_batches >= 2. */
+int cna_batch_kurtosis(const float *s, int64_t ld, int64_t n_rows, const double *inv_count,
+                       const int32_t *seg_order, const int32_t *seg_off, int n_batches, int n_sel,
+                       double *kurt, void *stream);
+
+typedef struct cna_resid_args {
+    /* input state (cells x all samples) and its per-sample scaling 1/C_n (_nam.py:73) */
+    const float *s;
+    int64_t ld_s;
+    int64_t n_rows;
+    const double *inv_count;
+    /* sample selection in phenotype order (_association.py:178-181): column ids, length n */
+    const int32_t *colmap;
+    int n;
+    /* QC keep mask from cna_batch_kurtosis + threshold (_nam.py:96), may be NULL (keep all) */
+    const uint8_t *row_keep;
+    /* residualisation (_nam.py:128-156): X <- X - (X Wt^T) C^T with C [n x r], Wt [r x n]; r may be 0 */
+    const double *C;
+    const double *Wt;
+    int r;
+    /* batches of the selected samples for the ridge stopping rule (_nam.py:150-155):
+     * positions 0..n-1 grouped by batch; n_batches <= 1 disables the kurtosis output */
+    const int32_t *seg_order;
+    const int32_t *seg_off;
+    int n_batches;
+    /* standardised phenotype (ddof=0, _association.py:22), length n */
+    const double *y;
+    /* outputs */
+    float *x_out;        /* [n_rows x ld_x] residualised + standardised NAM (_nam.py:159), zero rows for dropped cells */
+    int64_t ld_x;
+    double *kurt;        /* [n_rows] batch kurtosis after residualisation (NaN for dropped cells), may be NULL */
+    double *ncorr;       /* [n_rows] neighbourhood coefficients (_association.py:77), 0 for dropped cells */
+    uint8_t *row_valid;  /* [n_rows] row_keep && variance > 0 (_association.py:182-185) */
+} cna_resid_args;
+
+/* replaces: _association.py:178-185 (reindex, filter, zero-variance drop), _nam.py:122 (centre),
+ * :128-156 (M.NAM as a rank-r update), :159 (ddof=1 standardise), _association.py:77 (ncorrs). */
+int cna_resid_pass(const cna_resid_args *args, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * kernel (iii): Gram matrix of the standardised NAM
+ * ------------------------------------------------------------------------------------------ */
+
+/* gram[n x n] (fp64, row-major, zeroed by the caller) += X^T X for X [n_rows x ld_x] fp32.
+ * replaces: _nam.py:105 `NAM.dot(NAM.T)` (OpenBLAS dgemm).  Only ld_x % 4 == 0 and columns >= n
+ * being zero padding are required. */
+int cna_gram(const float *x, int64_t ld_x, int64_t n_rows, int n, double *gram, void *stream);
+/* the fp32 CUDA-core implementation of the same contract (cross-check for the tensor-core kernel) */
+int cna_gram_simt(const float *x, int64_t ld_x, int64_t n_rows, int n, double *gram, void *stream);
+
+/* out[n_rows x ld_out] (fp32) = X . B for B [ld_x x ld_b] fp32 (rows >= n zero).
+ * replaces: _nam.py:106 `NAM.T.dot(U) / sqrt(svs)` (the caller pre-divides U's columns). */
+int cna_right_multiply(const float *x, int64_t ld_x, int64_t n_rows, int n, const float *b,
+                       int64_t ld_b, int n_out, float *out, int64_t ld_out, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * permutation engine
+ * ------------------------------------------------------------------------------------------ */
+
+/* For every permutation k (one warp each): z = y[perm[k,:]], zc = (I - C.W) z, zc /= std_ddof1(zc),
+ * ssered[k] = |zc|^2, beta = Ut[:kmax] zc, ssefull[k, a] = |zc - U[:, :ks[a]] beta[:ks[a]]|^2.
+ * The first n_local conditioned phenotypes are also written as fp32 columns of ycond
+ * [ld_x rows x ld_y] for the neighbourhood-level null (_association.py:94-97).
+ * replaces: _stats.py:18 `Y[bix]`, _association.py:35-61 (`_reg`, `_stats`, `_minp_stats` up to the
+ * F statistic) evaluated in a Python loop at _association.py:84.
+ *   perm  [K x n] int32 (row k = sample indices of permutation k)
+ *   C [n x r], W [r x n] (last ridge stage only, _nam.py:169), Ut [kmax x n], ks [nks] ascending. */
+int cna_perm_stats(const double *y, const int32_t *perm, int64_t K, int n, const double *C,
+                   const double *W, int r, const double *Ut, int kmax, const int32_t *ks, int nks,
+                   double *ssered, double *ssefull, float *ycond, int64_t ld_y, int n_local,
+                   void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * neighbourhood-level null: GEMM with a threshold-histogram epilogue
+ * ------------------------------------------------------------------------------------------ */
+
+/* hist[k, b] (uint32, [n_null x n_edges], zeroed by caller) += #{cells i : edges[b] <= z_ik^2 <
+ * edges[b+1]} with z = X.ycond/n, last bin closed at +inf, values below edges[0] dropped.
+ * replaces: _association.py:99 `abs(NAMresid.T.dot(ycond_)/n)` + _stats.py:52-54 `np.histogram`
+ * per null column (the N x Nnull matrix is never materialised).  `edge0` is the host copy of
+ * edges[0] (lets the kernel reject sub-threshold products without touching the edge table). */
+int cna_null_hist(const float *x, int64_t ld_x, int64_t n_rows, int n, const float *ycond,
+                  int64_t ld_y, int n_null, const double *edges, int n_edges, double edge0,
+                  uint32_t *hist, void *stream);
+
+/* Histograms of the observed coefficients against the same edges and the strict thresholds:
+ * rank_hist[b] += #{i valid: edges[b] <= ncorr_i^2 < edges[b+1]} (last bin closed),
+ * det_hist[b]  += #{i valid: thresholds[b] < |ncorr_i| <= thresholds[b+1]} (last bin open above),
+ * maxabs[0] = max |ncorr_i| must be computed first with cna_absmax.
+ * replaces: _stats.py:73 (tail_counts of the observed z), _association.py:105-108. */
+int cna_obs_hist(const double *ncorr, const uint8_t *row_valid, int64_t n_rows, const double *edges,
+                 const double *thresholds, int n_edges, uint32_t *rank_hist, uint32_t *det_hist,
+                 void *stream);
+
+/* out[0] = max_i |v_i| over valid rows (0 if none).  replaces: _association.py:101. out zeroed by caller. */
+int cna_absmax(const double *v, const uint8_t *row_valid, int64_t n_rows, double *out, void *stream);
+
+/* Per-cell FDR: coef[i] = ncorr[i] (NaN for dropped cells); fdr[i] = prefix_min_fdr[idx-1] with
+ * idx = #{thresholds <= |ncorr_i|}, or 1 when idx == 0 or the cell was dropped.
+ * replaces: _association.py:228-237 (the per-cell `Series.apply(min_fdr_for_corr)`). */
+int cna_cell_fdr(const double *ncorr, const uint8_t *row_valid, int64_t n_rows,
+                 const double *thresholds, const double *prefix_min_fdr, int n_thr, double *coef,
+                 double *fdr, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * utilities used by the data generator (not on the timed path)
+ * ------------------------------------------------------------------------------------------ */
+
+/* Exact brute-force k nearest neighbours (self excluded) of fp32 points [n x dim], dim <= 32,
+ * k <= 64.  idx [n x k] int32 ascending by distance, dist2 [n x k] squared distances. */
+int cna_knn_bruteforce(const float *points, int64_t n, int dim, int k, int32_t *idx, float *dist2,
+                       void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CNA_B200_H */

@@ -1,0 +1,368 @@
+"""GPU parity: the CUDA path (through the C-ABI / public ``cna_b200.tl`` surface) against
+(a) the committed outputs of the unmodified reference (tests/golden) and (b) the CPU oracle on
+seeded inputs.  Integer / index outputs must be exact; floating-point outputs within the
+north-star tolerance of 1e-5 relative (the device state is fp32, the reference fp64).
+"""
+import numpy as np
+import pandas as pd
+import pytest
+import scipy.sparse as sp
+
+from tests import helpers
+from tests.golden import cases
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5  # BASELINE.json north_star: singular values, coefficients, p within 1e-5 relative
+
+
+@pytest.fixture(scope="module")
+def cna():
+    import cna_b200
+    from cna_b200 import _lib
+    _lib.load()
+    return cna_b200
+
+
+@pytest.fixture(scope="module")
+def demo():
+    return helpers.load_golden("demo_cases")
+
+
+@pytest.fixture(scope="module")
+def synth():
+    return helpers.load_golden("synth_cases")
+
+
+def test_library_loaded_and_counts_launches(cna):
+    import torch
+    from cna_b200 import _lib
+    before = _lib.launch_count()
+    out = torch.zeros(1, dtype=torch.float64, device="cuda")
+    _lib.absmax(torch.tensor([1.0, -3.0, 2.0], dtype=torch.float64, device="cuda"), None, out)
+    assert out.item() == 3.0
+    assert _lib.launch_count() == before + 1
+
+
+@pytest.mark.parametrize("name", list(cases.DEMO_CASES))
+def test_demo_cases_match_reference(cna, demo, name):
+    arrays, scalars = demo
+    spec = cases.DEMO_CASES[name]
+    data, kwargs = cases.build_demo_case(cases.load_demo_graph(), spec)
+    res, warns = helpers.run_association(cna.tl.association, data, kwargs, spec.get("np_seed"))
+    helpers.assert_matches_golden(res, data, kwargs.get("key_added", "coef"), arrays, scalars, name,
+                                  warns=warns, rtol=RTOL, atol=1e-9)
+
+
+@pytest.mark.parametrize("name", list(cases.SYNTH_CASES))
+def test_synth_cases_match_reference(cna, synth, name):
+    arrays, scalars = synth
+    spec = cases.SYNTH_CASES[name]
+    data, kwargs = cases.build_synth_case(spec, helpers.synth_raw(arrays, name))
+    res, warns = helpers.run_association(cna.tl.association, data, kwargs)
+    helpers.assert_matches_golden(res, data, "coef", arrays, scalars, name, warns=warns, rtol=RTOL,
+                                  atol=1e-9)
+
+
+def test_notebook_numbers(cna):
+    """demo/demo.ipynb cell 10: p = 0.000999000999000999 and 9555 neighbourhoods at FDR 5 %."""
+    data, kwargs = cases.build_demo_case(cases.load_demo_graph(), cases.DEMO_CASES["case_male_batch"])
+    np.random.seed(0)
+    with pytest.warns(UserWarning, match="minimal possible value"):
+        p = cna.tl.association(data, **kwargs)
+    assert p == 0.000999000999000999
+    assert int((data.obs["case_coef_fdr"] <= 0.05).sum()) == 9555
+    # resident graph handle: same numbers, no re-upload
+    data2, kwargs2 = cases.build_demo_case(cases.load_demo_graph(), cases.DEMO_CASES["male_case_batch"])
+    h = cna.tl.to_device(data2)
+    np.random.seed(0)
+    with pytest.warns(UserWarning):
+        p2 = cna.tl.association(h, **kwargs2)
+    assert p2 == 0.000999000999000999
+    assert int((data2.obs["male_coef_fdr"] <= 0.05).sum()) == 4509
+
+
+def test_nam_svd_diffuse_match_reference(cna, demo):
+    arrays, _ = demo
+    data = cases.demo_anndata()
+    meta = cases.demo_sample_meta()
+    NAM, keep = cna.tl.nam(data, "id", batches=meta.batch)
+    assert NAM.shape == (50, 10000) and NAM.index.name == "id"
+    np.testing.assert_array_equal(keep, arrays["nam/keep"])
+    np.testing.assert_allclose(NAM.to_numpy()[:, :256], arrays["nam/NAM_head"], rtol=RTOL, atol=1e-10)
+    np.testing.assert_allclose(NAM.to_numpy().sum(axis=1), arrays["nam/rowsum"], rtol=RTOL)
+    U, svs, V = cna.tl.svd_nam(NAM)
+    top = arrays["nam/svs"][:-2]  # the last 1-2 singular values are ~0 (null space)
+    np.testing.assert_allclose(svs.to_numpy()[:len(top)], top, rtol=RTOL, atol=RTOL * 1e-3 * top.max())
+    np.testing.assert_allclose(helpers.sign_align(U.to_numpy()[:, :5], arrays["nam/U"][:, :5]),
+                               arrays["nam/U"][:, :5], atol=2e-5)
+    np.testing.assert_allclose(helpers.sign_align(V.to_numpy()[:64, :4], arrays["nam/V_head"][:, :4]),
+                               arrays["nam/V_head"][:, :4], atol=2e-5 * np.abs(arrays["nam/V_head"]).max())
+    for s in (1, 2, 3):
+        got = cna.tl.nam(data, "id", nsteps=s)[0].to_numpy()[:, :256]
+        np.testing.assert_allclose(got, arrays[f"nam/steps{s}_head"], rtol=RTOL, atol=1e-10)
+    # public diffuse() on user vectors runs in float64 on the device
+    np.testing.assert_allclose(cna.tl.diffuse(data, arrays["diffuse/s0"], 2), arrays["diffuse/s2"], rtol=1e-12)
+    np.testing.assert_allclose(cna.tl.diffuse(data, arrays["diffuse/s0"], 3, self_weight=0.5),
+                               arrays["diffuse/s3_w05"], rtol=1e-12)
+    steps = list(cna.tl.diffuse_stepwise(data, arrays["diffuse/s0"], maxnsteps=2))
+    assert len(steps) == 2
+    np.testing.assert_allclose(steps[1], arrays["diffuse/s2"], rtol=1e-12)
+
+
+def test_auto_stop_diagnostics(cna):
+    """the demo auto-stops after 4 steps with these median kurtoses."""
+    from cna_b200.tl import _nam
+    data = cases.demo_anndata()
+    st = _nam._nam_device(data, "id")
+    assert st.nsteps == 4
+    np.testing.assert_allclose(st.medkurt, [16.40326205754668, 12.757992457504468,
+                                            6.115484918150449, 3.177490071480447], rtol=RTOL)
+
+
+def test_input_errors(cna):
+    data = cases.demo_anndata()
+    meta = cases.demo_sample_meta()
+    with pytest.raises(TypeError):
+        cna.tl.association(data, meta.case.to_numpy(), "id")
+    with pytest.raises(TypeError):
+        cna.tl.association(data, meta.case, "id", covs=meta.male)
+    with pytest.raises(ValueError):
+        cna.tl.association(data, meta.case.iloc[:40], "id")
+    with pytest.raises(ValueError):
+        cna.tl.association(data, meta.case, "id", batches=meta.batch, donorids=meta.batch)
+    y = meta.case.copy()
+    y.iloc[:45] = np.nan
+    with pytest.raises(ValueError, match="fewer than 10 samples"):
+        cna.tl.association(data, y, "id")
+    with pytest.raises(ValueError, match="Maximum number of PCs"):
+        cna.tl.association(data, meta.case, "id", ks=[50], nsteps=1, Nnull=10)
+    with pytest.raises(TypeError):
+        cna.tl.association(data, meta.case, "id", self_weight=2)
+
+
+# ---------------------------------------------------------------------------------------------
+# kernel-level parity against the oracle on seeded inputs (C-ABI wrappers called directly)
+# ---------------------------------------------------------------------------------------------
+def _random_graph(n, deg, seed, hub=None):
+    rng = np.random.default_rng(seed)
+    rows = np.repeat(np.arange(n), deg)
+    cols = rng.integers(0, n, size=n * deg)
+    if hub is not None:  # one heavy row / column, and an isolated cell (empty row)
+        cols[: n // 3] = hub
+    A = sp.csr_matrix((rng.uniform(0.05, 1.0, n * deg), (rows, cols)), shape=(n, n))
+    A = A.maximum(A.T).tolil()
+    A.setdiag(0)
+    A[n - 1, :] = 0
+    A[:, n - 1] = 0
+    A = A.tocsr()
+    A.eliminate_zeros()
+    A.sort_indices()
+    return A
+
+
+@pytest.mark.parametrize("n,S,deg", [(3000, 50, 7), (2048, 200, 12), (1500, 100, 5), (700, 333, 9), (257, 3, 4)])
+def test_diffusion_kernels_vs_oracle(cna, n, S, deg):
+    import torch
+    from cna_b200 import _lib
+    from cna_b200.tl._graph import DeviceGraph
+    from oracle import cna_oracle as orc
+    A = _random_graph(n, deg, seed=n + S, hub=5)
+    rng = np.random.default_rng(1)
+    codes = rng.integers(0, S, n)
+    codes[:S] = np.arange(S)
+    g = DeviceGraph(A)
+    vals, diag = g.scaled(1, torch.float32)
+    ld = (S + 7) // 8 * 8
+    cur = torch.full((n, ld), 7.0, dtype=torch.float32, device="cuda")
+    nxt = torch.zeros_like(cur)
+    code_d = torch.as_tensor(codes, dtype=torch.int32, device="cuda")
+    _lib.diffuse_onehot(g.indptr, g.indices, vals, diag, code_d, S, cur)
+    onehot = np.zeros((n, S))
+    onehot[np.arange(n), codes] = 1
+    ref = list(orc.diffuse_stepwise(A, onehot, maxnsteps=3))
+    got = cur.cpu().numpy()
+    assert (got[:, S:] == 0).all()
+    np.testing.assert_allclose(got[:, :S], ref[0], rtol=2e-6, atol=1e-9)
+    for t in (1, 2):
+        _lib.diffuse_step(g.indptr, g.indices, vals, diag, cur, nxt, S)
+        cur, nxt = nxt, cur
+        np.testing.assert_allclose(cur.cpu().numpy()[:, :S], ref[t], rtol=5e-6, atol=1e-9)
+    # per-sample mass is conserved by the column-stochastic operator
+    np.testing.assert_allclose(cur.double().sum(0).cpu().numpy()[:S], np.bincount(codes, minlength=S), rtol=1e-5)
+    # row kurtosis (auto-stop statistic)
+    import scipy.stats as st
+    C = np.bincount(codes, minlength=S).astype(float)
+    kurt = torch.empty(n, dtype=torch.float64, device="cuda")
+    _lib.row_kurtosis(cur, S, torch.as_tensor(1 / C, device="cuda"), kurt)
+    x = cur.cpu().numpy()[:, :S].astype(np.float64) / C
+    np.testing.assert_allclose(kurt.cpu().numpy(), st.kurtosis(x, axis=1), rtol=1e-9, atol=1e-9)
+    # fp64 generic kernel, odd column count
+    s0 = rng.normal(size=(n, 5))
+    v64, d64 = g.scaled(0.5, torch.float64)
+    a = torch.as_tensor(s0, device="cuda")
+    b = torch.empty_like(a)
+    _lib.diffuse_step(g.indptr, g.indices, v64, d64, a, b, 5)
+    np.testing.assert_allclose(b.cpu().numpy(), orc.diffuse(A, s0, 1, self_weight=0.5), rtol=1e-12, atol=1e-14)
+
+
+@pytest.mark.parametrize("N,n,S,r,nb", [(5000, 50, 50, 6, 5), (3000, 37, 45, 0, 1), (4100, 200, 200, 5, 4),
+                                       (1000, 100, 120, 12, 10), (2000, 330, 400, 3, 2)])
+def test_resid_pass_gram_null_vs_oracle(cna, N, n, S, r, nb):
+    import torch
+    from cna_b200 import _lib
+    from cna_b200.tl import _nam, _stats
+    from oracle import cna_oracle as orc
+    rng = np.random.default_rng(N + n)
+    counts = rng.integers(20, 60, S).astype(float)
+    raw = rng.gamma(2.0, 1.0, (N, S)) * counts  # un-normalised state
+    raw[5] = 0.0                                  # zero-variance row
+    raw32 = raw.astype(np.float32)
+    ld = (S + 7) // 8 * 8
+    s = torch.zeros((N, ld), dtype=torch.float32, device="cuda")
+    s[:, :S] = torch.as_tensor(raw32)
+    colmap = rng.permutation(S)[:n].astype(np.int32)
+    batches = rng.integers(0, nb, n) if nb > 1 else np.ones(n)
+    if nb > 1:
+        batches[:nb] = np.arange(nb)
+    ncov = r - (nb if nb > 1 else 0)
+    covs = rng.normal(size=(n, ncov)) if ncov > 0 else None
+    y = rng.normal(size=n)
+    y = (y - y.mean()) / y.std()
+    st = _nam.NamState(s, S, pd.Index(np.arange(S)), counts, pd.RangeIndex(N))
+    keep = rng.random(N) > 0.02
+    st.keep = torch.as_tensor(keep.astype(np.uint8), device="cuda")
+    res = _nam.resid_nam_device(st, colmap, covs, batches, y, ridges=[1.0, 0.0] if nb > 1 else None)
+    # oracle on the same fp32-rounded input
+    X0 = (raw32.astype(np.float64) / counts)[:, colmap]
+    valid = keep & (X0.std(axis=1, ddof=1) != 0)
+    np.testing.assert_array_equal(res.valid.cpu().numpy().astype(bool), valid)
+    o = orc.resid_nam(X0[valid], covs, batches, ridges=[1.0, 0.0] if nb > 1 else None)
+    assert o.r == res.r
+    np.testing.assert_allclose(res.M, o.M, atol=1e-12)
+    xg = res.x.cpu().numpy()
+    assert (xg[~valid] == 0).all() and (xg[:, n:] == 0).all()
+    np.testing.assert_allclose(xg[valid][:, :n], o.X, rtol=1e-6, atol=2e-6)
+    nc = (o.X * y).sum(axis=1) / n
+    np.testing.assert_allclose(res.ncorr.cpu().numpy()[valid], nc, rtol=1e-6, atol=1e-7)
+    # Gram: tensor-core (if enabled) and SIMT kernels against float64
+    x64 = xg[:, :n].astype(np.float64)
+    Gref = x64.T @ x64
+    for simt in (False, True):
+        G = torch.zeros((n, n), dtype=torch.float64, device="cuda")
+        _lib.gram(res.x, n, G, simt=simt)
+        np.testing.assert_allclose(G.cpu().numpy(), Gref, rtol=0, atol=5e-6 * np.abs(Gref).max())
+    # permutation engine against the oracle's matrix form
+    U, svs, _ = _nam.gram_svd(res.x, n)
+    K = 257
+    np.random.seed(3)
+    bix = _stats.conditional_permutation_indices(batches, K)
+    ks = [1, 3, 4] if n < 100 else list(_default_ks(n))
+    kmax = max(ks)
+    dev = "cuda"
+    Kl = 100
+    ycond = torch.zeros((res.x.shape[1], 104), dtype=torch.float32, device=dev)
+    ssered = torch.empty(K, dtype=torch.float64, device=dev)
+    ssefull = torch.empty((K, len(ks)), dtype=torch.float64, device=dev)
+    td = lambda a, dt=None: torch.as_tensor(np.ascontiguousarray(a), device=dev, dtype=dt)  # noqa: E731
+    _lib.perm_stats(td(y), td(bix.T, torch.int32), td(res.C) if res.r else None,
+                    td(res.W_last) if res.r else None, td(U[:, :kmax].T), td(ks, torch.int32),
+                    ssered, ssefull, ycond, Kl)
+    Z = y[bix]
+    Zc = res.M.dot(Z)
+    Zc = Zc / Zc.std(axis=0, ddof=1)
+    np.testing.assert_allclose(ssered.cpu().numpy(), (Zc * Zc).sum(0), rtol=1e-12)
+    for a, k in enumerate(ks):
+        sse = ((U[:, :k].dot(U[:, :k].T.dot(Zc)) - Zc) ** 2).sum(0)
+        np.testing.assert_allclose(ssefull.cpu().numpy()[:, a], sse, rtol=1e-9)
+    yc = ycond.cpu().numpy()
+    np.testing.assert_allclose(yc[:n, :Kl], Zc[:, :Kl], rtol=1e-6, atol=1e-7)
+    assert (yc[n:] == 0).all() and (yc[:, Kl:] == 0).all()
+    # null histogram: exact counts against the same fp32 inputs evaluated in float64, away from
+    # rounding distance of an edge
+    z = np.abs(x64 @ yc[:n, :Kl].astype(np.float64) / n)
+    mx = max(np.abs(res.ncorr.cpu().numpy()).max(), 0.001)
+    thr = np.arange(mx / 4, mx, mx / 400)
+    edges = _stats.threshold_edges(thr)
+    hist = torch.zeros((Kl, len(thr)), dtype=torch.int32, device=dev)
+    _lib.null_hist(res.x, n, ycond, Kl, td(edges), float(edges[0]), hist)
+    tails = _stats.tails_from_hist(hist.cpu().numpy().astype(np.int64))
+    z2 = z ** 2
+    lo = (z2[:, :, None] >= edges[None, None, :] * (1 + 1e-5)).sum(0)
+    hi = (z2[:, :, None] >= edges[None, None, :] * (1 - 1e-5)).sum(0)
+    assert (tails >= lo).all() and (tails <= hi).all()
+    assert tails.sum() > 0
+    # observed histograms + per-cell lookup: exact integer logic
+    ncorr = res.ncorr.cpu().numpy()
+    obs = torch.zeros((2, len(thr)), dtype=torch.int32, device=dev)
+    _lib.obs_hist(res.ncorr, res.valid, td(edges), td(thr), obs[0], obs[1])
+    oh = obs.cpu().numpy().astype(np.int64)
+    np.testing.assert_array_equal(_stats.tails_from_hist(oh[0]), orc.tail_counts(thr, ncorr[valid])[0])
+    np.testing.assert_array_equal(_stats.tails_from_hist(oh[1]),
+                                  [(np.abs(ncorr[valid]) > t).sum() for t in thr])
+    fdr = rng.random(len(thr))
+    pmin = np.fmin.accumulate(fdr)
+    coef = torch.empty(N, dtype=torch.float64, device=dev)
+    cf = torch.empty(N, dtype=torch.float64, device=dev)
+    _lib.cell_fdr(res.ncorr, res.valid, td(thr), td(pmin), coef, cf)
+    full = np.where(valid, ncorr, np.nan)
+    want = orc.cell_fdr_lookup(full, pd.DataFrame({"threshold": thr, "fdr": fdr}))
+    np.testing.assert_array_equal(cf.cpu().numpy(), want)
+    np.testing.assert_array_equal(np.isnan(coef.cpu().numpy()), ~valid)
+
+
+def _default_ks(n):
+    from cna_b200.tl._association import default_ks
+    return default_ks(n)
+
+
+def test_batch_kurtosis_qc_vs_oracle(cna):
+    import torch
+    from cna_b200 import _lib
+    from cna_b200.tl import _nam
+    from oracle import cna_oracle as orc
+    rng = np.random.default_rng(11)
+    N, S = 4000, 60
+    counts = rng.integers(20, 60, S).astype(float)
+    raw32 = (rng.gamma(2.0, 1.0, (N, S)) * counts).astype(np.float32)
+    raw32[:200, :10] *= 30  # batch-specific neighbourhoods
+    s = torch.zeros((N, 64), dtype=torch.float32, device="cuda")
+    s[:, :S] = torch.as_tensor(raw32)
+    for nb in (2, 6, 37):
+        b = pd.Series(rng.integers(0, nb, S), index=np.arange(S))
+        b.iloc[:nb] = np.arange(nb)
+        st = _nam.NamState(s, S, pd.Index(np.arange(S)), counts, pd.RangeIndex(N))
+        _nam._qc_device(st, b)
+        X = raw32.astype(np.float64) / counts
+        keep, thr = orc.qc_keep(X, b.to_numpy())
+        np.testing.assert_array_equal(_nam.keep_mask(st), keep)
+        assert st.qc_threshold == pytest.approx(thr, rel=1e-12)
+
+
+def test_large_size_properties(cna):
+    """Size-independent properties at a benchmark-like shape (100k cells): mass conservation and
+    row-stochasticity of the NAM, Gram trace = N'(n-1), idempotent re-run, resident == host path."""
+    import torch
+    from cna_b200 import synth
+    from cna_b200.tl import _nam
+    data, meta = synth.make_dataset(100_000, 100, 15, seed=0)
+    st = _nam._nam_device(data, "id", nsteps=3)
+    x = st.s[:, :100].double() * st.inv_count
+    np.testing.assert_allclose(x.sum(1).cpu().numpy(), 1.0, rtol=1e-5)      # NAM rows sum to 1
+    np.testing.assert_allclose(st.s[:, :100].double().sum(0).cpu().numpy(), st.counts, rtol=1e-5)
+    kw = dict(y=meta.case, sid_name="id", batches=meta.batch, covs=meta[["age"]], nsteps=3, Nnull=1000, seed=0)
+    import warnings
+    warnings.simplefilter("ignore")
+    r1 = cna.tl.association(data, return_full=True, **kw)
+    c1, f1 = data.obs["coef"].to_numpy().copy(), data.obs["coef_fdr"].to_numpy().copy()
+    nk = int(r1.kept.sum())
+    n = len(meta)
+    assert r1.namresid_svs.shape[0] == 15
+    np.testing.assert_allclose(r1.namresid_varexp.sum() * n * nk, nk * (n - 1), rtol=1e-5)
+    h = cna.tl.to_device(data)
+    p2 = cna.tl.association(h, **kw)
+    assert p2 == r1.p
+    np.testing.assert_array_equal(data.obs["coef"].to_numpy(), c1)
+    np.testing.assert_array_equal(data.obs["coef_fdr"].to_numpy(), f1)
+    assert np.all(np.diff(r1.fdrs.num_detected.to_numpy()) <= 0)               # tail counts are sorted
+    assert ((f1 >= 0) & (f1 <= 1) | np.isnan(f1)).all()
