@@ -1,0 +1,361 @@
+#!/usr/bin/env python
+"""Benchmark of the CNA hot path: cells/sec through nam() + association().
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config C|B|A]
+
+One "step" is one ``cna.tl.association`` call (which builds the NAM internally) on a synthetic
+AnnData of the named shape.  Default workload = BASELINE.json configs[2] ("C"): 1M cells, 200
+samples, k=30, s=3 diffusion steps, 10 000 permutations.
+
+  value : whole-job cells/sec with the kNN graph and sample codes already resident in HBM
+          (``cna.tl.to_device``); everything else — host RNG for the permutations, the n x n SVD,
+          the F tests, result read-back into ``data.obs`` — is inside the timed region.
+  e2e   : the same call on the host AnnData (scipy CSR in pinned host memory): H2D of the graph and
+          D2H of the per-cell results happen inside the timed region, every step.
+  roofline / rooflines : per-kernel achieved bandwidth / flop rate from CUDA-event pairs recorded
+          around every library call during the timed steps, against MEASURED_PEAKS.json.
+  cpu_baseline : the oracle in ``faithful`` mode (the reference's own cost structure: scipy SpMM,
+          per-step kurtosis, Python loop over permutations, np.histogram per null, per-cell
+          Series.apply) on a bounded sample of the same workload, on this box's host cores.
+
+``--impl reference`` times only that CPU arm.  Timing: CUDA events on the launching stream, barrier
+and synchronize on both sides, max over ranks.  Inputs (0.45 GB graph, 0.8 GB state) are far larger
+than the 126 MB L2, so no explicit L2 flush is needed between iterations.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+import warnings
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+CONFIGS = {
+    # name: (cells, samples, k, diffusion steps, permutations)
+    "A": (10_000, 50, 15, 3, 1000),
+    "B": (100_000, 100, 15, 3, 1000),
+    "C": (1_000_000, 200, 30, 3, 10_000),
+}
+METRIC = "cells/sec through nam()+association(), 1M cells/200 samples/10k perms"
+# CPU sample: same samples / k / steps, cells and permutations scaled down by the same factor
+CPU_SAMPLE_SCALE = 40
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="C", choices=sorted(CONFIGS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(cfg):
+    n, S, k, s, K = CONFIGS[cfg]
+    return f"{n} cells, {S} samples, k={k}, s={s}, {K} permutations (config {cfg})"
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm: the oracle with the reference's cost structure on a bounded sample
+# ---------------------------------------------------------------------------------------------
+def cpu_sample_spec(cfg):
+    n, S, k, s, K = CONFIGS[cfg]
+    scale = CPU_SAMPLE_SCALE if n >= 100_000 else 1
+    return max(n // scale, 20 * S // 2), S, k, s, max(K // scale, 50)
+
+
+def make_cpu_sample(cfg):
+    from cna_b200 import synth
+    n, S, k, s, K = cpu_sample_spec(cfg)
+    data, meta = synth.make_dataset(n, S, k, seed=0, dim=6 if CONFIGS[cfg][0] >= 1_000_000 else None,
+                                    knn="cpu", device="cpu")
+    kw = dict(y=meta.case, sid_name="id", batches=meta.batch, covs=meta[["age"]], nsteps=s, Nnull=K, seed=0)
+    return data, kw, f"{n} cells, {S} samples, k={k}, s={s}, {K} permutations (cells and permutations = config {cfg} / {CONFIGS[cfg][0] // n})"
+
+
+def cpu_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        return max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def time_cpu_arm(data, kw, steps, warmup):
+    from oracle import cna_oracle as orc
+    times = []
+    for i in range(warmup + steps):
+        d = type(data)(data.obs.copy(), data.obsp["connectivities"])
+        t0 = time.perf_counter()
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            orc.association(d, faithful=True, **kw)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return times
+
+
+def run_reference(args):
+    """--impl reference: the CPU implementation of the path on this box's host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    data, kw, sample = make_cpu_sample(args.config)
+    times = time_cpu_arm(data, kw, args.steps, min(args.warmup, 1))
+    n_cells = len(data.obs)
+    value = n_cells * len(times) / sum(times)
+    cores = cpu_threads()
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "cells/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": {"workload": workload_name(args.config), "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "cells/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.path = None
+
+    def __enter__(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+        return self
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if not self.path or not os.path.exists(self.path):
+            return out
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in open(self.path):
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons),
+                       samples=len(sm))
+        return out
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm=p["hbm_gbs"], tensor=p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                    tensor_burst=p["bf16_tflops"], source="measured")
+    return dict(hbm=6650.0, tensor=1400.0, tensor_burst=1590.0, source="fallback")
+
+
+def pin_graph(A):
+    """Register the scipy CSR buffers as pinned host memory (the e2e contract: inputs start in
+    pinned host memory).  Returns a callable that unregisters them."""
+    import torch
+    rt = torch.cuda.cudart()
+    regs = []
+    for arr in (A.data, A.indices, A.indptr):
+        if int(rt.cudaHostRegister(arr.ctypes.data, arr.nbytes, 0)) == 0:
+            regs.append(arr)
+
+    def undo():
+        for arr in regs:
+            rt.cudaHostUnregister(arr.ctypes.data)
+    return undo
+
+
+def rooflines(prof, steps, N, S, n, nnz, K, Kl, s_steps, peaks):
+    """Per-kernel achieved rates from the CUDA-event profile of the timed steps.
+    Algorithmic bytes / flops per launch follow SURVEY.md 8(d) and DESIGN.md."""
+    b_spmm = 8 * nnz + 4 * (N + 1) + 4 * N + 2 * 4 * N * S
+    spec = {
+        "cna_diffuse_step_f32": ("hbm", b_spmm, "diffusion SpMM (one step)"),
+        "cna_diffuse_onehot": ("hbm", b_spmm, "diffusion step 1 from the one-hot indicator"),
+        "cna_resid_pass": ("hbm", 2 * 4 * N * S, "select/centre/residualise/standardise/ncorr pass"),
+        "cna_gram": ("tensor", 2.0 * n * n * N, "Gram X^T X"),
+        "cna_null_hist": ("tensor", 2.0 * N * n * Kl, "null GEMM + threshold histogram"),
+        "cna_perm_stats": (None, None, "permutation engine (fp64)"),
+    }
+    total = sum(ms for _, ms in prof.values()) or 1.0
+    out = []
+    for name, (calls, ms) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
+        bound, work, what = spec.get(name, (None, None, name))
+        avg = ms / max(calls, 1)
+        item = {"kernel": name, "what": what, "launches_per_step": calls / steps, "avg_ms": avg,
+                "share_of_device_time": ms / total}
+        if bound == "hbm":
+            ach = work / (avg * 1e-3) / 1e9
+            item.update(bound="hbm", achieved=ach, peak=peaks["hbm"], unit="GB/s", frac=ach / peaks["hbm"],
+                        algorithmic_bytes=work)
+        elif bound == "tensor":
+            ach = work / (avg * 1e-3) / 1e12
+            item.update(bound="tensor", achieved=ach, peak=peaks["tensor"], unit="TFLOP/s",
+                        frac=ach / peaks["tensor"], algorithmic_flops=work)
+        out.append(item)
+    return out
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    import cna_b200 as cna
+    from cna_b200 import _lib, synth
+    _lib.load()
+
+    N, S, k, s_steps, K = CONFIGS[args.config]
+    t0 = time.perf_counter()
+    data, meta = synth.make_dataset(N, S, k, seed=0)
+    gen_s = time.perf_counter() - t0
+    A = data.obsp["connectivities"]
+    nnz = int(A.nnz)
+    kw = dict(y=meta.case, sid_name="id", batches=meta.batch, covs=meta[["age"]], nsteps=s_steps, Nnull=K, seed=0)
+    n = S
+    Kl = min(1000, K)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record()
+        for _ in range(steps):
+            fn()
+        ev1.record()
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    if world > 1:
+        from cna_b200.parallel import association_sharded, shard_to_device
+        handle = shard_to_device(data, "id")
+        step_dev = lambda: association_sharded(handle, **kw)  # noqa: E731
+        step_e2e = lambda: association_sharded(shard_to_device(data, "id"), **kw)  # noqa: E731
+    else:
+        handle = cna.tl.to_device(data)
+        step_dev = lambda: cna.tl.association(handle, **kw)  # noqa: E731
+        step_e2e = lambda: cna.tl.association(data, **kw)  # noqa: E731
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for _ in range(args.warmup):
+            step_dev()
+        launches0 = _lib.launch_count()
+        with ClockSampler(local) as clk:
+            _lib.profile_start()
+            ms = timed(step_dev, args.steps)
+            prof = _lib.profile_stop()
+        launches = _lib.launch_count() - launches0
+        p_value = step_dev()
+        e2e = None
+        if not args.no_e2e:
+            undo = pin_graph(A)
+            for _ in range(min(args.warmup, 2)):
+                step_e2e()
+            ms_e2e = timed(step_e2e, args.steps)
+            undo()
+            h2d = A.data.nbytes + A.indices.nbytes + A.indptr.nbytes + 4 * N
+            d2h = 2 * 8 * N + 8 * n * n + 8 * K * 5
+            e2e = {"value": N * args.steps / (ms_e2e * 1e-3), "unit": "cells/s", "ms_per_step": ms_e2e / args.steps,
+                   "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)}
+
+    if rank != 0:
+        return
+    peaks = measured_peaks()
+    roofs = rooflines(prof, args.steps, N, S, n, nnz, K, Kl, s_steps, peaks)
+    spmm = next((r for r in roofs if r["kernel"] == "cna_diffuse_step_f32"), None)
+    primary = None
+    if spmm:
+        primary = {"kernel": "cna_diffuse_step_f32 (CSR SpMM diffusion step)", "bound": "hbm",
+                   "achieved": spmm["achieved"], "peak": spmm["peak"], "unit": "GB/s", "frac": spmm["frac"],
+                   "traffic": None, "peak_source": peaks["source"] + " (MEASURED_PEAKS.json hbm_gbs)"}
+    line = {
+        "metric": METRIC, "value": N * args.steps / (ms * 1e-3), "unit": "cells/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32 state / f64 statistics", "data": "synthetic",
+        "config": {"workload": workload_name(args.config), "nnz": nnz, "l2": "inputs larger than L2 (no flush)",
+                   "parallelism": f"cell-axis shards x{world}" if world > 1 else "single GPU",
+                   "p_value": p_value, "datagen_s": round(gen_s, 1)},
+        "clocks": clk.summary(), "e2e": e2e, "gpu_launches": launches / args.steps,
+        "roofline": primary, "rooflines": roofs,
+    }
+    if not args.no_cpu_baseline and world == 1:
+        cdata, ckw, sample = make_cpu_sample(args.config)
+        t = time_cpu_arm(cdata, ckw, 1, 0)
+        line["cpu_baseline"] = {"value": len(cdata.obs) / t[0], "unit": "cells/s", "cores": cpu_threads(),
+                                "kind": "port", "sample": sample, "seconds": t[0]}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

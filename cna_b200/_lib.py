@@ -97,7 +97,34 @@ def _declare(lib):
         fn.argtypes = args
 
 
-def _check(rc, name):
+_PROFILE = None  # name -> list of (start event, end event) while profiling is on
+
+
+def profile_start():
+    """Record a CUDA-event pair around every library call (on torch's current stream, the stream
+    the kernels are launched on) until ``profile_stop``."""
+    global _PROFILE
+    _PROFILE = {}
+
+
+def profile_stop():
+    """Returns {entry point: (number of calls, total milliseconds)}."""
+    global _PROFILE
+    prof, _PROFILE = _PROFILE, None
+    torch.cuda.synchronize()
+    return {k: (len(v), sum(a.elapsed_time(b) for a, b in v)) for k, v in (prof or {}).items()}
+
+
+def _call(name, *args):
+    fn = getattr(load(), name)
+    if _PROFILE is None:
+        rc = fn(*args)
+    else:
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        rc = fn(*args)
+        b.record()
+        _PROFILE.setdefault(name, []).append((a, b))
     if rc != 0:
         raise CnaError(f"{name} failed ({rc}): {load().cna_last_error().decode()}")
 
@@ -129,52 +156,51 @@ def launch_count():
 # ---------------------------------------------------------------------------------------------
 def graph_colsum(indptr, indices, data, colsum):
     is64 = data.dtype == torch.float64
-    _check(load().cna_graph_colsum(_ptr(indptr, torch.int32, "indptr"), _ptr(indices, torch.int32, "indices"),
+    _call("cna_graph_colsum", _ptr(indptr, torch.int32, "indptr"), _ptr(indices, torch.int32, "indices"),
                                    _ptr(data, data.dtype, "data"), int(is64), indptr.numel() - 1,
-                                   _ptr(colsum, torch.float64, "colsum"), _stream()), "cna_graph_colsum")
+                                   _ptr(colsum, torch.float64, "colsum"), _stream())
 
 
 def graph_scale(indptr, indices, data, colsum, self_weight, vals, diag):
     is64 = data.dtype == torch.float64
     out64 = vals.dtype == torch.float64
-    _check(load().cna_graph_scale(_ptr(indptr, torch.int32, "indptr"), _ptr(indices, torch.int32, "indices"),
+    _call("cna_graph_scale", _ptr(indptr, torch.int32, "indptr"), _ptr(indices, torch.int32, "indices"),
                                   _ptr(data, data.dtype, "data"), int(is64), indptr.numel() - 1,
                                   _ptr(colsum, torch.float64, "colsum"), float(self_weight),
                                   _ptr(vals, vals.dtype, "vals"), _ptr(diag, vals.dtype, "diag"),
-                                  int(out64), _stream()), "cna_graph_scale")
+                                  int(out64), _stream())
 
 
 def diffuse_onehot(indptr, indices, vals, diag, code, n_samples, out):
-    _check(load().cna_diffuse_onehot(_ptr(indptr, torch.int32, "indptr"), _ptr(indices, torch.int32, "indices"),
+    _call("cna_diffuse_onehot", _ptr(indptr, torch.int32, "indptr"), _ptr(indices, torch.int32, "indices"),
                                      _ptr(vals, torch.float32, "vals"), _ptr(diag, torch.float32, "diag"),
                                      _ptr(code, torch.int32, "code"), out.shape[0], int(n_samples),
-                                     _ptr(out, torch.float32, "out"), out.shape[1], _stream()),
-           "cna_diffuse_onehot")
+                                     _ptr(out, torch.float32, "out"), out.shape[1], _stream())
 
 
 def diffuse_step(indptr, indices, vals, diag, src, dst, n_cols):
     if src.dtype == torch.float32:
-        fn, name, dt = load().cna_diffuse_step_f32, "cna_diffuse_step_f32", torch.float32
+        name, dt = "cna_diffuse_step_f32", torch.float32
     else:
-        fn, name, dt = load().cna_diffuse_step_f64, "cna_diffuse_step_f64", torch.float64
-    _check(fn(_ptr(indptr, torch.int32, "indptr"), _ptr(indices, torch.int32, "indices"),
-              _ptr(vals, dt, "vals"), _ptr(diag, dt, "diag"), _ptr(src, dt, "src"), _ptr(dst, dt, "dst"),
-              src.shape[0], int(n_cols), src.shape[1], _stream()), name)
+        name, dt = "cna_diffuse_step_f64", torch.float64
+    _call(name, _ptr(indptr, torch.int32, "indptr"), _ptr(indices, torch.int32, "indices"),
+          _ptr(vals, dt, "vals"), _ptr(diag, dt, "diag"), _ptr(src, dt, "src"), _ptr(dst, dt, "dst"),
+          src.shape[0], int(n_cols), src.shape[1], _stream())
 
 
 def row_kurtosis(s, n_samples, inv_count, kurt):
-    _check(load().cna_row_kurtosis(_ptr(s, torch.float32, "s"), s.shape[1], s.shape[0], int(n_samples),
+    _call("cna_row_kurtosis", _ptr(s, torch.float32, "s"), s.shape[1], s.shape[0], int(n_samples),
                                    _ptr(inv_count, torch.float64, "inv_count"),
-                                   _ptr(kurt, torch.float64, "kurt"), _stream()), "cna_row_kurtosis")
+                                   _ptr(kurt, torch.float64, "kurt"), _stream())
 
 
 def batch_kurtosis(s, inv_count, seg_order, seg_off, kurt):
     nb = seg_off.numel() - 1
-    _check(load().cna_batch_kurtosis(_ptr(s, torch.float32, "s"), s.shape[1], s.shape[0],
+    _call("cna_batch_kurtosis", _ptr(s, torch.float32, "s"), s.shape[1], s.shape[0],
                                      _ptr(inv_count, torch.float64, "inv_count"),
                                      _ptr(seg_order, torch.int32, "seg_order"),
                                      _ptr(seg_off, torch.int32, "seg_off"), nb, seg_order.numel(),
-                                     _ptr(kurt, torch.float64, "kurt"), _stream()), "cna_batch_kurtosis")
+                                     _ptr(kurt, torch.float64, "kurt"), _stream())
 
 
 def resid_pass(s, inv_count, colmap, row_keep, C, Wt, seg_order, seg_off, y, x_out, kurt, ncorr, row_valid):
@@ -198,63 +224,59 @@ def resid_pass(s, inv_count, colmap, row_keep, C, Wt, seg_order, seg_off, y, x_o
     a.kurt = _ptr(kurt, torch.float64, "kurt", allow_none=True)
     a.ncorr = _ptr(ncorr, torch.float64, "ncorr")
     a.row_valid = _ptr(row_valid, torch.uint8, "row_valid")
-    _check(load().cna_resid_pass(ctypes.byref(a), _stream()), "cna_resid_pass")
+    _call("cna_resid_pass", ctypes.byref(a), _stream())
 
 
 def gram(x, n, out, simt=False):
-    fn = load().cna_gram_simt if simt else load().cna_gram
-    _check(fn(_ptr(x, torch.float32, "x"), x.shape[1], x.shape[0], int(n), _ptr(out, torch.float64, "gram"),
-              _stream()), "cna_gram")
+    _call("cna_gram_simt" if simt else "cna_gram", _ptr(x, torch.float32, "x"), x.shape[1], x.shape[0],
+          int(n), _ptr(out, torch.float64, "gram"), _stream())
 
 
 def right_multiply(x, n, b, n_out, out):
-    _check(load().cna_right_multiply(_ptr(x, torch.float32, "x"), x.shape[1], x.shape[0], int(n),
+    _call("cna_right_multiply", _ptr(x, torch.float32, "x"), x.shape[1], x.shape[0], int(n),
                                      _ptr(b, torch.float32, "b"), b.shape[1], int(n_out),
-                                     _ptr(out, torch.float32, "out"), out.shape[1], _stream()),
-           "cna_right_multiply")
+                                     _ptr(out, torch.float32, "out"), out.shape[1], _stream())
 
 
 def perm_stats(y, perm, C, W, Ut, ks, ssered, ssefull, ycond, n_local):
     K, n = perm.shape
     r = 0 if C is None else C.shape[1]
-    _check(load().cna_perm_stats(_ptr(y, torch.float64, "y"), _ptr(perm, torch.int32, "perm"), K, n,
+    _call("cna_perm_stats", _ptr(y, torch.float64, "y"), _ptr(perm, torch.int32, "perm"), K, n,
                                  _ptr(C, torch.float64, "C") if r else None,
                                  _ptr(W, torch.float64, "W") if r else None, r,
                                  _ptr(Ut, torch.float64, "Ut"), Ut.shape[0], _ptr(ks, torch.int32, "ks"),
                                  ks.numel(), _ptr(ssered, torch.float64, "ssered"),
                                  _ptr(ssefull, torch.float64, "ssefull"),
                                  _ptr(ycond, torch.float32, "ycond", allow_none=True),
-                                 0 if ycond is None else ycond.shape[1], int(n_local), _stream()),
-           "cna_perm_stats")
+                                 0 if ycond is None else ycond.shape[1], int(n_local), _stream())
 
 
 def null_hist(x, n, ycond, n_null, edges, edge0, hist):
-    _check(load().cna_null_hist(_ptr(x, torch.float32, "x"), x.shape[1], x.shape[0], int(n),
+    _call("cna_null_hist", _ptr(x, torch.float32, "x"), x.shape[1], x.shape[0], int(n),
                                 _ptr(ycond, torch.float32, "ycond"), ycond.shape[1], int(n_null),
                                 _ptr(edges, torch.float64, "edges"), edges.numel(), float(edge0),
-                                _ptr(hist, torch.int32, "hist"), _stream()), "cna_null_hist")
+                                _ptr(hist, torch.int32, "hist"), _stream())
 
 
 def obs_hist(ncorr, row_valid, edges, thresholds, rank_hist, det_hist):
-    _check(load().cna_obs_hist(_ptr(ncorr, torch.float64, "ncorr"),
+    _call("cna_obs_hist", _ptr(ncorr, torch.float64, "ncorr"),
                                _ptr(row_valid, torch.uint8, "row_valid", allow_none=True), ncorr.numel(),
                                _ptr(edges, torch.float64, "edges"), _ptr(thresholds, torch.float64, "thresholds"),
                                edges.numel(), _ptr(rank_hist, torch.int32, "rank_hist"),
-                               _ptr(det_hist, torch.int32, "det_hist"), _stream()), "cna_obs_hist")
+                               _ptr(det_hist, torch.int32, "det_hist"), _stream())
 
 
 def absmax(v, row_valid, out):
-    _check(load().cna_absmax(_ptr(v, torch.float64, "v"), _ptr(row_valid, torch.uint8, "row_valid", allow_none=True),
-                             v.numel(), _ptr(out, torch.float64, "out"), _stream()), "cna_absmax")
+    _call("cna_absmax", _ptr(v, torch.float64, "v"), _ptr(row_valid, torch.uint8, "row_valid", allow_none=True),
+                             v.numel(), _ptr(out, torch.float64, "out"), _stream())
 
 
 def cell_fdr(ncorr, row_valid, thresholds, prefix_min_fdr, coef, fdr):
-    _check(load().cna_cell_fdr(_ptr(ncorr, torch.float64, "ncorr"),
+    _call("cna_cell_fdr", _ptr(ncorr, torch.float64, "ncorr"),
                                _ptr(row_valid, torch.uint8, "row_valid", allow_none=True), ncorr.numel(),
                                _ptr(thresholds, torch.float64, "thresholds"),
                                _ptr(prefix_min_fdr, torch.float64, "prefix_min_fdr"), thresholds.numel(),
-                               _ptr(coef, torch.float64, "coef"), _ptr(fdr, torch.float64, "fdr"), _stream()),
-           "cna_cell_fdr")
+                               _ptr(coef, torch.float64, "coef"), _ptr(fdr, torch.float64, "fdr"), _stream())
 
 
 def knn_bruteforce(points, k):
@@ -268,7 +290,7 @@ def knn_bruteforce(points, k):
     points = points.contiguous()
     idx = torch.empty((n, k), dtype=torch.int32, device=points.device)
     d2 = torch.empty((n, k), dtype=torch.float32, device=points.device)
-    _check(load().cna_knn_bruteforce(_ptr(points, torch.float32, "points"), n, pad, int(k),
+    _call("cna_knn_bruteforce", _ptr(points, torch.float32, "points"), n, pad, int(k),
                                      _ptr(idx, torch.int32, "idx"), _ptr(d2, torch.float32, "dist2"),
-                                     _stream()), "cna_knn_bruteforce")
+                                     _stream())
     return idx.long(), d2

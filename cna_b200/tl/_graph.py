@@ -3,6 +3,8 @@
 Reference: ``src/cna/tools/_nam.py:12-19`` (get_connectivity), ``:28`` (column sums + self weight),
 ``:51-54`` (one-hot sample indicator and cells-per-sample counts).
 """
+import warnings
+
 import numpy as np
 import pandas as pd
 import scipy.sparse as sp
@@ -30,7 +32,10 @@ def device():
 
 
 def _to_dev(arr, dtype=None):
-    t = torch.from_numpy(np.ascontiguousarray(arr))
+    arr = np.ascontiguousarray(arr)
+    with warnings.catch_warnings():  # read-only numpy views (pandas CoW, mmap) are only read from
+        warnings.simplefilter("ignore", UserWarning)
+        t = torch.from_numpy(arr)
     if dtype is not None and t.dtype != dtype:
         t = t.to(dtype)
     return t.to(device(), non_blocking=True)

@@ -51,7 +51,7 @@ def test_demo_cases_match_reference(cna, demo, name):
     data, kwargs = cases.build_demo_case(cases.load_demo_graph(), spec)
     res, warns = helpers.run_association(cna.tl.association, data, kwargs, spec.get("np_seed"))
     helpers.assert_matches_golden(res, data, kwargs.get("key_added", "coef"), arrays, scalars, name,
-                                  warns=warns, rtol=RTOL, atol=1e-9)
+                                  warns=warns, rtol=RTOL, atol=1e-9, fp32=True)
 
 
 @pytest.mark.parametrize("name", list(cases.SYNTH_CASES))
@@ -61,7 +61,7 @@ def test_synth_cases_match_reference(cna, synth, name):
     data, kwargs = cases.build_synth_case(spec, helpers.synth_raw(arrays, name))
     res, warns = helpers.run_association(cna.tl.association, data, kwargs)
     helpers.assert_matches_golden(res, data, "coef", arrays, scalars, name, warns=warns, rtol=RTOL,
-                                  atol=1e-9)
+                                  atol=1e-9, fp32=True)
 
 
 def test_notebook_numbers(cna):
@@ -102,12 +102,12 @@ def test_nam_svd_diffuse_match_reference(cna, demo):
         got = cna.tl.nam(data, "id", nsteps=s)[0].to_numpy()[:, :256]
         np.testing.assert_allclose(got, arrays[f"nam/steps{s}_head"], rtol=RTOL, atol=1e-10)
     # public diffuse() on user vectors runs in float64 on the device
-    np.testing.assert_allclose(cna.tl.diffuse(data, arrays["diffuse/s0"], 2), arrays["diffuse/s2"], rtol=1e-12)
+    np.testing.assert_allclose(cna.tl.diffuse(data, arrays["diffuse/s0"], 2), arrays["diffuse/s2"], rtol=1e-12, atol=1e-15)
     np.testing.assert_allclose(cna.tl.diffuse(data, arrays["diffuse/s0"], 3, self_weight=0.5),
-                               arrays["diffuse/s3_w05"], rtol=1e-12)
+                               arrays["diffuse/s3_w05"], rtol=1e-12, atol=1e-15)
     steps = list(cna.tl.diffuse_stepwise(data, arrays["diffuse/s0"], maxnsteps=2))
     assert len(steps) == 2
-    np.testing.assert_allclose(steps[1], arrays["diffuse/s2"], rtol=1e-12)
+    np.testing.assert_allclose(steps[1], arrays["diffuse/s2"], rtol=1e-12, atol=1e-15)
 
 
 def test_auto_stop_diagnostics(cna):
