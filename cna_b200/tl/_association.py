@@ -84,15 +84,46 @@ def _pick(p, r2, ks):
     return np.asarray(ks)[pick], p[rows, pick], r2[rows, pick]
 
 
-def _association(st_nam, res, y, batches, donorids, ks=None, Nnull=1000, force_permute_all=False,
-                 local_test=True, seed=None, show_progress=False):
-    """``_association.py:10-129``.  ``res`` carries the device-resident residualised NAM (``res.x``),
-    U, M, r; ``y`` / ``batches`` / ``donorids`` are length-n arrays in the order of res.x's columns."""
+class _PermutationJob:
+    """Draws the permutation index matrix on a helper thread while the GPU builds the NAM.
+
+    The draws use the reference's exact sequence of legacy-RNG calls on the *global* numpy state
+    (``_stats.py:8-16`` / ``:31``); numpy releases the GIL inside ``randn`` and ``argsort``, so the
+    ~50 ms this takes at 10 000 permutations x 200 samples overlap with the diffusion kernels.  The
+    caller must not touch ``np.random`` until ``result()`` has returned."""
+
+    def __init__(self, y_std, batches, donorids, Nnull):
+        import threading
+        self._out = None
+        self._exc = None
+
+        def work():
+            try:
+                if donorids is not None:  # _association.py:80-83
+                    bix = _stats.grouplevel_permutation_indices(donorids, y_std, Nnull)
+                else:
+                    bix = _stats.conditional_permutation_indices(batches, Nnull)
+                self._out = None if bix is None else np.ascontiguousarray(bix.T, dtype=np.int32)
+            except BaseException as exc:  # re-raised on the caller's thread
+                self._exc = exc
+
+        self._thread = threading.Thread(target=work, name="cna-permutations", daemon=True)
+        self._thread.start()
+
+    def result(self):
+        self._thread.join()
+        if self._exc is not None:
+            raise self._exc
+        if self._out is None:
+            raise TypeError("'NoneType' object is not subscriptable")  # what the reference dies with
+        return self._out
+
+
+def _association(res, perms, Nnull=1000, local_test=True, show_progress=False):
+    """``_association.py:10-129`` after seeding / permutation drawing (done by the caller so that
+    they overlap with the NAM kernels).  ``res`` carries the device-resident residualised NAM
+    (``res.x``), U, M, r, the standardised phenotype and ks."""
     out = select_output(show_progress)
-    if seed is not None:
-        np.random.seed(seed)  # :15-16
-    if force_permute_all:
-        batches = np.ones(len(y))  # :17-18
     U, M, r, n = res.U, res.M, res.r, res.n
     dev = res.x.device
     y = res.y_std
@@ -113,15 +144,9 @@ def _association(st_nam, res, y, batches, donorids, ks=None, Nnull=1000, force_p
     yhat = U[:, :k].dot(beta)
     r2_perpc = (beta / np.sqrt(ycond.dot(ycond))) ** 2  # :74
 
-    # ---- permutations: indices on the host (bit-exact RNG), everything else on the device ----
-    if donorids is not None:  # :80-83
-        bix = _stats.grouplevel_permutation_indices(donorids, y, Nnull)
-        if bix is None:
-            raise TypeError("'NoneType' object is not subscriptable")  # what the reference dies with
-    else:
-        bix = _stats.conditional_permutation_indices(batches, Nnull)
+    # ---- permutations: indices from the host RNG (bit-exact), everything else on the device ----
     Kl = min(1000, Nnull) if local_test else 0
-    perm_d = _to_dev(np.ascontiguousarray(bix.T, dtype=np.int32))
+    perm_d = _to_dev(perms.result())
     ld_y = _nam._round_up(max(Kl, 1), 4)
     ycond_d = torch.zeros((res.x.shape[1], ld_y), dtype=torch.float32, device=dev) if Kl else None
     ssered_d = torch.empty(Nnull, dtype=torch.float64, device=dev)
@@ -185,36 +210,47 @@ def association(data, y, sid_name, batches=None, covs=None, donorids=None, ks=No
         raise TypeError(f"_association() got an unexpected keyword argument '{sorted(bad)[0]}'")
     batches, filter_samples = check_inputs(data, y, sid_name, batches, covs, donorids,
                                            allow_low_sample_size)
+    Nnull = kwargs.get("Nnull", 1000)
+    local_test = kwargs.get("local_test", True)
 
-    # ---- NAM (compute_nam_and_reindex, :175-191): diffusion + QC on the device ----
-    print("computing NAM", file=out)
-    stn = _nam._nam_device(data, sid_name, nsteps=nsteps, show_progress=show_progress)
-    _nam._qc_device(stn, batches, show_progress=show_progress)
-
+    # ---- sample bookkeeping (:178-191) and the small design algebra, all on the host ----
     fs = np.asarray(filter_samples, dtype=bool)
     sids = y.index[fs]
-    colmap = stn.labels.get_indexer(sids)  # NAM.reindex(y.index)[filter_samples], :178-181
     n = int(fs.sum())
     batches_f = batches.reindex(y.index).to_numpy()[fs]
     covs_f = covs.reindex(y.index).to_numpy()[fs] if covs is not None else None
     donor_f = donorids.reindex(y.index).to_numpy()[fs] if donorids is not None else None
     y_f = np.asarray(y.to_numpy()[fs], dtype=np.float64)
     y_std = (y_f - y_f.mean()) / y_f.std()  # :22 (ndarray -> ddof=0)
-
     npcs = min(n, max([10] + [int(max_frac_pcs * n)] + [ks if ks is not None else []][0]))  # :207
+    ks_eff = default_ks(n) if ks is None else ks
+    r = _nam.design_matrix(covs_f, batches_f, n)[0].shape[1]
+
+    # ---- launch the diffusion (asynchronous unless nsteps is None) ----
+    print("computing NAM", file=out)
+    stn = _nam._nam_device(data, sid_name, nsteps=nsteps, show_progress=show_progress)
+
+    if kwargs.get("seed") is not None:
+        np.random.seed(kwargs["seed"])  # :15-16
+    if max(ks_eff) + r >= n:  # :29-33 (the reference raises this after seeding, before any draw)
+        raise ValueError(
+            "Maximum number of PCs plus number of covariates must be less than n-1. "
+            f"Currently it is {max(ks_eff) + r} while n is {n}. Either reduce the number of covariates "
+            "or reduce the number of PCs to consider using the optional argument ks=[...].")
+    perm_batches = np.ones(n) if kwargs.get("force_permute_all", False) else batches_f  # :17-18
+    perms = _PermutationJob(y_std, perm_batches, donor_f, Nnull)
+
+    # ---- QC, residualisation, Gram + SVD ----
+    _nam._qc_device(stn, batches, show_progress=show_progress)
+    colmap = stn.labels.get_indexer(sids)  # NAM.reindex(y.index)[filter_samples], :178-181
     res = _nam.resid_nam_device(stn, colmap, covs_f, batches_f, y_std, ridges=ridges,
                                 show_progress=show_progress)
     res.y_std = y_std
-    res.ks = default_ks(n) if ks is None else ks
-    if max(res.ks) + res.r >= n:  # :29-33
-        raise ValueError(
-            "Maximum number of PCs plus number of covariates must be less than n-1. "
-            f"Currently it is {max(res.ks) + res.r} while n is {n}. Either reduce the number of covariates "
-            "or reduce the number of PCs to consider using the optional argument ks=[...].")
+    res.ks = ks_eff
     res.U, svs, res.G = _nam.gram_svd(res.x, n)  # _nam.py:163
 
     print("performing association test", file=out)
-    core = _association(stn, res, y_f, batches_f, donor_f, ks=ks, show_progress=show_progress, **kwargs)
+    core = _association(res, perms, Nnull=Nnull, local_test=local_test, show_progress=show_progress)
 
     # ---- neighbourhood-level outputs (:228-237) ----
     N = stn.N

@@ -61,8 +61,10 @@ def assert_matches_golden(res, data, key, arrays, scalars, name, warns=None, rto
     FDR-passing set) keeps the strict bar.
     """
     vec_rtol = 1e-3 if fp32 else rtol
-    edge_tol = 1e-6 if fp32 else 0.0
     ref_nc, ref_fd = arrays[name + "/ncorrs"], arrays[name + "/fdrs"]
+    # coefficients are only required to rtol * max|coef| (checked below), so a threshold count may
+    # move by the number of reference cells that close to the threshold
+    edge_tol = rtol * np.abs(ref_nc).max() if fp32 else 0.0
     sc = scalars[name]
     g = lambda f: arrays[name + "/" + f]  # noqa: E731
     # ---- integer / index outputs: exact ----
@@ -105,21 +107,35 @@ def assert_matches_golden(res, data, key, arrays, scalars, name, warns=None, rto
     assert len(fd) in (300, 301) and len(res.fdrs) in (300, 301)
     nt = min(len(fd), len(res.fdrs))
     close(res.fdrs["threshold"].to_numpy()[:nt], fd[:nt, 0])
+    fdr_tol = np.full(nt, max(atol, rtol))
     if fp32:
-        # a flip of one knife-edge cell in the observed tail count ranks_i moves fdr_i by 1/ranks_i
+        # fdr_i = mean_k(tails_ki) / ranks_i (_stats.py:79-80).  One knife-edge cell moving across
+        # edge i changes ranks_i by one (relative 1/ranks_i); a null value doing the same changes
+        # mean_k(tails_ki) by 1/Kl (the null matrix is not stored in the fixtures, so allow three).
         cuts = np.sqrt(np.maximum(fd[:nt, 0] ** 2 * (1 - 1e-5) - 1e-8, 0))  # _stats.py:51
         ranks = np.maximum((np.abs(ref_nc)[:, None] >= cuts[None, :]).sum(0), 1)
-        allow = _knife_edge_counts(ref_nc, cuts, edge_tol) / ranks + 1e-4
-        err = np.abs(res.fdrs["fdr"].to_numpy()[:nt] - fd[:nt, 1])
-        assert (err <= allow * np.abs(fd[:nt, 1]) + max(atol, rtol)).all(), err.max()
-    else:
-        close(res.fdrs["fdr"].to_numpy()[:nt], fd[:nt, 1], rtol=max(rtol, 1e-9), atol=max(atol, rtol))
+        n_local = min(1000, len(g("nullminps")))
+        rel = _knife_edge_counts(ref_nc, cuts, edge_tol) / ranks + 1e-4
+        fdr_tol = rel * np.abs(fd[:nt, 1]) + 3.0 / (n_local * ranks) + max(atol, rtol)
+    err = np.abs(res.fdrs["fdr"].to_numpy()[:nt] - fd[:nt, 1])
+    assert (err <= fdr_tol).all(), (err.max(), np.flatnonzero(err > fdr_tol))
     for f in ("fdr_5p_t", "fdr_10p_t"):
         if sc[f] is None:
             assert getattr(res, f) is None
         else:
             close(getattr(res, f), sc[f])
-    close(coef_fdr, g("coef_fdr"), atol=max(atol, rtol))
+    if fp32:
+        # per-cell fdr = running minimum of fdr over thresholds <= |coef| (_association.py:234-237):
+        # a cell within edge_tol of a threshold may land on either side of it
+        t = fd[:nt, 0]
+        pm = np.concatenate([[1.0], np.fmin.accumulate(fd[:nt, 1])])
+        tol_cum = np.concatenate([[0.0], np.maximum.accumulate(fdr_tol)])
+        c = np.nan_to_num(np.abs(g("coef")), nan=-1.0)
+        lo = np.searchsorted(t, c - edge_tol, side="right")
+        hi = np.searchsorted(t, c + edge_tol, side="right")
+        assert ((coef_fdr <= pm[lo] + tol_cum[hi]) & (coef_fdr >= pm[hi] - tol_cum[hi])).all()
+    else:
+        close(coef_fdr, g("coef_fdr"), atol=max(atol, rtol))
     close(res.M.to_numpy(), g("M"), atol=max(atol, rtol))
     if check_full:
         n_top = max(kk, 4)

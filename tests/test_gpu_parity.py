@@ -348,7 +348,7 @@ def test_large_size_properties(cna):
     data, meta = synth.make_dataset(100_000, 100, 15, seed=0)
     st = _nam._nam_device(data, "id", nsteps=3)
     x = st.s[:, :100].double() * st.inv_count
-    np.testing.assert_allclose(x.sum(1).cpu().numpy(), 1.0, rtol=1e-5)      # NAM rows sum to 1
+    np.testing.assert_allclose(x.sum(0).cpu().numpy(), 1.0, rtol=1e-5)      # each sample's NAM row sums to 1
     np.testing.assert_allclose(st.s[:, :100].double().sum(0).cpu().numpy(), st.counts, rtol=1e-5)
     kw = dict(y=meta.case, sid_name="id", batches=meta.batch, covs=meta[["age"]], nsteps=3, Nnull=1000, seed=0)
     import warnings

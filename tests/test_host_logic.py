@@ -1,0 +1,185 @@
+"""CPU tests: the C-ABI library builds / loads / exports what include/cna_b200.h declares, and the
+host-side logic of ``cna_b200.tl`` (input checks, permutation drawing, FDR bookkeeping, the small
+design algebra) agrees with the oracle.  No kernel is launched here."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pandas as pd
+import pytest
+import torch
+
+from oracle import cna_oracle as orc
+from tests.golden import cases
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from cna_b200 import _lib
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "cna_b200.h")).read()
+    declared = set(re.findall(r"^(?:int|int64_t|const char \*)\s*\*?\s*(cna_\w+)\s*\(", header, flags=re.M))
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/cna_b200.h but not exported"
+    assert declared == set(_lib.EXPORTS)
+    assert lib.cna_abi_version() == 1
+    assert isinstance(lib.cna_last_error(), bytes)
+
+
+def test_no_cpu_fallback():
+    """Product code must fail loudly without a CUDA device / with CPU tensors."""
+    from cna_b200 import _lib
+    from cna_b200.tl import _graph
+    with pytest.raises(_lib.CnaError, match="CUDA tensor"):
+        _lib.absmax(torch.zeros(3, dtype=torch.float64), None, torch.zeros(1, dtype=torch.float64))
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="no CPU path"):
+            _graph.device()
+    src = "".join(open(os.path.join(ROOT, "cna_b200", d, f)).read()
+                  for d in ("", "tl") for f in os.listdir(os.path.join(ROOT, "cna_b200", d)) if f.endswith(".py"))
+    assert "oracle" not in src.replace("the oracle", ""), "product code must not import the oracle"
+
+
+def test_default_ks():
+    from cna_b200.tl._association import default_ks
+    assert list(default_ks(50)) == [1, 2, 3, 4]
+    assert list(default_ks(100)) == [2, 4, 6, 8]
+    assert list(default_ks(200)) == [4, 8, 12, 16]
+    assert list(default_ks(500)) == [10, 20, 30, 40]
+    for n in (10, 13, 24, 77, 333):
+        assert list(default_ks(n)) == list(orc.default_ks(n))
+
+
+def test_check_inputs_matches_oracle():
+    from cna_b200.tl._association import check_inputs
+    data = cases.demo_anndata()
+    meta = cases.demo_sample_meta()
+    y = meta.case.copy()
+    y.iloc[3] = np.nan
+    covs = meta[["male"]].copy()
+    covs.iloc[7, 0] = np.nan
+    extra = pd.concat([y, pd.Series([1.0], index=[99])])
+    for args in [(y, None, None, None), (y, meta.batch, covs, None), (extra, None, None, None),
+                 (y, None, covs, meta.batch)]:
+        a = check_inputs(data, args[0], "id", args[1], args[2], args[3], False)
+        b = orc.check_inputs(data, args[0], "id", args[1], args[2], args[3], False)
+        pd.testing.assert_series_equal(a[0], b[0])
+        np.testing.assert_array_equal(np.asarray(a[1]), np.asarray(b[1]))
+    for bad, exc in [((y.to_numpy(), None, None, None), TypeError), ((y, [1], None, None), TypeError),
+                     ((y, None, meta.male, None), TypeError), ((y, None, None, [1]), TypeError),
+                     ((y.iloc[:30], None, None, None), ValueError), ((y, meta.batch, None, meta.batch), ValueError)]:
+        with pytest.raises(exc):
+            check_inputs(data, bad[0], "id", bad[1], bad[2], bad[3], False)
+    few = y.copy()
+    few.iloc[:45] = np.nan
+    with pytest.raises(ValueError, match="fewer than 10"):
+        check_inputs(data, few, "id", None, None, None, False)
+    check_inputs(data, few, "id", None, None, None, True)
+
+
+def test_permutation_indices_are_bit_exact():
+    from cna_b200.tl import _stats
+    from cna_b200.tl._association import _PermutationJob
+    rng = np.random.default_rng(0)
+    B = rng.integers(0, 4, 57)
+    Y = rng.normal(size=57)
+    np.random.seed(11)
+    want = orc.conditional_permutation(B, Y, 300)
+    state_after = np.random.get_state()[1].copy()
+    np.random.seed(11)
+    bix = _stats.conditional_permutation_indices(B, 300)
+    np.testing.assert_array_equal(Y[bix], want)
+    np.testing.assert_array_equal(np.random.get_state()[1], state_after)  # same RNG consumption
+    np.random.seed(11)
+    np.testing.assert_array_equal(_PermutationJob(Y, B, None, 300).result(), bix.T)
+    # every column permutes within batches only
+    assert all((B[bix[:, k]] == B).all() and len(set(bix[:, k])) == 57 for k in range(300))
+    G = np.arange(57) // 3
+    Yg = (G % 2).astype(float)
+    np.random.seed(5)
+    want = orc.grouplevel_permutation(G, Yg, 200)
+    np.random.seed(5)
+    np.testing.assert_array_equal(Yg[_stats.grouplevel_permutation_indices(G, Yg, 200)], want)
+    assert _stats.grouplevel_permutation_indices(G, Y, 10) is None
+    np.random.seed(5)
+    with pytest.raises(TypeError):
+        _PermutationJob(Y, None, G, 10).result()
+
+
+def test_fdr_bookkeeping_matches_oracle():
+    from cna_b200.tl import _stats
+    rng = np.random.default_rng(3)
+    z = rng.normal(0, 0.2, 5000)
+    znull = np.abs(rng.normal(0, 0.08, (5000, 37)))
+    mx = max(np.abs(z).max(), 0.001)
+    t = np.arange(mx / 4, mx, mx / 400)
+    edges = _stats.threshold_edges(t)
+    np.testing.assert_array_equal(edges, orc.threshold_edges(t))
+    bins = np.concatenate([edges, [np.inf]])
+    hist = np.array([np.histogram(c ** 2, bins=bins)[0] for c in znull.T])
+    rank_hist = np.histogram(z ** 2, bins=bins)[0]
+    np.testing.assert_array_equal(_stats.tails_from_hist(hist), orc.tail_counts(t, znull, faithful=True))
+    np.testing.assert_allclose(_stats.fdr_from_counts(hist, rank_hist), orc.empirical_fdrs(z, znull, t), rtol=1e-15)
+
+
+def test_cumulative_projector_algebra():
+    """_nam.py:148 applies M = I - C.W cumulatively; resid_nam_device folds the product into one
+    rank-r update: prod_k (I - C W_k) = I - C W_cum."""
+    from cna_b200.tl import _nam
+    rng = np.random.default_rng(1)
+    n = 40
+    batches = rng.integers(0, 5, n)
+    covs = rng.normal(size=(n, 2))
+    C, nb = _nam.design_matrix(covs, batches, n)
+    Co, nbo = orc.design_matrix(covs, batches)
+    np.testing.assert_array_equal(C, Co)
+    assert nb == nbo == 5
+    Mprod, Wcum = np.eye(n), np.zeros((C.shape[1], n))
+    for ridge in (1e3, 10.0, 0.1, 0.0):
+        W = _nam.projector(C, nb, ridge)
+        np.testing.assert_allclose(W, orc.projector_stage(C, nb, ridge), rtol=1e-13)
+        Mprod = (np.eye(n) - C.dot(W)).dot(Mprod)
+        Wcum = Wcum + W - W.dot(C).dot(Wcum)
+        np.testing.assert_allclose(np.eye(n) - C.dot(Wcum), Mprod, atol=1e-12)
+
+
+def test_f_statistics_match_oracle():
+    from cna_b200.tl._association import _f_pvalues, _pick
+    rng = np.random.default_rng(2)
+    n, r, K = 60, 3, 50
+    U = np.linalg.qr(rng.normal(size=(n, n)))[0]
+    M = np.eye(n) - np.outer(U[:, -1], U[:, -1])
+    Z = rng.normal(size=(n, K))
+    ks = [2, 5, 9]
+    kk, pp, rr = orc.minp_stats_matrix(Z, M, U, ks, n, r)
+    Zc = M.dot(Z)
+    Zc = Zc / Zc.std(axis=0, ddof=1)
+    ssered = (Zc * Zc).sum(0)
+    ssefull = np.stack([((U[:, :k].dot(U[:, :k].T.dot(Zc)) - Zc) ** 2).sum(0) for k in ks], axis=1)
+    p, r2 = _f_pvalues(ssered, ssefull, ks, n, r)
+    k2, p2, r22 = _pick(p, r2, ks)
+    np.testing.assert_array_equal(k2, kk)
+    np.testing.assert_allclose(p2, pp, rtol=1e-12)
+    np.testing.assert_allclose(r22, rr, rtol=1e-12)
+
+
+def test_device_median_numpy_semantics():
+    from cna_b200.tl._nam import device_median
+    rng = np.random.default_rng(0)
+    for n in (1, 2, 7, 10, 1001):
+        v = rng.normal(size=n)
+        assert device_median(torch.as_tensor(v)) == np.median(v)
+    v[3] = np.nan
+    assert np.isnan(device_median(torch.as_tensor(v)))
+    assert np.isnan(device_median(torch.empty(0, dtype=torch.float64)))
+
+
+def test_batch_segments():
+    from cna_b200.tl._nam import _batch_segments
+    b = np.array([2.0, 0.0, 2.0, 1.0, 0.0, 2.0])
+    ub, order, off = _batch_segments(b)
+    assert list(ub) == [0.0, 1.0, 2.0] and list(off) == [0, 2, 3, 6]
+    assert [sorted(order[off[i]:off[i + 1]]) for i in range(3)] == [[1, 4], [3], [0, 2, 5]]
