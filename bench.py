@@ -45,7 +45,7 @@ CONFIGS = {
 }
 METRIC = "cells/sec through nam()+association(), 1M cells/200 samples/10k perms"
 # CPU sample: same samples / k / steps, cells and permutations scaled down by the same factor
-CPU_SAMPLE_SCALE = 40
+CPU_SAMPLE_SCALE = 20
 
 
 def parse_args():

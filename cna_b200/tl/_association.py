@@ -16,6 +16,7 @@ from .. import _lib
 from . import _nam, _stats
 from ._graph import _to_dev
 from ._out import select_output
+from ._timing import mark, report
 
 
 def check_inputs(data, y, sid_name, batches, covs, donorids, allow_low_sample_size):
@@ -98,6 +99,7 @@ class _PermutationJob:
         self._exc = None
 
         def work():
+            mark("perm thread start")
             try:
                 if donorids is not None:  # _association.py:80-83
                     bix = _stats.grouplevel_permutation_indices(donorids, y_std, Nnull)
@@ -106,6 +108,7 @@ class _PermutationJob:
                 self._out = None if bix is None else np.ascontiguousarray(bix.T, dtype=np.int32)
             except BaseException as exc:  # re-raised on the caller's thread
                 self._exc = exc
+            mark("perm thread done")
 
         self._thread = threading.Thread(target=work, name="cna-permutations", daemon=True)
         self._thread.start()
@@ -146,7 +149,9 @@ def _association(res, perms, Nnull=1000, local_test=True, show_progress=False):
 
     # ---- permutations: indices from the host RNG (bit-exact), everything else on the device ----
     Kl = min(1000, Nnull) if local_test else 0
+    mark("observed stats done; waiting for permutations")
     perm_d = _to_dev(perms.result())
+    mark("permutations uploaded")
     ld_y = _nam._round_up(max(Kl, 1), 4)
     ycond_d = torch.zeros((res.x.shape[1], ld_y), dtype=torch.float32, device=dev) if Kl else None
     ssered_d = torch.empty(Nnull, dtype=torch.float64, device=dev)
@@ -174,6 +179,7 @@ def _association(res, perms, Nnull=1000, local_test=True, show_progress=False):
         _lib.null_hist(res.x, n, ycond_d, Kl, edges_d, float(edges[0]), hist)
         _lib.obs_hist(res.ncorr, res.valid, edges_d, thr_d, obs[0], obs[1])
 
+    mark("null kernels launched")
     # ---- global p-value (:84-88) ----
     nullp, nullr2 = _f_pvalues(ssered_d.cpu().numpy(), ssefull_d.cpu().numpy(), ks, n, r)
     _, nullminps, nullr2s = _pick(nullp, nullr2, ks)
@@ -183,6 +189,7 @@ def _association(res, perms, Nnull=1000, local_test=True, show_progress=False):
         warnings.warn("global association p-value attained minimal possible value. "
                       "Consider increasing Nnull")
 
+    mark("global p done")
     if local_test:
         obs_h = obs.cpu().numpy()
         fdr_vals = _stats.fdr_from_counts(hist.cpu().numpy(), obs_h[0])  # _stats.py:64-83
@@ -208,8 +215,10 @@ def association(data, y, sid_name, batches=None, covs=None, donorids=None, ks=No
     bad = set(kwargs) - {"Nnull", "force_permute_all", "local_test", "seed"}
     if bad:  # the reference forwards **kwargs to _association(), which rejects anything else
         raise TypeError(f"_association() got an unexpected keyword argument '{sorted(bad)[0]}'")
+    mark("association() entered")
     batches, filter_samples = check_inputs(data, y, sid_name, batches, covs, donorids,
                                            allow_low_sample_size)
+    mark("check_inputs done")
     Nnull = kwargs.get("Nnull", 1000)
     local_test = kwargs.get("local_test", True)
 
@@ -230,6 +239,7 @@ def association(data, y, sid_name, batches=None, covs=None, donorids=None, ks=No
     print("computing NAM", file=out)
     stn = _nam._nam_device(data, sid_name, nsteps=nsteps, show_progress=show_progress)
 
+    mark("diffusion launched")
     if kwargs.get("seed") is not None:
         np.random.seed(kwargs["seed"])  # :15-16
     if max(ks_eff) + r >= n:  # :29-33 (the reference raises this after seeding, before any draw)
@@ -242,13 +252,16 @@ def association(data, y, sid_name, batches=None, covs=None, donorids=None, ks=No
 
     # ---- QC, residualisation, Gram + SVD ----
     _nam._qc_device(stn, batches, show_progress=show_progress)
+    mark("QC done (first sync)")
     colmap = stn.labels.get_indexer(sids)  # NAM.reindex(y.index)[filter_samples], :178-181
     res = _nam.resid_nam_device(stn, colmap, covs_f, batches_f, y_std, ridges=ridges,
                                 show_progress=show_progress)
+    mark("resid pass done")
     res.y_std = y_std
     res.ks = ks_eff
     res.U, svs, res.G = _nam.gram_svd(res.x, n)  # _nam.py:163
 
+    mark("gram + svd done")
     print("performing association test", file=out)
     core = _association(res, perms, Nnull=Nnull, local_test=local_test, show_progress=show_progress)
 
@@ -268,10 +281,13 @@ def association(data, y, sid_name, batches=None, covs=None, donorids=None, ks=No
         pmin = np.fmin.accumulate(core.fdrs.fdr.to_numpy())  # Series.min() skips NaN
     _lib.cell_fdr(res.ncorr, res.valid, _to_dev(thr), _to_dev(pmin), coef_d, fdr_d)
     both = torch.stack([coef_d, fdr_d]).cpu().numpy()
+    mark("results on host")
     data.obs[key_added] = both[0]
     if core.fdrs is not None:
         data.obs[f"{key_added}_fdr"] = both[1]
     if not return_full:
+        mark("obs written")
+        report()
         return core.p
 
     # ---- full result surface (_nam.py:168-175, _association.py:223-225) ----

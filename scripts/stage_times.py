@@ -1,0 +1,23 @@
+"""Wall-clock stage breakdown of association() (CNA_B200_TIMING=1) at a bench configuration."""
+import os
+import sys
+import warnings
+
+os.environ["CNA_B200_TIMING"] = "1"
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+import cna_b200 as cna  # noqa: E402
+from cna_b200 import synth  # noqa: E402
+from bench import CONFIGS  # noqa: E402
+
+cfg = sys.argv[1] if len(sys.argv) > 1 else "C"
+N, S, k, s, K = CONFIGS[cfg]
+data, meta = synth.make_dataset(N, S, k, seed=0)
+kw = dict(y=meta.case, sid_name="id", batches=meta.batch, covs=meta[["age"]], nsteps=s, Nnull=K, seed=0)
+warnings.simplefilter("ignore")
+h = cna.tl.to_device(data)
+for mode, obj in (("resident", h), ("resident", h), ("host", data), ("host", data)):
+    torch.cuda.synchronize()
+    print("----", mode)
+    cna.tl.association(obj, **kw)
