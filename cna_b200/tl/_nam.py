@@ -13,6 +13,7 @@ import torch
 from .. import _lib
 from ._graph import get_connectivity, graph_of, sample_codes, device, _to_dev  # noqa: F401
 from ._out import select_output
+from ._timing import mark
 
 DEFAULT_RIDGES = [1e5, 1e4, 1e3, 1e2, 1e1, 1e0, 1e-1, 1e-2, 1e-3, 1e-4, 0]
 
@@ -244,8 +245,10 @@ def gram_svd(x, n):
     G = torch.zeros((n, n), dtype=torch.float64, device=x.device)
     _lib.gram(x, n, G)
     Gh = G.cpu().numpy()
+    mark("gram on host")
     Gh = (Gh + Gh.T) / 2  # the kernel fills both triangles from the same products; keep it exact
     U, svs, _ = np.linalg.svd(Gh)
+    mark("svd done")
     return U, svs, Gh
 
 

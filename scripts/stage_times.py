@@ -17,7 +17,16 @@ data, meta = synth.make_dataset(N, S, k, seed=0)
 kw = dict(y=meta.case, sid_name="id", batches=meta.batch, covs=meta[["age"]], nsteps=s, Nnull=K, seed=0)
 warnings.simplefilter("ignore")
 h = cna.tl.to_device(data)
-for mode, obj in (("resident", h), ("resident", h), ("host", data), ("host", data)):
+from bench import pin_graph  # noqa: E402
+undo = pin_graph(data.obsp["connectivities"])
+for mode, obj in (("resident", h), ("resident", h), ("host-pinned", data), ("host-pinned", data), ("resident", h)):
     torch.cuda.synchronize()
     print("----", mode)
     cna.tl.association(obj, **kw)
+if len(sys.argv) > 2:
+    from threadpoolctl import threadpool_limits
+    with threadpool_limits(limits=int(sys.argv[2])):
+        for mode, obj in (("resident, blas threads=" + sys.argv[2], h), ("host-pinned, blas threads=" + sys.argv[2], data)):
+            torch.cuda.synchronize()
+            print("----", mode)
+            cna.tl.association(obj, **kw)
