@@ -287,10 +287,10 @@ def run_ours(args):
         return ms
 
     if world > 1:
-        from cna_b200.parallel import association_sharded, shard_to_device
-        handle = shard_to_device(data, "id")
-        step_dev = lambda: association_sharded(handle, **kw)  # noqa: E731
-        step_e2e = lambda: association_sharded(shard_to_device(data, "id"), **kw)  # noqa: E731
+        from cna_b200.sharded import shard_to_device
+        handle = shard_to_device(data)
+        step_dev = lambda: cna.tl.association(handle, **kw)  # noqa: E731
+        step_e2e = lambda: cna.tl.association(shard_to_device(data), **kw)  # noqa: E731
     else:
         handle = cna.tl.to_device(data)
         step_dev = lambda: cna.tl.association(handle, **kw)  # noqa: E731
@@ -314,12 +314,13 @@ def run_ours(args):
                 step_e2e()
             ms_e2e = timed(step_e2e, args.steps)
             undo()
-            h2d = A.data.nbytes + A.indices.nbytes + A.indptr.nbytes + 4 * N
+            h2d = (A.data.nbytes + A.indices.nbytes + A.indptr.nbytes) + 4 * N * world
             d2h = 2 * 8 * N + 8 * n * n + 8 * K * 5
             e2e = {"value": N * args.steps / (ms_e2e * 1e-3), "unit": "cells/s", "ms_per_step": ms_e2e / args.steps,
                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)}
 
     if rank != 0:
+        dist.destroy_process_group()
         return
     peaks = measured_peaks()
     roofs = rooflines(prof, args.steps, N, S, n, nnz, K, Kl, s_steps, peaks)

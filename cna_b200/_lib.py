@@ -63,10 +63,10 @@ class ResidArgs(ctypes.Structure):
 # name -> argtypes; every function returns int except the three bookkeeping calls
 _SIGNATURES = {
     "cna_graph_colsum": [_VP, _VP, _VP, _INT, _I64, _VP, _VP],
-    "cna_graph_scale": [_VP, _VP, _VP, _INT, _I64, _VP, _DBL, _VP, _VP, _INT, _VP],
-    "cna_diffuse_onehot": [_VP, _VP, _VP, _VP, _VP, _I64, _INT, _VP, _I64, _VP],
-    "cna_diffuse_step_f32": [_VP, _VP, _VP, _VP, _VP, _VP, _I64, _INT, _I64, _VP],
-    "cna_diffuse_step_f64": [_VP, _VP, _VP, _VP, _VP, _VP, _I64, _INT, _I64, _VP],
+    "cna_graph_scale": [_VP, _VP, _VP, _INT, _I64, _VP, _DBL, _VP, _VP, _INT, _I64, _VP],
+    "cna_diffuse_onehot": [_VP, _VP, _VP, _VP, _VP, _I64, _INT, _VP, _I64, _I64, _VP],
+    "cna_diffuse_step_f32": [_VP, _VP, _VP, _VP, _VP, _VP, _I64, _INT, _I64, _I64, _VP],
+    "cna_diffuse_step_f64": [_VP, _VP, _VP, _VP, _VP, _VP, _I64, _INT, _I64, _I64, _VP],
     "cna_row_kurtosis": [_VP, _I64, _I64, _INT, _VP, _VP, _VP],
     "cna_batch_kurtosis": [_VP, _I64, _I64, _VP, _VP, _VP, _INT, _INT, _VP, _VP],
     "cna_resid_pass": [ctypes.POINTER(ResidArgs), _VP],
@@ -161,31 +161,32 @@ def graph_colsum(indptr, indices, data, colsum):
                                    _ptr(colsum, torch.float64, "colsum"), _stream())
 
 
-def graph_scale(indptr, indices, data, colsum, self_weight, vals, diag):
+def graph_scale(indptr, indices, data, colsum, self_weight, vals, diag, row_offset=0):
     is64 = data.dtype == torch.float64
     out64 = vals.dtype == torch.float64
     _call("cna_graph_scale", _ptr(indptr, torch.int32, "indptr"), _ptr(indices, torch.int32, "indices"),
                                   _ptr(data, data.dtype, "data"), int(is64), indptr.numel() - 1,
                                   _ptr(colsum, torch.float64, "colsum"), float(self_weight),
                                   _ptr(vals, vals.dtype, "vals"), _ptr(diag, vals.dtype, "diag"),
-                                  int(out64), _stream())
+                                  int(out64), int(row_offset), _stream())
 
 
-def diffuse_onehot(indptr, indices, vals, diag, code, n_samples, out):
+def diffuse_onehot(indptr, indices, vals, diag, code, n_samples, out, n_rows=None, row_offset=0):
     _call("cna_diffuse_onehot", _ptr(indptr, torch.int32, "indptr"), _ptr(indices, torch.int32, "indices"),
                                      _ptr(vals, torch.float32, "vals"), _ptr(diag, torch.float32, "diag"),
-                                     _ptr(code, torch.int32, "code"), out.shape[0], int(n_samples),
-                                     _ptr(out, torch.float32, "out"), out.shape[1], _stream())
+                                     _ptr(code, torch.int32, "code"), out.shape[0] if n_rows is None else int(n_rows),
+                                     int(n_samples), _ptr(out, torch.float32, "out"), out.shape[1], int(row_offset),
+                                     _stream())
 
 
-def diffuse_step(indptr, indices, vals, diag, src, dst, n_cols):
+def diffuse_step(indptr, indices, vals, diag, src, dst, n_cols, n_rows=None, row_offset=0):
     if src.dtype == torch.float32:
         name, dt = "cna_diffuse_step_f32", torch.float32
     else:
         name, dt = "cna_diffuse_step_f64", torch.float64
     _call(name, _ptr(indptr, torch.int32, "indptr"), _ptr(indices, torch.int32, "indices"),
           _ptr(vals, dt, "vals"), _ptr(diag, dt, "diag"), _ptr(src, dt, "src"), _ptr(dst, dt, "dst"),
-          src.shape[0], int(n_cols), src.shape[1], _stream())
+          dst.shape[0] if n_rows is None else int(n_rows), int(n_cols), src.shape[1], int(row_offset), _stream())
 
 
 def row_kurtosis(s, n_samples, inv_count, kurt):

@@ -32,14 +32,14 @@ template <typename T, typename O>
 __global__ void scale_kernel(const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices,
                              const T *__restrict__ data, int64_t n_rows,
                              const double *__restrict__ colsum, double w, O *__restrict__ vals,
-                             O *__restrict__ diag) {
+                             O *__restrict__ diag, int64_t row_offset) {
     int64_t row = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
     if (row >= n_rows) return;
     int e0 = indptr[row], e1 = indptr[row + 1];
     for (int e = e0 + lane; e < e1; e += 32)
         vals[e] = O(double(data[e]) / (colsum[indices[e]] + w));
-    if (lane == 0) diag[row] = O(w / (colsum[row] + w));
+    if (lane == 0) diag[row] = O(w / (colsum[row + row_offset] + w));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(256)
 onehot_step_kernel(const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices,
                    const float *__restrict__ vals, const float *__restrict__ diag,
                    const int32_t *__restrict__ code, int64_t n_rows, float *__restrict__ out,
-                   int64_t ld) {
+                   int64_t ld, int64_t row_offset) {
     int64_t row = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
     if (row >= n_rows) return;
@@ -79,7 +79,7 @@ onehot_step_kernel(const int32_t *__restrict__ indptr, const int32_t *__restrict
         }
     }
     {  // self term is added last (_nam.py:33: a.dot(...) + w*s/colsums)
-        int ct = code[row];
+        int ct = code[row + row_offset];
         float d = diag[row];
         if ((ct & 31) == lane) {
 #pragma unroll
@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(256)
 spmm_f32_kernel(const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices,
                 const float *__restrict__ vals, const float *__restrict__ diag,
                 const float *__restrict__ in, float *__restrict__ out, int64_t n_rows, int nvec,
-                int64_t ld4) {
+                int64_t ld4, int64_t in_row_offset) {
     int64_t row = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
     if (row >= n_rows) return;
@@ -162,7 +162,7 @@ spmm_f32_kernel(const int32_t *__restrict__ indptr, const int32_t *__restrict__ 
     for (int q = 0; q < NV; ++q) {
         int c = lane + 32 * q;
         if (c < nvec) {
-            float4 x = ldg4(in4 + row * ld4 + c);
+            float4 x = ldg4(in4 + (row + in_row_offset) * ld4 + c);
             acc[q].x = fmaf(d, x.x, acc[q].x);
             acc[q].y = fmaf(d, x.y, acc[q].y);
             acc[q].z = fmaf(d, x.z, acc[q].z);
@@ -177,7 +177,8 @@ template <typename T>
 __global__ void spmm_generic_kernel(const int32_t *__restrict__ indptr,
                                     const int32_t *__restrict__ indices, const T *__restrict__ vals,
                                     const T *__restrict__ diag, const T *__restrict__ in,
-                                    T *__restrict__ out, int64_t n_rows, int n_cols, int64_t ld) {
+                                    T *__restrict__ out, int64_t n_rows, int n_cols, int64_t ld,
+                                    int64_t in_row_offset) {
     int64_t row = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
     if (row >= n_rows) return;
@@ -186,7 +187,7 @@ __global__ void spmm_generic_kernel(const int32_t *__restrict__ indptr,
     for (int c = lane; c < n_cols; c += 32) {
         T acc = T(0);
         for (int e = e0; e < e1; ++e) acc += vals[e] * in[int64_t(indices[e]) * ld + c];
-        out[row * ld + c] = acc + d * in[row * ld + c];
+        out[row * ld + c] = acc + d * in[(row + in_row_offset) * ld + c];
     }
 }
 
@@ -243,7 +244,7 @@ int cna_graph_colsum(const int32_t *indptr, const int32_t *indices, const void *
 
 int cna_graph_scale(const int32_t *indptr, const int32_t *indices, const void *data, int is_f64,
                     int64_t n_rows, const double *colsum, double self_weight, void *vals,
-                    void *diag, int out_f64, void *stream) {
+                    void *diag, int out_f64, int64_t row_offset, void *stream) {
     CNA_REQUIRE(n_rows >= 0 && indptr && colsum && vals && diag, "cna_graph_scale: bad arguments");
     if (n_rows == 0) return CNA_OK;
     unsigned grid = warp_rows_grid(n_rows, 256);
@@ -251,7 +252,7 @@ int cna_graph_scale(const int32_t *indptr, const int32_t *indices, const void *d
 #define CNA_SCALE(T, O)                                                                       \
     scale_kernel<T, O><<<grid, 256, 0, st>>>(indptr, indices, static_cast<const T *>(data),   \
                                               n_rows, colsum, self_weight,                    \
-                                              static_cast<O *>(vals), static_cast<O *>(diag))
+                                              static_cast<O *>(vals), static_cast<O *>(diag), row_offset)
     if (is_f64 && out_f64) CNA_SCALE(double, double);
     else if (is_f64) CNA_SCALE(double, float);
     else if (out_f64) CNA_SCALE(float, double);
@@ -263,7 +264,7 @@ int cna_graph_scale(const int32_t *indptr, const int32_t *indices, const void *d
 
 int cna_diffuse_onehot(const int32_t *indptr, const int32_t *indices, const float *vals,
                        const float *diag, const int32_t *code, int64_t n_rows, int n_samples,
-                       float *out, int64_t ld, void *stream) {
+                       float *out, int64_t ld, int64_t row_offset, void *stream) {
     CNA_REQUIRE(n_rows >= 0 && n_samples > 0 && ld >= n_samples, "cna_diffuse_onehot: bad shape");
     CNA_REQUIRE(ld <= 1024, "cna_diffuse_onehot: at most 1024 sample columns (got ld=%lld)",
                 (long long)ld);
@@ -272,7 +273,7 @@ int cna_diffuse_onehot(const int32_t *indptr, const int32_t *indices, const floa
     cudaStream_t st = as_stream(stream);
     int nq = int((ld + 31) / 32);
 #define CNA_ONEHOT(NQ) \
-    onehot_step_kernel<NQ><<<grid, 256, 0, st>>>(indptr, indices, vals, diag, code, n_rows, out, ld)
+    onehot_step_kernel<NQ><<<grid, 256, 0, st>>>(indptr, indices, vals, diag, code, n_rows, out, ld, row_offset)
     if (nq <= 2) CNA_ONEHOT(2);
     else if (nq <= 4) CNA_ONEHOT(4);
     else if (nq <= 8) CNA_ONEHOT(8);
@@ -285,7 +286,7 @@ int cna_diffuse_onehot(const int32_t *indptr, const int32_t *indices, const floa
 
 int cna_diffuse_step_f32(const int32_t *indptr, const int32_t *indices, const float *vals,
                          const float *diag, const float *in, float *out, int64_t n_rows,
-                         int n_cols, int64_t ld, void *stream) {
+                         int n_cols, int64_t ld, int64_t in_row_offset, void *stream) {
     CNA_REQUIRE(n_rows >= 0 && n_cols > 0 && ld >= n_cols, "cna_diffuse_step_f32: bad shape");
     CNA_REQUIRE(in != out, "cna_diffuse_step_f32: in-place step is not supported");
     if (n_rows == 0) return CNA_OK;
@@ -296,7 +297,7 @@ int cna_diffuse_step_f32(const int32_t *indptr, const int32_t *indices, const fl
     if (vec_ok && nvec <= 128) {
         int64_t ld4 = ld / 4;
 #define CNA_SPMM(NV) \
-    spmm_f32_kernel<NV><<<grid, 256, 0, st>>>(indptr, indices, vals, diag, in, out, n_rows, nvec, ld4)
+    spmm_f32_kernel<NV><<<grid, 256, 0, st>>>(indptr, indices, vals, diag, in, out, n_rows, nvec, ld4, in_row_offset)
         if (nvec <= 32) CNA_SPMM(1);
         else if (nvec <= 64) CNA_SPMM(2);
         else if (nvec <= 96) CNA_SPMM(3);
@@ -305,7 +306,7 @@ int cna_diffuse_step_f32(const int32_t *indptr, const int32_t *indices, const fl
         CNA_LAUNCHED("spmm_f32_kernel");
     } else {
         spmm_generic_kernel<float><<<grid, 256, 0, st>>>(indptr, indices, vals, diag, in, out,
-                                                         n_rows, n_cols, ld);
+                                                         n_rows, n_cols, ld, in_row_offset);
         CNA_LAUNCHED("spmm_generic_kernel<float>");
     }
     return CNA_OK;
@@ -313,13 +314,13 @@ int cna_diffuse_step_f32(const int32_t *indptr, const int32_t *indices, const fl
 
 int cna_diffuse_step_f64(const int32_t *indptr, const int32_t *indices, const double *vals,
                          const double *diag, const double *in, double *out, int64_t n_rows,
-                         int n_cols, int64_t ld, void *stream) {
+                         int n_cols, int64_t ld, int64_t in_row_offset, void *stream) {
     CNA_REQUIRE(n_rows >= 0 && n_cols > 0 && ld >= n_cols, "cna_diffuse_step_f64: bad shape");
     CNA_REQUIRE(in != out, "cna_diffuse_step_f64: in-place step is not supported");
     if (n_rows == 0) return CNA_OK;
     unsigned grid = warp_rows_grid(n_rows, 256);
     spmm_generic_kernel<double><<<grid, 256, 0, as_stream(stream)>>>(indptr, indices, vals, diag,
-                                                                     in, out, n_rows, n_cols, ld);
+                                                                     in, out, n_rows, n_cols, ld, in_row_offset);
     CNA_LAUNCHED("spmm_generic_kernel<double>");
     return CNA_OK;
 }

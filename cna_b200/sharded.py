@@ -1,0 +1,98 @@
+"""Cell-axis sharding of the hot path across the GPUs of one box.
+
+One process per GPU (``torchrun``); rank g owns a contiguous block of cells: its rows of the kNN
+CSR (column indices stay global), of the diffusion state and of the residualised NAM.  Everything
+sample-sized is replicated.  The data-path exchanges are
+
+  * all-reduce of the graph's column sums (once per graph),
+  * an all-gather of the state before every diffusion step after the first (with the
+    sample-contiguous cell order of real data the kNN halo is ~every other shard's rows, so the
+    halo exchange degenerates to an all-gather),
+  * all-gathers of one float64 per cell for the global medians (auto-stop, QC, ridge loop),
+  * all-reduce of the n x n Gram, of max|ncorr| and of the (Kl x T) null / observed histograms,
+  * a broadcast of the permutation indices from rank 0 (the legacy RNG stream is drawn once),
+  * an all-gather of the per-cell outputs, so every rank ends with the full ``data.obs`` columns.
+
+``Comm`` is backend-agnostic (NCCL on GPUs; gloo for the CPU tests of the host logic).
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n_total, world, rank):
+    """Contiguous row blocks of equal allocation ``rows_per = ceil(N / world)``; only the last
+    non-empty block may be short.  Returns (row0, row1, rows_per)."""
+    rows_per = (n_total + world - 1) // world
+    r0 = min(rank * rows_per, n_total)
+    r1 = min(r0 + rows_per, n_total)
+    return r0, r1, rows_per
+
+
+def slice_csr(A, r0, r1):
+    """Rows [r0, r1) of a scipy CSR as (indptr rebased to 0, indices, data) without copying more
+    than the slice."""
+    A = A.tocsr()
+    e0, e1 = int(A.indptr[r0]), int(A.indptr[r1])
+    indptr = (A.indptr[r0:r1 + 1] - A.indptr[r0]).astype(np.int32)
+    return indptr, A.indices[e0:e1], A.data[e0:e1]
+
+
+class Comm:
+    """Thin wrapper over a torch.distributed process group."""
+
+    def __init__(self, group=None):
+        if not dist.is_initialized():
+            raise RuntimeError("torch.distributed is not initialised (launch with torchrun)")
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.backend = dist.get_backend(group)
+
+    def all_reduce(self, t, op="sum"):
+        dist.all_reduce(t, op=dist.ReduceOp.SUM if op == "sum" else dist.ReduceOp.MAX, group=self.group)
+        return t
+
+    def all_gather_rows(self, local):
+        """local: [rows_per, ...] on every rank -> [world * rows_per, ...] (rank-major)."""
+        local = local.contiguous()
+        out = torch.empty((self.world * local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype,
+                          device=local.device)
+        if self.backend == "nccl":
+            dist.all_gather_into_tensor(out, local, group=self.group)
+        else:
+            dist.all_gather(list(out.chunk(self.world, dim=0)), local, group=self.group)
+        return out
+
+    def broadcast(self, t, src=0):
+        dist.broadcast(t, src=src, group=self.group)
+        return t
+
+    def barrier(self):
+        dist.barrier(group=self.group)
+
+
+class ShardedData:
+    """This rank's shard of an AnnData-like object, graph resident on its GPU.  Accepted by
+    ``cna_b200.tl.association`` / ``nam`` in place of ``data``; results are written to the full
+    ``data.obs`` on every rank."""
+
+    def __init__(self, data, comm=None):
+        from .tl._graph import DeviceGraph, get_connectivity
+        self._host = data
+        self.comm = comm or Comm()
+        A = get_connectivity(data)
+        n_total = A.shape[0]
+        r0, r1, rows_per = shard_bounds(n_total, self.comm.world, self.comm.rank)
+        self.graph = DeviceGraph(A, shard=(self.comm, r0, r1, rows_per))
+        self.obsp = getattr(data, "obsp", None)
+        self.uns = getattr(data, "uns", None)
+        self._codes = {}
+
+    @property
+    def obs(self):
+        return self._host.obs
+
+
+def shard_to_device(data, comm=None):
+    return data if isinstance(data, ShardedData) else ShardedData(data, comm)

@@ -149,8 +149,14 @@ def _association(res, perms, Nnull=1000, local_test=True, show_progress=False):
 
     # ---- permutations: indices from the host RNG (bit-exact), everything else on the device ----
     Kl = min(1000, Nnull) if local_test else 0
+    comm = res.comm
     mark("observed stats done; waiting for permutations")
-    perm_d = _to_dev(perms.result())
+    if perms is not None:
+        perm_d = _to_dev(perms.result())
+    else:  # a shard other than rank 0: the indices are drawn once, by rank 0
+        perm_d = torch.empty((Nnull, n), dtype=torch.int32, device=dev)
+    if comm is not None:
+        comm.broadcast(perm_d, src=0)
     mark("permutations uploaded")
     ld_y = _nam._round_up(max(Kl, 1), 4)
     ycond_d = torch.zeros((res.x.shape[1], ld_y), dtype=torch.float32, device=dev) if Kl else None
@@ -169,6 +175,8 @@ def _association(res, perms, Nnull=1000, local_test=True, show_progress=False):
         print("computing neighborhood-level FDRs", file=out)
         mx = torch.zeros(1, dtype=torch.float64, device=dev)
         _lib.absmax(res.ncorr, res.valid, mx)
+        if comm is not None:
+            comm.all_reduce(mx, op="max")
         maxcorr = max(float(mx.item()), 0.001)  # :101
         thresholds = np.arange(maxcorr / 4, maxcorr, maxcorr / 400)  # :102
         edges = _stats.threshold_edges(thresholds)
@@ -178,6 +186,9 @@ def _association(res, perms, Nnull=1000, local_test=True, show_progress=False):
         obs = torch.zeros((2, T), dtype=torch.int32, device=dev)
         _lib.null_hist(res.x, n, ycond_d, Kl, edges_d, float(edges[0]), hist)
         _lib.obs_hist(res.ncorr, res.valid, edges_d, thr_d, obs[0], obs[1])
+        if comm is not None:  # counts over all shards
+            comm.all_reduce(hist)
+            comm.all_reduce(obs)
 
     mark("null kernels launched")
     # ---- global p-value (:84-88) ----
@@ -248,7 +259,10 @@ def association(data, y, sid_name, batches=None, covs=None, donorids=None, ks=No
             f"Currently it is {max(ks_eff) + r} while n is {n}. Either reduce the number of covariates "
             "or reduce the number of PCs to consider using the optional argument ks=[...].")
     perm_batches = np.ones(n) if kwargs.get("force_permute_all", False) else batches_f  # :17-18
-    perms = _PermutationJob(y_std, perm_batches, donor_f, Nnull)
+    comm = stn.comm
+    if comm is not None and return_full:
+        raise NotImplementedError("return_full=True is not supported on a cell-axis shard")
+    perms = _PermutationJob(y_std, perm_batches, donor_f, Nnull) if comm is None or comm.rank == 0 else None
 
     # ---- QC, residualisation, Gram + SVD ----
     _nam._qc_device(stn, batches, show_progress=show_progress)
@@ -259,7 +273,7 @@ def association(data, y, sid_name, batches=None, covs=None, donorids=None, ks=No
     mark("resid pass done")
     res.y_std = y_std
     res.ks = ks_eff
-    res.U, svs, res.G = _nam.gram_svd(res.x, n)  # _nam.py:163
+    res.U, svs, res.G = _nam.gram_svd(res.x, n, comm=comm)  # _nam.py:163
 
     mark("gram + svd done")
     print("performing association test", file=out)
@@ -280,7 +294,12 @@ def association(data, y, sid_name, batches=None, covs=None, donorids=None, ks=No
         thr = core.fdrs.threshold.to_numpy()
         pmin = np.fmin.accumulate(core.fdrs.fdr.to_numpy())  # Series.min() skips NaN
     _lib.cell_fdr(res.ncorr, res.valid, _to_dev(thr), _to_dev(pmin), coef_d, fdr_d)
-    both = torch.stack([coef_d, fdr_d]).cpu().numpy()
+    both = torch.stack([coef_d, fdr_d])
+    if comm is not None:  # every rank ends with the full per-cell columns
+        pad = torch.zeros((2, stn.rows_per), dtype=torch.float64, device=dev)
+        pad[:, :N] = both
+        both = comm.all_gather_rows(pad.t().contiguous())[: len(data.obs)].t()
+    both = both.cpu().numpy()
     mark("results on host")
     data.obs[key_added] = both[0]
     if core.fdrs is not None:

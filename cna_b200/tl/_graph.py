@@ -46,19 +46,28 @@ class DeviceGraph:
     normalised edge values ``A_ij / (colsum_j + w)`` and the diagonal ``w / (colsum_i + w)`` are
     derived per (self_weight, dtype) and cached."""
 
-    def __init__(self, A):
+    def __init__(self, A, shard=None):
+        """``shard`` = (comm, row0, row1, rows_per) keeps only rows [row0, row1) on this device
+        (cell-axis sharding, ``cna_b200.sharded``); column indices stay global."""
         if not sp.issparse(A):
             raise TypeError("connectivities must be a scipy sparse matrix")
         A = A.tocsr()
         if A.shape[0] != A.shape[1]:
             raise ValueError("connectivities must be square")
-        if A.nnz >= 2 ** 31:
-            raise ValueError("graphs with >= 2^31 stored edges must be sharded across GPUs")
-        self.n = A.shape[0]
-        self.nnz = int(A.nnz)
-        self.indptr = _to_dev(A.indptr, torch.int32)
-        self.indices = _to_dev(A.indices, torch.int32)
-        data = A.data
+        self.n_total = A.shape[0]
+        if shard is None:
+            self.comm, self.row0, self.rows_per = None, 0, A.shape[0]
+            indptr, indices, data = A.indptr, A.indices, A.data
+        else:
+            from ..sharded import slice_csr
+            self.comm, self.row0, row1, self.rows_per = shard
+            indptr, indices, data = slice_csr(A, self.row0, row1)
+        if len(indices) >= 2 ** 31:
+            raise ValueError("graphs with >= 2^31 stored edges per GPU must be sharded further")
+        self.n = len(indptr) - 1  # rows held by this device
+        self.nnz = int(len(indices))
+        self.indptr = _to_dev(indptr, torch.int32)
+        self.indices = _to_dev(indices, torch.int32)
         if data.dtype not in (np.float32, np.float64):
             data = data.astype(np.float64)
         self.data = _to_dev(data)
@@ -67,11 +76,14 @@ class DeviceGraph:
     def scaled(self, self_weight=1, dtype=torch.float32):
         key = (float(self_weight), dtype)
         if key not in self._scaled:
-            colsum = torch.zeros(self.n, dtype=torch.float64, device=self.indptr.device)
+            colsum = torch.zeros(self.n_total, dtype=torch.float64, device=self.indptr.device)
             _lib.graph_colsum(self.indptr, self.indices, self.data, colsum)
+            if self.comm is not None:  # column sums need every shard's rows (_nam.py:28)
+                self.comm.all_reduce(colsum)
             vals = torch.empty(self.nnz, dtype=dtype, device=colsum.device)
             diag = torch.empty(self.n, dtype=dtype, device=colsum.device)
-            _lib.graph_scale(self.indptr, self.indices, self.data, colsum, self_weight, vals, diag)
+            _lib.graph_scale(self.indptr, self.indices, self.data, colsum, self_weight, vals, diag,
+                             row_offset=self.row0)
             self._scaled[key] = (vals, diag)
         return self._scaled[key]
 
@@ -102,8 +114,9 @@ def to_device(data):
 
 
 def graph_of(data):
-    if isinstance(data, ResidentData):
-        return data.graph
+    g = getattr(data, "graph", None)
+    if isinstance(g, DeviceGraph):  # ResidentData / ShardedData
+        return g
     return DeviceGraph(get_connectivity(data))
 
 

@@ -22,13 +22,28 @@ def _round_up(x, m):
     return (x + m - 1) // m * m
 
 
-def device_median(t):
+def device_median(t, valid=None, comm=None, rows_per=None):
     """``np.median`` of a 1-D device tensor: mean of the two middle order statistics, NaN if any
-    element is NaN.  One device sort and one 24-byte copy back."""
-    n = t.numel()
+    (valid) element is NaN.  ``valid`` (bool/uint8 mask) restricts the median to a subset; with a
+    ``comm`` the median is over the concatenation of every rank's values (all-gather of one padded
+    float64 vector).  One device sort and one small copy back."""
+    t = t.double()
+    n_valid = torch.tensor(float(t.numel()), dtype=torch.float64, device=t.device)
+    if valid is not None:
+        vb = valid.bool()
+        t = torch.where(vb, t, torch.full_like(t, float("inf")))  # dropped cells sort to the end
+        n_valid = vb.sum().double()
+    if comm is not None:
+        pad = torch.full((rows_per,), float("inf"), dtype=torch.float64, device=t.device)
+        pad[: t.numel()] = t
+        t = comm.all_gather_rows(pad)
+        n_valid = comm.all_reduce(n_valid.reshape(1)).reshape(())
+    if t.numel() == 0:
+        return float("nan")
+    v, _ = torch.sort(t)  # NaNs sort last, after +inf
+    n = int(n_valid.item())
     if n == 0:
         return float("nan")
-    v, _ = torch.sort(t)  # NaNs sort last
     lo, hi, last = torch.stack([v[(n - 1) // 2], v[n // 2], v[-1]]).tolist()
     if last != last:
         return float("nan")
@@ -94,6 +109,9 @@ class NamState:
         self.qc_threshold = None
         self.medkurt = []
         self.nsteps = 0
+        self.comm = None  # set for cell-axis shards (cna_b200.sharded)
+        self.row0 = 0
+        self.rows_per = s.shape[0]
 
     @property
     def N(self):
@@ -113,15 +131,19 @@ def _nam_device(data, sid_name, nsteps=None, maxnsteps=15, self_weight=1, show_p
     out = select_output(show_progress)
     g = graph_of(data)
     labels, codes, counts = sample_codes(data, sid_name)
-    if codes.numel() != g.n:
-        raise ValueError("data.obs and the connectivities graph disagree on the number of cells")
     S = len(labels)
     ld = _round_up(S, 8)
     dev = codes.device
+    comm = g.comm
+    if codes.numel() != g.n_total:
+        raise ValueError("data.obs and the connectivities graph disagree on the number of cells")
     vals, diag = g.scaled(self_weight, torch.float32)
-    cur = torch.empty((g.n, ld), dtype=torch.float32, device=dev)
-    nxt = torch.zeros((g.n, ld), dtype=torch.float32, device=dev)
-    st = NamState(cur, S, labels, counts, data.obs.index)
+    # a shard allocates rows_per rows (equal on every rank, so the state can be all-gathered) and
+    # touches only its first g.n
+    cur = torch.zeros((g.rows_per, ld), dtype=torch.float32, device=dev)
+    nxt = torch.zeros((g.rows_per, ld), dtype=torch.float32, device=dev)
+    st = NamState(cur[: g.n], S, labels, counts, data.obs.index[g.row0: g.row0 + g.n])
+    st.comm, st.row0, st.rows_per = comm, g.row0, g.rows_per
     need_stats = nsteps is None or show_progress
     kurt = torch.empty(g.n, dtype=torch.float64, device=dev) if need_stats else None
     old = None
@@ -130,19 +152,21 @@ def _nam_device(data, sid_name, nsteps=None, maxnsteps=15, self_weight=1, show_p
     for i in range(maxnsteps):
         print("\ttaking step", i + 1, file=out)
         if i == 0:
-            _lib.diffuse_onehot(g.indptr, g.indices, vals, diag, codes, S, cur)
+            _lib.diffuse_onehot(g.indptr, g.indices, vals, diag, codes, S, cur, n_rows=g.n, row_offset=g.row0)
         else:
             if show_progress:
                 old = cur.clone()
-            _lib.diffuse_step(g.indptr, g.indices, vals, diag, cur, nxt, S)
+            # the gathered rows live on other shards: exchange the state, then a local SpMM
+            src = comm.all_gather_rows(cur) if comm is not None else cur
+            _lib.diffuse_step(g.indptr, g.indices, vals, diag, src, nxt, S, n_rows=g.n, row_offset=g.row0)
             cur, nxt = nxt, cur
         if need_stats:
-            _lib.row_kurtosis(cur, S, st.inv_count, kurt)
-            medkurt = device_median(kurt)  # _nam.py:59
+            _lib.row_kurtosis(cur[: g.n], S, st.inv_count, kurt)
+            medkurt = device_median(kurt, comm=comm, rows_per=g.rows_per)  # _nam.py:59
             st.medkurt.append(medkurt + 3)
             print("\tmedian kurtosis:", medkurt + 3, file=out)
             if show_progress:
-                r2 = _r2_p20(cur, old, S) if old is not None else float("nan")
+                r2 = _r2_p20(cur[: g.n], old[: g.n], S) if old is not None and comm is None else float("nan")
                 print("\t20th percentile R2(t,t-1):", r2, file=out)
         if nsteps is None:
             if prevmedkurt - medkurt < 3 and i + 1 >= 3:  # _nam.py:65
@@ -151,7 +175,7 @@ def _nam_device(data, sid_name, nsteps=None, maxnsteps=15, self_weight=1, show_p
             prevmedkurt = medkurt
         elif i + 1 == nsteps:  # _nam.py:69
             break
-    st.s = cur
+    st.s = cur[: g.n]
     st.nsteps = i + 1
     return st
 
@@ -178,11 +202,14 @@ def _qc_device(st, batches, show_progress=False):
     dev = st.s.device
     kurt = torch.empty(st.N, dtype=torch.float64, device=dev)
     _lib.batch_kurtosis(st.s, st.inv_count, _to_dev(order), _to_dev(off), kurt)
-    med = device_median(kurt)
+    med = device_median(kurt, comm=st.comm, rows_per=st.rows_per)
     threshold = max(6, 2 * med)  # _nam.py:94 (python max: a NaN median gives 6)
     print("throwing out neighborhoods with batch kurtosis >=", threshold, file=out)
     keep = kurt < threshold  # NaN -> dropped, _nam.py:96
-    print("keeping", int(keep.sum()), "neighborhoods", file=out)
+    if show_progress:
+        nkeep = keep.sum().double().reshape(1)
+        print("keeping", int((st.comm.all_reduce(nkeep) if st.comm is not None else nkeep).item()),
+              "neighborhoods", file=out)
     st.keep = keep.to(torch.uint8)
     st.qc_threshold = threshold
 
@@ -240,10 +267,13 @@ def svd_nam(NAM):
             pd.DataFrame(V, index=cols, columns=pcs))
 
 
-def gram_svd(x, n):
-    """``_nam.py:105``: U, svs, _ = svd(NAM.NAM^T) with the Gram matrix contracted on the GPU."""
+def gram_svd(x, n, comm=None):
+    """``_nam.py:105``: U, svs, _ = svd(NAM.NAM^T) with the Gram matrix contracted on the GPU
+    (summed over shards when the cell axis is sharded)."""
     G = torch.zeros((n, n), dtype=torch.float64, device=x.device)
     _lib.gram(x, n, G)
+    if comm is not None:
+        comm.all_reduce(G)
     Gh = G.cpu().numpy()
     mark("gram on host")
     Gh = (Gh + Gh.T) / 2  # the kernel fills both triangles from the same products; keep it exact
@@ -315,7 +345,7 @@ def resid_nam_device(st, colmap, covs, batches, y_std, ridges=None, show_progres
     valid = torch.empty(st.N, dtype=torch.uint8, device=dev)
     colmap_d = _to_dev(np.asarray(colmap, dtype=np.int32))
     y_d = _to_dev(np.asarray(y_std, dtype=np.float64))
-    res = Namespace(x=x, ncorr=ncorr, valid=valid, n=n, r=r, C=C, ridge_log=[])
+    res = Namespace(x=x, ncorr=ncorr, valid=valid, n=n, r=r, C=C, ridge_log=[], comm=st.comm)
 
     def run(Wcum, seg=None, kurt=None):
         C_d = _to_dev(C) if r else None
@@ -343,7 +373,7 @@ def resid_nam_device(st, colmap, covs, batches, y_std, ridges=None, show_progres
             # projectors is again I - C.W' with W' = W_prev + W - (W C) W_prev
             Wcum = Wcum + W - W.dot(C).dot(Wcum)
             run(Wcum, seg, kurt)
-            med = device_median(kurt[valid.bool()])  # :150-155
+            med = device_median(kurt, valid=valid, comm=st.comm, rows_per=st.rows_per)  # :150-155
             res.ridge_log.append((ridge, med))
             print("\twith ridge", ridge, "median batch kurtosis = ", med, file=out)
             if med <= 6:

@@ -14,6 +14,9 @@
  *   - matrices are row-major with an explicit leading dimension `ld*` counted in elements;
  *   - the diffusion state / NAM is CELLS x SAMPLES (the transpose of the reference's DataFrames),
  *     fp32, leading dimension a multiple of 8 floats (32-byte sectors), padding columns zero;
+ *   - cell-axis shards (one process per GPU): a shard passes its own rows of the CSR (column
+ *     indices stay global) and `row_offset` = global index of its first row; n_rows is the number
+ *     of local rows.  Single-GPU callers pass row_offset = 0;
  *   - return value 0 = success, otherwise an error code; cna_last_error() returns the message of
  *     the last failing call on the calling thread.
  */
@@ -53,26 +56,26 @@ int cna_graph_colsum(const int32_t *indptr, const int32_t *indices, const void *
  * out_f64 selects double outputs (used by cna.tl.diffuse on user vectors) or float. */
 int cna_graph_scale(const int32_t *indptr, const int32_t *indices, const void *data, int is_f64,
                     int64_t n_rows, const double *colsum, double self_weight, void *vals,
-                    void *diag, int out_f64, void *stream);
+                    void *diag, int out_f64, int64_t row_offset, void *stream);
 
 /* First diffusion step when the state is the one-hot sample indicator (never materialised):
  * out[i, c] = sum_{j: code[j]=c} vals[i,j] + diag[i]*[code[i]=c].
  * replaces: _nam.py:51 `pd.get_dummies` + the first iteration of _nam.py:33. */
 int cna_diffuse_onehot(const int32_t *indptr, const int32_t *indices, const float *vals,
                        const float *diag, const int32_t *code, int64_t n_rows, int n_samples,
-                       float *out, int64_t ld, void *stream);
+                       float *out, int64_t ld, int64_t row_offset, void *stream);
 
 /* One diffusion step on a dense fp32 state: out = A'.in + diag*in  (CSR SpMM).
  * replaces: _nam.py:33 `a.dot(s/colsums[:,None]) + self_weight*s/colsums[:,None]`
  * (scipy _sparsetools.csr_matvecs).  n_cols <= ld, ld % 4 == 0, in != out. */
 int cna_diffuse_step_f32(const int32_t *indptr, const int32_t *indices, const float *vals,
                          const float *diag, const float *in, float *out, int64_t n_rows,
-                         int n_cols, int64_t ld, void *stream);
+                         int n_cols, int64_t ld, int64_t in_row_offset, void *stream);
 
 /* Same, fp64 state with any number of columns (cna.tl.diffuse / diffuse_stepwise on user input). */
 int cna_diffuse_step_f64(const int32_t *indptr, const int32_t *indices, const double *vals,
                          const double *diag, const double *in, double *out, int64_t n_rows,
-                         int n_cols, int64_t ld, void *stream);
+                         int n_cols, int64_t ld, int64_t in_row_offset, void *stream);
 
 /* Per-cell excess kurtosis (biased, Fisher) across samples of s[i,:]*inv_count[:].
  * replaces: _nam.py:59 `st.kurtosis(s/C, axis=1)`.  kurt[n_rows] fp64 (NaN where scipy gives NaN). */

@@ -1,0 +1,133 @@
+"""Cell-axis sharding (cna_b200/sharded.py): world_size-2 tests.
+
+CPU (gloo): the host-side plumbing — shard bounds, CSR slicing, the collective helpers, the global
+median.  GPU (``-m gpu``; two ranks sharing one device over gloo, so it runs on a single-GPU box):
+the sharded association() must reproduce the single-GPU result.
+"""
+import os
+import socket
+import warnings
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from tests.golden import cases
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _spawn(fn, world, *args):
+    port = _free_port()
+    mp.spawn(_entry, args=(world, port, fn, args), nprocs=world, join=True)
+
+
+def _entry(rank, world, port, fn, args):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        fn(rank, world, *args)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_shard_bounds_and_slicing():
+    from cna_b200.sharded import shard_bounds, slice_csr
+    for n, w in [(10, 2), (11, 2), (7, 8), (1_000_000, 8), (5, 1)]:
+        blocks = [shard_bounds(n, w, r) for r in range(w)]
+        assert blocks[0][0] == 0 and blocks[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(blocks, blocks[1:]))
+        assert all(b[1] - b[0] <= b[2] for b in blocks) and len({b[2] for b in blocks}) == 1
+        assert all(b[1] - b[0] == b[2] for b in blocks if b[1] < n)  # only the tail may be short
+    A = sp.random(50, 50, density=0.2, format="csr", random_state=0)
+    ip, ix, dv = slice_csr(A, 13, 31)
+    B = sp.csr_matrix((dv, ix, ip), shape=(18, 50))
+    assert (B != A[13:31]).nnz == 0
+
+
+def _comm_checks(rank, world):
+    from cna_b200.sharded import Comm, shard_bounds
+    from cna_b200.tl._nam import device_median
+    comm = Comm()
+    assert (comm.rank, comm.world) == (rank, world)
+    t = torch.full((3,), float(rank + 1), dtype=torch.float64)
+    assert comm.all_reduce(t.clone()).tolist() == [3.0] * 3
+    assert comm.all_reduce(t.clone(), op="max").tolist() == [2.0] * 3
+    g = comm.all_gather_rows(torch.full((2, 3), float(rank)))
+    assert g.shape == (4, 3) and g[:2].eq(0).all() and g[2:].eq(1).all()
+    b = torch.arange(5, dtype=torch.int32) if rank == 0 else torch.zeros(5, dtype=torch.int32)
+    assert comm.broadcast(b).tolist() == list(range(5))
+    # global median == numpy median of the concatenation, with masks, NaNs and a short tail shard
+    rng = np.random.default_rng(0)
+    for n in (11, 12, 2, 1):
+        full = rng.normal(size=n)
+        valid = rng.random(n) > 0.3
+        valid[0] = True
+        r0, r1, rows_per = shard_bounds(n, world, rank)
+        loc = torch.as_tensor(full[r0:r1])
+        assert device_median(loc, comm=comm, rows_per=rows_per) == np.median(full)
+        got = device_median(loc, valid=torch.as_tensor(valid[r0:r1]), comm=comm, rows_per=rows_per)
+        assert got == np.median(full[valid])
+        full[0] = np.nan
+        assert np.isnan(device_median(torch.as_tensor(full[r0:r1]), comm=comm, rows_per=rows_per))
+
+
+def test_comm_helpers_gloo_world2():
+    _spawn(_comm_checks, 2)
+
+
+def _sharded_vs_single(rank, world, spec):
+    import cna_b200 as cna
+    from cna_b200.sharded import shard_to_device
+    torch.cuda.set_device(0)
+    g = cases.load_demo_graph()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        d1, kw = cases.build_demo_case(g, spec)
+        p1 = cna.tl.association(d1, **kw)
+        d2, kw = cases.build_demo_case(g, spec)
+        p2 = cna.tl.association(shard_to_device(d2), **kw)
+    key = kw.get("key_added", "coef")
+    assert p1 == p2
+    # the residualisation pass is row-local, so coefficients agree bit for bit; FDRs go through the
+    # all-reduced Gram (summation order) only via U, which does not enter them at all
+    np.testing.assert_array_equal(d1.obs[key].to_numpy(), d2.obs[key].to_numpy())
+    np.testing.assert_allclose(d1.obs[key + "_fdr"].to_numpy(), d2.obs[key + "_fdr"].to_numpy(), rtol=1e-12)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["case_male_batch", "case_plain", "donor"])
+def test_sharded_association_matches_single_gpu(name):
+    spec = dict(cases.DEMO_CASES[name])
+    spec.pop("np_seed", None)
+    spec.setdefault("seed", 0)
+    _spawn(_sharded_vs_single, 2, spec)
+
+
+def _sharded_auto_stop(rank, world):
+    from cna_b200.sharded import shard_to_device
+    from cna_b200.tl import _nam
+    torch.cuda.set_device(0)
+    data = cases.demo_anndata()
+    meta = cases.demo_sample_meta()
+    st1 = _nam._nam_device(data, "id")
+    st2 = _nam._nam_device(shard_to_device(cases.demo_anndata()), "id")
+    assert st1.nsteps == st2.nsteps == 4
+    np.testing.assert_allclose(st2.medkurt, st1.medkurt, rtol=1e-12)
+    r0 = st2.row0
+    assert torch.equal(st1.s[r0:r0 + st2.N], st2.s)
+    _nam._qc_device(st1, meta.batch)
+    _nam._qc_device(st2, meta.batch)
+    assert st1.qc_threshold == st2.qc_threshold
+
+
+@pytest.mark.gpu
+def test_sharded_nam_auto_stop_and_qc():
+    _spawn(_sharded_auto_stop, 2)
