@@ -35,7 +35,7 @@ def load():
                 "Run `python -m cna_b200.build` on a machine with nvcc 12.9.") from exc
     lib = ctypes.CDLL(LIB_PATH)
     _declare(lib)
-    if lib.cna_abi_version() != 1:
+    if lib.cna_abi_version() != 2:
         raise ImportError("cna_b200: ABI version mismatch between _lib.py and libcna_b200.so")
     _lib = lib
     return lib
@@ -57,6 +57,7 @@ class ResidArgs(ctypes.Structure):
         ("seg_order", _VP), ("seg_off", _VP), ("n_batches", _INT),
         ("y", _VP),
         ("x_out", _VP), ("ld_x", _I64), ("kurt", _VP), ("ncorr", _VP), ("row_valid", _VP),
+        ("x16_hi", _VP), ("x16_lo", _VP), ("ld16", _I64),
     ]
 
 
@@ -80,8 +81,13 @@ _SIGNATURES = {
     "cna_absmax": [_VP, _VP, _I64, _VP, _VP],
     "cna_cell_fdr": [_VP, _VP, _I64, _VP, _VP, _INT, _VP, _VP, _VP],
     "cna_knn_bruteforce": [_VP, _I64, _INT, _INT, _VP, _VP, _VP],
+    "cna_split_f16": [_VP, _I64, _I64, _INT, _INT, _VP, _VP, _I64, _I64, _VP],
+    "cna_gram_tc": [_VP, _VP, _I64, _I64, _INT, _VP, _VP, _I64, _VP],
+    "cna_right_multiply_tc": [_VP, _VP, _I64, _I64, _INT, _VP, _VP, _I64, _INT, _VP, _I64, _VP],
+    "cna_null_hist_tc": [_VP, _VP, _I64, _I64, _INT, _VP, _VP, _I64, _INT, _VP, _INT, _DBL, _VP, _VP],
 }
-EXPORTS = sorted(list(_SIGNATURES) + ["cna_abi_version", "cna_last_error", "cna_launch_count"])
+EXPORTS = sorted(list(_SIGNATURES) + ["cna_abi_version", "cna_last_error", "cna_launch_count",
+                                      "cna_gram_tc_workspace"])
 
 
 def _declare(lib):
@@ -91,6 +97,8 @@ def _declare(lib):
     lib.cna_last_error.argtypes = []
     lib.cna_launch_count.restype = ctypes.c_int64
     lib.cna_launch_count.argtypes = []
+    lib.cna_gram_tc_workspace.restype = ctypes.c_int64
+    lib.cna_gram_tc_workspace.argtypes = [ctypes.c_int]
     for name, args in _SIGNATURES.items():
         fn = getattr(lib, name)
         fn.restype = ctypes.c_int
@@ -204,7 +212,8 @@ def batch_kurtosis(s, inv_count, seg_order, seg_off, kurt):
                                      _ptr(kurt, torch.float64, "kurt"), _stream())
 
 
-def resid_pass(s, inv_count, colmap, row_keep, C, Wt, seg_order, seg_off, y, x_out, kurt, ncorr, row_valid):
+def resid_pass(s, inv_count, colmap, row_keep, C, Wt, seg_order, seg_off, y, x_out, kurt, ncorr, row_valid,
+               planes=None):
     a = ResidArgs()
     a.s = _ptr(s, torch.float32, "s"); a.ld_s = s.shape[1]; a.n_rows = s.shape[0]
     a.inv_count = _ptr(inv_count, torch.float64, "inv_count")
@@ -221,7 +230,13 @@ def resid_pass(s, inv_count, colmap, row_keep, C, Wt, seg_order, seg_off, y, x_o
     else:
         a.seg_order = None; a.seg_off = None; a.n_batches = 1
     a.y = _ptr(y, torch.float64, "y")
-    a.x_out = _ptr(x_out, torch.float32, "x_out"); a.ld_x = x_out.shape[1]
+    a.x_out = _ptr(x_out, torch.float32, "x_out", allow_none=True)
+    a.ld_x = x_out.shape[1] if x_out is not None else 0
+    if planes is not None:
+        a.x16_hi = _ptr(planes.hi, torch.float16, "x16_hi"); a.x16_lo = _ptr(planes.lo, torch.float16, "x16_lo")
+        a.ld16 = planes.ld
+    else:
+        a.x16_hi = None; a.x16_lo = None; a.ld16 = 0
     a.kurt = _ptr(kurt, torch.float64, "kurt", allow_none=True)
     a.ncorr = _ptr(ncorr, torch.float64, "ncorr")
     a.row_valid = _ptr(row_valid, torch.uint8, "row_valid")
@@ -278,6 +293,70 @@ def cell_fdr(ncorr, row_valid, thresholds, prefix_min_fdr, coef, fdr):
                                _ptr(thresholds, torch.float64, "thresholds"),
                                _ptr(prefix_min_fdr, torch.float64, "prefix_min_fdr"), thresholds.numel(),
                                _ptr(coef, torch.float64, "coef"), _ptr(fdr, torch.float64, "fdr"), _stream())
+
+
+def round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+class Planes:
+    """fp16 hi/lo planes of an fp32 matrix (x = hi + lo to 2^-22): the operand format of the
+    tcgen05 kernels.  ``t`` is one [2, rows, ld16] tensor (plane 0 = hi, 1 = lo)."""
+
+    def __init__(self, rows, cols, device):
+        self.rows, self.cols = int(rows), int(cols)
+        self.ld = round_up(max(self.cols, 1), 16)
+        self.t = torch.empty((2, self.rows, self.ld), dtype=torch.float16, device=device)
+
+    @property
+    def hi(self):
+        return self.t[0]
+
+    @property
+    def lo(self):
+        return self.t[1]
+
+
+def split_f16(src, n_cols, transpose=False, planes=None):
+    """src [rows x ld] fp32 -> Planes of src[:, :n_cols] (or of its transpose)."""
+    rows = src.shape[0]
+    if planes is None:
+        planes = Planes(n_cols, rows, src.device) if transpose else Planes(rows, n_cols, src.device)
+    _call("cna_split_f16", _ptr(src, torch.float32, "src"), src.shape[1], rows, int(n_cols), int(transpose),
+          _ptr(planes.hi, torch.float16, "hi"), _ptr(planes.lo, torch.float16, "lo"), planes.ld, planes.rows,
+          _stream())
+    return planes
+
+
+_GRAM_WS = {}
+
+
+def gram_tc(xp, n, out):
+    """out[n x n] (fp64) += X^T X on the tensor cores; xp = Planes of X."""
+    need = int(load().cna_gram_tc_workspace(int(n)))
+    if need < 0:
+        raise CnaError(f"cna_gram_tc: n={n} not supported (n <= 256)")
+    key = (xp.t.device, need)
+    ws = _GRAM_WS.get(key)
+    if ws is None:
+        _GRAM_WS.clear()
+        ws = _GRAM_WS[key] = torch.empty(need, dtype=torch.uint8, device=xp.t.device)
+    _call("cna_gram_tc", _ptr(xp.hi, torch.float16, "xh"), _ptr(xp.lo, torch.float16, "xl"), xp.ld, xp.rows,
+          int(n), _ptr(out, torch.float64, "gram"), ws.data_ptr(), need, _stream())
+
+
+def right_multiply_tc(xp, n, btp, n_out, out):
+    """out[rows x ld_out] (fp32) = X . B; xp = Planes of X, btp = Planes of B^T [n_out x n]."""
+    _call("cna_right_multiply_tc", _ptr(xp.hi, torch.float16, "xh"), _ptr(xp.lo, torch.float16, "xl"), xp.ld,
+          xp.rows, int(n), _ptr(btp.hi, torch.float16, "bth"), _ptr(btp.lo, torch.float16, "btl"), btp.ld,
+          int(n_out), _ptr(out, torch.float32, "out"), out.shape[1], _stream())
+
+
+def null_hist_tc(xp, n, ytp, n_null, edges, edge0, hist):
+    _call("cna_null_hist_tc", _ptr(xp.hi, torch.float16, "xh"), _ptr(xp.lo, torch.float16, "xl"), xp.ld,
+          xp.rows, int(n), _ptr(ytp.hi, torch.float16, "yth"), _ptr(ytp.lo, torch.float16, "ytl"), ytp.ld,
+          int(n_null), _ptr(edges, torch.float64, "edges"), edges.numel(), float(edge0),
+          _ptr(hist, torch.int32, "hist"), _stream())
 
 
 def knn_bruteforce(points, k):

@@ -289,14 +289,6 @@ __global__ void cell_fdr_kernel(const double *__restrict__ ncorr, const uint8_t 
 
 using namespace cna;
 
-// provided by gemm_tc.cu
-namespace cna {
-bool tc_enabled();
-int gram_tc(const float *x, int64_t ld_x, int64_t n_rows, int n, double *gram, cudaStream_t st);
-int null_hist_tc(const float *x, int64_t ld_x, int64_t n_rows, int n, const float *ycond, int64_t ld_y,
-                 int n_null, const double *edges, int n_edges, uint32_t *hist, cudaStream_t st);
-}  // namespace cna
-
 extern "C" {
 
 int cna_gram_simt(const float *x, int64_t ld_x, int64_t n_rows, int n, double *gram, void *stream) {
@@ -312,10 +304,6 @@ int cna_gram_simt(const float *x, int64_t ld_x, int64_t n_rows, int n, double *g
 }
 
 int cna_gram(const float *x, int64_t ld_x, int64_t n_rows, int n, double *gram, void *stream) {
-    if (tc_enabled()) {
-        int rc = gram_tc(x, ld_x, n_rows, n, gram, as_stream(stream));
-        if (rc >= 0) return rc;  // negative: shape not covered by the tensor-core kernel
-    }
     return cna_gram_simt(x, ld_x, n_rows, n, gram, stream);
 }
 

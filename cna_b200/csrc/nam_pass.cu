@@ -8,6 +8,8 @@
 //
 // Reference: src/cna/tools/_nam.py:78-99 (QC), :118-159 (_resid_nam), _association.py:175-185
 // (reindex, filter, zero-variance drop), :77 (ncorrs).
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace cna {
@@ -130,7 +132,9 @@ __global__ void __launch_bounds__(256) resid_kernel(cna_resid_args a) {
     int64_t stride = int64_t(gridDim.x) * warps;
     for (int64_t row = int64_t(blockIdx.x) * warps + w; row < a.n_rows; row += stride) {
         const float *p = a.s + row * a.ld_s;
-        float *o = a.x_out + row * a.ld_x;
+        float *o = a.x_out ? a.x_out + row * a.ld_x : nullptr;
+        __half *ph = a.x16_hi ? static_cast<__half *>(a.x16_hi) + row * a.ld16 : nullptr;
+        __half *pl = a.x16_hi ? static_cast<__half *>(a.x16_lo) + row * a.ld16 : nullptr;
         double x[NQ];
         double sum = 0.0;
 #pragma unroll
@@ -154,7 +158,11 @@ __global__ void __launch_bounds__(256) resid_kernel(cna_resid_args a) {
 #pragma unroll
             for (int q = 0; q < NQ; ++q) {
                 int m = lane + 32 * q;
-                if (m < a.ld_x) o[m] = 0.f;
+                if (o && m < a.ld_x) o[m] = 0.f;
+                if (ph && m < a.ld16) {
+                    ph[m] = __float2half_rn(0.f);
+                    pl[m] = __float2half_rn(0.f);
+                }
             }
             if (lane == 0) {
                 if (a.kurt) a.kurt[row] = nan("");
@@ -213,12 +221,13 @@ __global__ void __launch_bounds__(256) resid_kernel(cna_resid_args a) {
 #pragma unroll
         for (int q = 0; q < NQ; ++q) {
             int m = lane + 32 * q;
-            double v = x[q] / sd;
-            if (m < n) {
-                dot += v * ys[m];
-                o[m] = float(v);
-            } else if (m < a.ld_x) {
-                o[m] = 0.f;
+            double v = (m < n) ? x[q] / sd : 0.0;
+            if (m < n) dot += v * ys[m];
+            if (o && m < a.ld_x) o[m] = float(v);
+            if (ph && m < a.ld16) {  // v = hi + lo to 2^-22
+                __half h = __float2half_rn(float(v));
+                ph[m] = h;
+                pl[m] = __float2half_rn(float(v - double(__half2float(h))));
             }
         }
         dot = warp_sum(dot);
@@ -259,10 +268,12 @@ int cna_resid_pass(const cna_resid_args *args, void *stream) {
     CNA_REQUIRE(args != nullptr, "cna_resid_pass: null args");
     const cna_resid_args &a = *args;
     CNA_REQUIRE(a.n_rows >= 0 && a.n >= 2 && a.n <= 1024, "cna_resid_pass: n must be in [2, 1024] (got %d)", a.n);
-    CNA_REQUIRE(a.r >= 0 && a.ld_x >= a.n && a.ld_x <= ((a.n + 31) / 32) * 32,
+    CNA_REQUIRE(a.r >= 0 && (!a.x_out || (a.ld_x >= a.n && a.ld_x <= ((a.n + 31) / 32) * 32)),
                 "cna_resid_pass: bad r/ld_x (r=%d ld_x=%lld n=%d)", a.r, (long long)a.ld_x, a.n);
-    CNA_REQUIRE(a.s && a.inv_count && a.colmap && a.y && a.x_out && a.ncorr && a.row_valid,
+    CNA_REQUIRE(a.s && a.inv_count && a.colmap && a.y && (a.x_out || a.x16_hi) && a.ncorr && a.row_valid,
                 "cna_resid_pass: null pointer");
+    CNA_REQUIRE(!a.x16_hi || (a.x16_lo && a.ld16 % 16 == 0 && a.ld16 >= a.n && a.ld16 <= ((a.n + 31) / 32) * 32),
+                "cna_resid_pass: bad fp16 planes (ld16=%lld n=%d)", (long long)a.ld16, a.n);
     CNA_REQUIRE(a.r == 0 || (a.C && a.Wt), "cna_resid_pass: C/Wt missing");
     if (a.n_rows == 0) return CNA_OK;
     const int threads = 256, warps = threads / 32;

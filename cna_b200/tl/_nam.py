@@ -260,18 +260,32 @@ def svd_nam(NAM):
     x = torch.zeros((x64.shape[0], ld), dtype=torch.float32, device=x64.device)
     x[:, :n] = x64
     del x64
-    U, svs, _ = gram_svd(x, n)
+    xp = planes_of(x, n)
+    U, svs, _ = gram_svd(x, n, planes=xp)
     pcs = ["PC" + str(i) for i in range(1, n + 1)]
-    V = nbhd_loadings(x, n, U, svs)
+    V = nbhd_loadings(x, n, U, svs, planes=xp)
     return (pd.DataFrame(U, index=idx, columns=pcs), pd.Series(svs, index=pcs),
             pd.DataFrame(V, index=cols, columns=pcs))
 
 
-def gram_svd(x, n, comm=None):
+TC_GRAM_MAX_N = 256  # TMEM holds the fp32 accumulators of at most 256 samples
+
+
+def planes_of(x, n):
+    """fp16 hi/lo operand planes of the fp32 matrix x[:, :n] (tensor-core operand format)."""
+    return _lib.split_f16(x, n)
+
+
+def gram_svd(x, n, comm=None, planes=None):
     """``_nam.py:105``: U, svs, _ = svd(NAM.NAM^T) with the Gram matrix contracted on the GPU
-    (summed over shards when the cell axis is sharded)."""
-    G = torch.zeros((n, n), dtype=torch.float64, device=x.device)
-    _lib.gram(x, n, G)
+    (tcgen05 kernel on the fp16 hi/lo planes when n <= 256, CUDA cores otherwise; summed over
+    shards when the cell axis is sharded)."""
+    dev = x.device if x is not None else planes.t.device
+    G = torch.zeros((n, n), dtype=torch.float64, device=dev)
+    if n <= TC_GRAM_MAX_N:
+        _lib.gram_tc(planes if planes is not None else planes_of(x, n), n, G)
+    else:
+        _lib.gram(x, n, G)
     if comm is not None:
         comm.all_reduce(G)
     Gh = G.cpu().numpy()
@@ -282,20 +296,24 @@ def gram_svd(x, n, comm=None):
     return U, svs, Gh
 
 
-def nbhd_loadings(x, n, U, svs, rows=None):
+def nbhd_loadings(x, n, U, svs, rows=None, planes=None):
     """``_nam.py:106``: V = NAM^T U / sqrt(svs) (cells x n).  The trailing ~null-space columns divide
-    by ~0 exactly like the reference."""
-    with np.errstate(divide="ignore", invalid="ignore"):
-        B = U / np.sqrt(svs)
+    by ~0 exactly like the reference.  The product X.U runs on the tensor cores (columns of U are
+    unit vectors, inside fp16 range); the per-column 1/sqrt(svs) scaling is applied afterwards in
+    float64 so that the near-null-space blow-up never passes through fp16."""
+    xp = planes if planes is not None else planes_of(x, n)
     ldb = _round_up(n, 4)
-    b = np.zeros((x.shape[1], ldb), dtype=np.float32)
-    b[:n, :n] = np.nan_to_num(B, nan=0.0, posinf=3e38, neginf=-3e38)
-    out = torch.empty((x.shape[0], ldb), dtype=torch.float32, device=x.device)
-    _lib.right_multiply(x, n, _to_dev(b), n, out)
-    V = out[:, :n]
+    ut = torch.zeros((n, _round_up(n, 4)), dtype=torch.float32, device=xp.t.device)
+    ut[:, :n] = _to_dev(np.ascontiguousarray(U.T, dtype=np.float32))
+    utp = _lib.split_f16(ut, n)  # planes of U^T: row j = column j of U
+    out = torch.empty((xp.rows, ldb), dtype=torch.float32, device=xp.t.device)
+    _lib.right_multiply_tc(xp, n, utp, n, out)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        scale = _to_dev(1.0 / np.sqrt(svs))
+    V = out[:, :n].double() * scale
     if rows is not None:
         V = V[rows]
-    return V.double().cpu().numpy()
+    return V.cpu().numpy()
 
 
 # ---------------------------------------------------------------------------------------------
@@ -327,7 +345,7 @@ def projector(C, nb, ridge):
     return np.linalg.solve(CtC, C.T)
 
 
-def resid_nam_device(st, colmap, covs, batches, y_std, ridges=None, show_progress=False):
+def resid_nam_device(st, colmap, covs, batches, y_std, ridges=None, show_progress=False, want_x=True):
     """``_nam.py:118-177`` + ``_association.py:178-185`` + ``:77`` on the device.
 
     colmap : int array, state column of each of the n selected samples (phenotype order)
@@ -340,18 +358,20 @@ def resid_nam_device(st, colmap, covs, batches, y_std, ridges=None, show_progres
     C, nb = design_matrix(covs, batches, n)
     r = C.shape[1]
     ld = _round_up(n, 8)
-    x = torch.empty((st.N, ld), dtype=torch.float32, device=dev)
+    x = torch.empty((st.N, ld), dtype=torch.float32, device=dev) if want_x else None
+    planes = _lib.Planes(st.N, n, dev)
     ncorr = torch.empty(st.N, dtype=torch.float64, device=dev)
     valid = torch.empty(st.N, dtype=torch.uint8, device=dev)
     colmap_d = _to_dev(np.asarray(colmap, dtype=np.int32))
     y_d = _to_dev(np.asarray(y_std, dtype=np.float64))
-    res = Namespace(x=x, ncorr=ncorr, valid=valid, n=n, r=r, C=C, ridge_log=[], comm=st.comm)
+    res = Namespace(x=x, planes=planes, ncorr=ncorr, valid=valid, n=n, r=r, C=C, ridge_log=[], comm=st.comm)
 
     def run(Wcum, seg=None, kurt=None):
         C_d = _to_dev(C) if r else None
         W_d = _to_dev(np.ascontiguousarray(Wcum)) if r else None
         _lib.resid_pass(st.s, st.inv_count, colmap_d, st.keep, C_d, W_d,
-                        seg[0] if seg else None, seg[1] if seg else None, y_d, x, kurt, ncorr, valid)
+                        seg[0] if seg else None, seg[1] if seg else None, y_d, x, kurt, ncorr, valid,
+                        planes=planes)
 
     if nb == 0:
         if r > 0:  # _nam.py:133

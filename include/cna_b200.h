@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define CNA_B200_ABI_VERSION 1
+#define CNA_B200_ABI_VERSION 2
 
 enum {
     CNA_OK = 0,
@@ -122,6 +122,12 @@ typedef struct cna_resid_args {
     double *kurt;        /* [n_rows] batch kurtosis after residualisation (NaN for dropped cells), may be NULL */
     double *ncorr;       /* [n_rows] neighbourhood coefficients (_association.py:77), 0 for dropped cells */
     uint8_t *row_valid;  /* [n_rows] row_keep && variance > 0 (_association.py:182-185) */
+    /* optional fp16 hi/lo planes of x_out for the tensor-core kernels ([n_rows x ld16] each,
+     * ld16 a multiple of 16 with n <= ld16 <= 32 * ceil(n / 32)); NULL to skip.  x_out itself may
+     * be NULL when only the planes are wanted. */
+    void *x16_hi;
+    void *x16_lo;
+    int64_t ld16;
 } cna_resid_args;
 
 /* replaces: _association.py:178-185 (reindex, filter, zero-variance drop), _nam.py:122 (centre),
@@ -173,6 +179,35 @@ int cna_perm_stats(const double *y, const int32_t *perm, int64_t K, int n, const
 int cna_null_hist(const float *x, int64_t ld_x, int64_t n_rows, int n, const float *ycond,
                   int64_t ld_y, int n_null, const double *edges, int n_edges, double edge0,
                   uint32_t *hist, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * tensor-core (tcgen05 / TMEM / TMA) versions of the dense contractions.  Operands are the fp16
+ * hi/lo planes produced by cna_split_f16 (or directly by cna_resid_pass): x = hi + lo to 2^-22.
+ * ------------------------------------------------------------------------------------------ */
+
+/* dst planes [dst_rows x ld_dst] fp16: hi = fp16(v), lo = fp16(v - hi) with v = src[r][c]
+ * (transpose = 0) or src[c][r] (transpose = 1); everything outside the source extent is zero. */
+int cna_split_f16(const float *src, int64_t ld_src, int64_t src_rows, int src_cols, int transpose,
+                  void *hi, void *lo, int64_t ld_dst, int64_t dst_rows, void *stream);
+
+/* Same contract as cna_gram (gram += X^T X), X given as fp16 planes [n_rows x ld16], n <= 256.
+ * `workspace` holds per-SM fp64 partial Grams (cna_gram_tc_workspace(n) bytes, contents
+ * irrelevant on entry).  replaces: _nam.py:105 `NAM.dot(NAM.T)`. */
+int64_t cna_gram_tc_workspace(int n);
+int cna_gram_tc(const void *xh, const void *xl, int64_t ld16, int64_t n_rows, int n, double *gram,
+                void *workspace, int64_t workspace_bytes, void *stream);
+
+/* Same contract as cna_right_multiply: out = X . B, with B given TRANSPOSED as fp16 planes
+ * bt [n_out x ld16_b] (row j = column j of B).  replaces: _nam.py:106. */
+int cna_right_multiply_tc(const void *xh, const void *xl, int64_t ld16, int64_t n_rows, int n,
+                          const void *bth, const void *btl, int64_t ld16_b, int n_out, float *out,
+                          int64_t ld_out, void *stream);
+
+/* Same contract as cna_null_hist with the conditioned phenotypes given TRANSPOSED as fp16 planes
+ * yt [n_null x ld16_y].  replaces: _association.py:99 + _stats.py:52-54. */
+int cna_null_hist_tc(const void *xh, const void *xl, int64_t ld16, int64_t n_rows, int n,
+                     const void *yth, const void *ytl, int64_t ld16_y, int n_null, const double *edges,
+                     int n_edges, double edge0, uint32_t *hist, void *stream);
 
 /* Histograms of the observed coefficients against the same edges and the strict thresholds:
  * rank_hist[b] += #{i valid: edges[b] <= ncorr_i^2 < edges[b+1]} (last bin closed),
