@@ -218,8 +218,10 @@ def rooflines(prof, steps, N, S, n, nnz, K, Kl, s_steps, peaks):
         "cna_diffuse_step_f32": ("hbm", b_spmm, "diffusion SpMM (one step)"),
         "cna_diffuse_onehot": ("hbm", b_spmm, "diffusion step 1 from the one-hot indicator"),
         "cna_resid_pass": ("hbm", 2 * 4 * N * S, "select/centre/residualise/standardise/ncorr pass"),
-        "cna_gram": ("tensor", 2.0 * n * n * N, "Gram X^T X"),
-        "cna_null_hist": ("tensor", 2.0 * N * n * Kl, "null GEMM + threshold histogram"),
+        "cna_gram": ("tensor", 2.0 * n * n * N, "Gram X^T X (CUDA cores)"),
+        "cna_gram_tc": ("tensor", 2.0 * n * n * N, "Gram X^T X (tcgen05, fp16 hi/lo split, fp64 flush)"),
+        "cna_null_hist": ("tensor", 2.0 * N * n * Kl, "null GEMM + threshold histogram (CUDA cores)"),
+        "cna_null_hist_tc": ("tensor", 2.0 * N * n * Kl, "null GEMM + threshold histogram (tcgen05, fp16 hi/lo split)"),
         "cna_perm_stats": (None, None, "permutation engine (fp64)"),
     }
     total = sum(ms for _, ms in prof.values()) or 1.0
@@ -333,7 +335,7 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": N * args.steps / (ms * 1e-3), "unit": "cells/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "f32 state / f64 statistics", "data": "synthetic",
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32 state, fp16x2-split tensor-core GEMMs with f32 accumulate, f64 statistics", "data": "synthetic",
         "config": {"workload": workload_name(args.config), "nnz": nnz, "l2": "inputs larger than L2 (no flush)",
                    "parallelism": f"cell-axis shards x{world}" if world > 1 else "single GPU",
                    "p_value": p_value, "datagen_s": round(gen_s, 1)},

@@ -81,6 +81,8 @@ _SIGNATURES = {
     "cna_absmax": [_VP, _VP, _I64, _VP, _VP],
     "cna_cell_fdr": [_VP, _VP, _I64, _VP, _VP, _INT, _VP, _VP, _VP],
     "cna_knn_bruteforce": [_VP, _I64, _INT, _INT, _VP, _VP, _VP],
+    "cna_host_randn": [_VP, _VP, _VP, _VP, _I64, _VP, _INT],
+    "cna_host_perm_blocks": [_VP, _VP, _VP, _VP, _INT, _VP, _VP, _I64, _VP, _I64, _INT],
     "cna_split_f16": [_VP, _I64, _I64, _INT, _INT, _VP, _VP, _I64, _I64, _VP],
     "cna_gram_tc": [_VP, _VP, _I64, _I64, _INT, _VP, _VP, _I64, _VP],
     "cna_right_multiply_tc": [_VP, _VP, _I64, _I64, _INT, _VP, _VP, _I64, _INT, _VP, _I64, _VP],
@@ -357,6 +359,60 @@ def null_hist_tc(xp, n, ytp, n_null, edges, edge0, hist):
           xp.rows, int(n), _ptr(ytp.hi, torch.float16, "yth"), _ptr(ytp.lo, torch.float16, "ytl"), ytp.ld,
           int(n_null), _ptr(edges, torch.float64, "edges"), edges.numel(), float(edge0),
           _ptr(hist, torch.int32, "hist"), _stream())
+
+
+# ---------------------------------------------------------------------------------------------
+# host-side permutation drawing on numpy's legacy global generator
+# ---------------------------------------------------------------------------------------------
+class _LegacyState:
+    """np.random's global RandomState unpacked for the C-ABI, written back on exit."""
+
+    def __enter__(self):
+        import numpy as np
+        kind, key, pos, has_gauss, gauss = np.random.get_state()
+        if kind != "MT19937":
+            raise CnaError(f"numpy's global generator is {kind}, expected MT19937")
+        self.key = np.array(key, dtype=np.uint32)
+        self.pos = ctypes.c_int(int(pos))
+        self.has_gauss = ctypes.c_int(int(has_gauss))
+        self.gauss = ctypes.c_double(float(gauss))
+        return self
+
+    def args(self):
+        return (self.key.ctypes.data, ctypes.addressof(self.pos), ctypes.addressof(self.has_gauss),
+                ctypes.addressof(self.gauss))
+
+    def __exit__(self, *exc):
+        import numpy as np
+        np.random.set_state(("MT19937", self.key, self.pos.value, self.has_gauss.value, self.gauss.value))
+
+
+def _host_call(name, *args):
+    rc = getattr(load(), name)(*args)
+    if rc != 0:
+        raise CnaError(f"{name} failed ({rc}): {load().cna_last_error().decode()}")
+
+
+def host_randn(count, n_threads=0):
+    """``np.random.randn(count)`` from (and advancing) numpy's legacy global generator."""
+    import numpy as np
+    out = np.empty(int(count), dtype=np.float64)
+    with _LegacyState() as st:
+        _host_call("cna_host_randn", *st.args(), int(count), out.ctypes.data, int(n_threads))
+    return out
+
+
+def host_perm_blocks(block_off, src_pos, num, n_threads=0):
+    """int32 [num x total_rows] permutation matrix, see cna_host_perm_blocks in the header."""
+    import numpy as np
+    block_off = np.ascontiguousarray(block_off, dtype=np.int32)
+    total = int(block_off[-1])
+    out = np.empty((int(num), total), dtype=np.int32)
+    sp = None if src_pos is None else np.ascontiguousarray(src_pos, dtype=np.int32)
+    with _LegacyState() as st:
+        _host_call("cna_host_perm_blocks", *st.args(), len(block_off) - 1, block_off.ctypes.data,
+                   None if sp is None else sp.ctypes.data, int(num), out.ctypes.data, total, int(n_threads))
+    return out
 
 
 def knn_bruteforce(points, k):

@@ -24,6 +24,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC",
+    "-Xcompiler", "-ffp-contract=off",  # perm_host.cu restates numpy's RNG arithmetic literally
     "-Xptxas", "-v",
     "--expt-relaxed-constexpr",
 ]

@@ -187,8 +187,10 @@ constexpr int kBN = 256;                 // output columns per tile (UMMA N)
 constexpr int kStepBytesA = kBM * 32;    // one k-step (16 fp16) of one plane of A
 constexpr int kStepBytesB = kBN * 32;
 constexpr int kStageBytes = 2 * kStepBytesA + 2 * kStepBytesB;  // hi+lo of A and B: 24 KiB
-constexpr int kStages = 8;
-constexpr int kXbThreads = 192;
+constexpr int kStages = 7;
+constexpr int kXbEpiWarps = 8;           // two warps per TMEM lane quarter, each owning half the columns
+constexpr int kXbThreads = 64 + kXbEpiWarps * 32;
+constexpr int kQueue = 512;              // candidates of one 16-column batch of one warp (32 lanes x 16)
 constexpr uint32_t kSw32 = 6, kSw128 = 2;
 
 enum class Epi { STORE, HIST };
@@ -219,7 +221,10 @@ xb_tc_kernel(const __grid_constant__ CUtensorMap tm_ah, const __grid_constant__ 
     uint64_t *tfull = empty + kStages;
     uint64_t *tempty = tfull + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
-    double *edges_s = reinterpret_cast<double *>(tmem_slot + 2);
+    float *guess = reinterpret_cast<float *>(tmem_slot + 2);              // [2]: sqrt(e_0), bins per unit sqrt
+    float *queue_v = guess + 2;                                            // [warps][kQueue]
+    uint16_t *queue_c = reinterpret_cast<uint16_t *>(queue_v + kXbEpiWarps * kQueue);
+    double *edges_s = reinterpret_cast<double *>(queue_c + kXbEpiWarps * kQueue);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_row_tiles = int((a.n_rows + kBM - 1) / kBM);
@@ -232,7 +237,7 @@ xb_tc_kernel(const __grid_constant__ CUtensorMap tm_ah, const __grid_constant__ 
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(tfull + b, 1);
-            mbar_init(tempty + b, 4);  // one arrive per epilogue warp
+            mbar_init(tempty + b, kXbEpiWarps);  // one arrive per epilogue warp
         }
         fence_barrier_init();
         tma_prefetch_desc(&tm_ah);
@@ -241,8 +246,16 @@ xb_tc_kernel(const __grid_constant__ CUtensorMap tm_ah, const __grid_constant__ 
         tma_prefetch_desc(&tm_bl);
     }
     if (warp == 1) tmem_alloc(tmem_slot, 512);
-    if (E == Epi::HIST)
+    if (E == Epi::HIST) {
         for (int t = threadIdx.x; t < a.n_edges; t += blockDim.x) edges_s[t] = a.edges[t];
+        if (threadIdx.x == 32) {
+            // the thresholds are (close to) an arithmetic progression, so sqrt(edge) is close to
+            // linear in the bin index: a one-multiply first guess, corrected against the table
+            double s0 = sqrt(fmax(a.edges[0], 0.0)), s1 = sqrt(fmax(a.edges[a.n_edges - 1], 0.0));
+            guess[0] = float(s0);
+            guess[1] = (s1 > s0) ? float((a.n_edges - 1) / (s1 - s0)) : 0.f;
+        }
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -303,46 +316,72 @@ xb_tc_kernel(const __grid_constant__ CUtensorMap tm_ah, const __grid_constant__ 
                     }
                 }
         }
-    } else {  // ---- epilogue: warps 2..5, TMEM lane quarter = warp % 4 ----
-        const int q = warp & 3;
+    } else {  // ---- epilogue: warps 2..9; TMEM lane quarter = warp % 4, column half = (warp - 2) / 4 ----
+        const int q = warp & 3, half = (warp - 2) >> 2, ew = warp - 2;
+        float *qv = queue_v + ew * kQueue;
+        uint16_t *qc = queue_c + ew * kQueue;
+        const float g0 = (E == Epi::HIST) ? guess[0] : 0.f, g1 = (E == Epi::HIST) ? guess[1] : 0.f;
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int rt = blockIdx.x; rt < n_row_tiles; rt += gridDim.x) {
             const int64_t row = int64_t(rt) * kBM + q * 32 + lane;
+            const bool row_ok = row < a.n_rows;
             for (int nc = 0; nc < n_chunks; ++nc) {
                 mbar_wait(tfull + acc, acc_phase);
                 tc_fence_after();
                 const uint32_t t0 = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * kBN);
-                for (int c0 = 0; c0 < kBN; c0 += 32) {
+                for (int c0 = half * (kBN / 2); c0 < (half + 1) * (kBN / 2); c0 += 16) {
                     const int col0 = nc * kBN + c0;
-                    if (col0 >= a.n_out) break;  // uniform over the CTA
-                    uint32_t r[32];
-                    tmem_ld32(t0 + c0, r);
+                    if (col0 >= a.n_out) break;  // uniform over the warp
+                    uint32_t r[16];
+                    tmem_ld16(t0 + c0, r);
                     tmem_ld_wait();
                     if (E == Epi::STORE) {
-                        if (row < a.n_rows) {
+                        if (row_ok) {
                             float *o = a.out + row * a.ld_out + col0;
 #pragma unroll
-                            for (int j = 0; j < 32; ++j)
+                            for (int j = 0; j < 16; ++j)
                                 if (col0 + j < a.n_out) o[j] = __uint_as_float(r[j]);
                         }
                     } else {
+                        // pass 1: which of my 16 products can reach the first edge at all?
+                        uint32_t mask = 0;
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
+                        for (int j = 0; j < 16; ++j) {
                             float v = __uint_as_float(r[j]);
-                            if (v * v < a.reject_below) continue;
-                            if (row >= a.n_rows || col0 + j >= a.n_out) continue;
-                            double z = double(v) * a.inv_n;
+                            if (v * v >= a.reject_below && col0 + j < a.n_out) mask |= 1u << j;
+                        }
+                        if (!row_ok) mask = 0;
+                        // compact the survivors of the whole warp into its queue
+                        int cnt = __popc(mask), off = cnt;
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) {
+                            int t = __shfl_up_sync(kFull, off, o);
+                            if (lane >= o) off += t;
+                        }
+                        const int total = __shfl_sync(kFull, off, 31);
+                        if (total == 0) continue;
+                        off -= cnt;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (mask & (1u << j)) {
+                                qv[off] = __uint_as_float(r[j]);
+                                qc[off] = uint16_t(c0 + j);
+                                ++off;
+                            }
+                        __syncwarp();
+                        // pass 2: all lanes busy on survivors: bin lookup + one atomic each
+                        for (int i = lane; i < total; i += 32) {
+                            double z = double(qv[i]) * a.inv_n;
                             double z2 = z * z;
                             if (!(z2 >= edges_s[0])) continue;
-                            int lo = 0, hi = a.n_edges - 1;  // largest b with edges[b] <= z2
-                            while (lo < hi) {
-                                int mid = (lo + hi + 1) >> 1;
-                                if (edges_s[mid] <= z2) lo = mid;
-                                else hi = mid - 1;
-                            }
-                            atomicAdd(a.hist + int64_t(col0 + j) * a.n_edges + lo, 1u);
+                            int b = int((sqrtf(float(z2)) - g0) * g1);
+                            b = max(0, min(b, a.n_edges - 1));
+                            while (b + 1 < a.n_edges && edges_s[b + 1] <= z2) ++b;  // largest b with edges[b] <= z2
+                            while (b > 0 && edges_s[b] > z2) --b;
+                            atomicAdd(a.hist + int64_t(nc * kBN + qc[i]) * a.n_edges + b, 1u);
                         }
+                        __syncwarp();
                     }
                 }
                 tc_fence_before();
@@ -594,7 +633,8 @@ static int xb_tc_launch(Epi epi, const void *xh, const void *xl, int64_t ld16, i
     a.n_rows = n_rows;
     a.n_ksteps = (n + 15) / 16;
     a.n_out = n_out;
-    size_t smem = size_t(kStages) * kStageBytes + 1024 + 256 + (epi == Epi::HIST ? sizeof(double) * a.n_edges : 0);
+    size_t smem = size_t(kStages) * kStageBytes + 1024 + 256 + size_t(kXbEpiWarps) * kQueue * 6 +
+                  (epi == Epi::HIST ? sizeof(double) * a.n_edges : 0);
     int64_t tiles = (n_rows + kBM - 1) / kBM;
     unsigned grid = unsigned(tiles < num_sms() ? tiles : num_sms());
     if (epi == Epi::HIST) {

@@ -88,10 +88,10 @@ def _pick(p, r2, ks):
 class _PermutationJob:
     """Draws the permutation index matrix on a helper thread while the GPU builds the NAM.
 
-    The draws use the reference's exact sequence of legacy-RNG calls on the *global* numpy state
-    (``_stats.py:8-16`` / ``:31``); numpy releases the GIL inside ``randn`` and ``argsort``, so the
-    ~50 ms this takes at 10 000 permutations x 200 samples overlap with the diffusion kernels.  The
-    caller must not touch ``np.random`` until ``result()`` has returned."""
+    The draws reproduce the reference's exact sequence of legacy-RNG calls on the *global* numpy
+    state (``_stats.py:8-16`` / ``:31``) through the native restatement in ``csrc/perm_host.cu``
+    (ctypes releases the GIL), so they overlap with the diffusion kernels.  The caller must not
+    touch ``np.random`` until ``result()`` has returned."""
 
     def __init__(self, y_std, batches, donorids, Nnull):
         import threading
@@ -102,10 +102,9 @@ class _PermutationJob:
             mark("perm thread start")
             try:
                 if donorids is not None:  # _association.py:80-83
-                    bix = _stats.grouplevel_permutation_indices(donorids, y_std, Nnull)
+                    self._out = _stats.grouplevel_permutation_matrix(donorids, y_std, Nnull)
                 else:
-                    bix = _stats.conditional_permutation_indices(batches, Nnull)
-                self._out = None if bix is None else np.ascontiguousarray(bix.T, dtype=np.int32)
+                    self._out = _stats.conditional_permutation_matrix(batches, Nnull)
             except BaseException as exc:  # re-raised on the caller's thread
                 self._exc = exc
             mark("perm thread done")
@@ -128,7 +127,7 @@ def _association(res, perms, Nnull=1000, local_test=True, show_progress=False):
     (``res.x``), U, M, r, the standardised phenotype and ks."""
     out = select_output(show_progress)
     U, M, r, n = res.U, res.M, res.r, res.n
-    dev = res.x.device
+    dev = res.ncorr.device
     y = res.y_std
     ks = res.ks
     kmax = int(max(ks))
@@ -159,7 +158,7 @@ def _association(res, perms, Nnull=1000, local_test=True, show_progress=False):
         comm.broadcast(perm_d, src=0)
     mark("permutations uploaded")
     ld_y = _nam._round_up(max(Kl, 1), 4)
-    ycond_d = torch.zeros((res.x.shape[1], ld_y), dtype=torch.float32, device=dev) if Kl else None
+    ycond_d = torch.zeros((_nam._round_up(n, 8), ld_y), dtype=torch.float32, device=dev) if Kl else None
     ssered_d = torch.empty(Nnull, dtype=torch.float64, device=dev)
     ssefull_d = torch.empty((Nnull, len(ks)), dtype=torch.float64, device=dev)
     y_d = _to_dev(y)
@@ -184,7 +183,9 @@ def _association(res, perms, Nnull=1000, local_test=True, show_progress=False):
         edges_d, thr_d = _to_dev(edges), _to_dev(thresholds)
         hist = torch.zeros((Kl, T), dtype=torch.int32, device=dev)
         obs = torch.zeros((2, T), dtype=torch.int32, device=dev)
-        _lib.null_hist(res.x, n, ycond_d, Kl, edges_d, float(edges[0]), hist)
+        # (cells x n) . (n x Kl) on the tensor cores, histogram epilogue straight out of TMEM
+        ytp = _lib.split_f16(ycond_d, Kl, transpose=True)
+        _lib.null_hist_tc(res.planes, n, ytp, Kl, edges_d, float(edges[0]), hist)
         _lib.obs_hist(res.ncorr, res.valid, edges_d, thr_d, obs[0], obs[1])
         if comm is not None:  # counts over all shards
             comm.all_reduce(hist)
@@ -269,11 +270,11 @@ def association(data, y, sid_name, batches=None, covs=None, donorids=None, ks=No
     mark("QC done (first sync)")
     colmap = stn.labels.get_indexer(sids)  # NAM.reindex(y.index)[filter_samples], :178-181
     res = _nam.resid_nam_device(stn, colmap, covs_f, batches_f, y_std, ridges=ridges,
-                                show_progress=show_progress)
+                                show_progress=show_progress, want_x=return_full)
     mark("resid pass done")
     res.y_std = y_std
     res.ks = ks_eff
-    res.U, svs, res.G = _nam.gram_svd(res.x, n, comm=comm)  # _nam.py:163
+    res.U, svs, res.G = _nam.gram_svd(res.x, n, comm=comm, planes=res.planes)  # _nam.py:163
 
     mark("gram + svd done")
     print("performing association test", file=out)
@@ -281,7 +282,7 @@ def association(data, y, sid_name, batches=None, covs=None, donorids=None, ks=No
 
     # ---- neighbourhood-level outputs (:228-237) ----
     N = stn.N
-    dev = res.x.device
+    dev = res.ncorr.device
     coef_d = torch.empty(N, dtype=torch.float64, device=dev)
     fdr_d = torch.empty(N, dtype=torch.float64, device=dev)
     if key_added in data.obs:
@@ -320,7 +321,7 @@ def association(data, y, sid_name, batches=None, covs=None, donorids=None, ks=No
     xk = res.x[vmask][:, :n]
     full.namresid = pd.DataFrame(xk.t().double().cpu().numpy(), index=sids, columns=cells)
     full.namresid_sampleXpc = pd.DataFrame(res.U, index=sids, columns=pcs)
-    V = _nam.nbhd_loadings(res.x, n, res.U, svs, rows=vmask)
+    V = _nam.nbhd_loadings(res.x, n, res.U, svs, rows=vmask, planes=res.planes)
     full.namresid_nbhdXpc = pd.DataFrame(V, index=cells, columns=pcs)
     full.namresid_svs = pd.Series(svs, index=pcs)[:npcs]
     full.namresid_varexp = pd.Series(svs / n / len(cells), index=pcs)

@@ -48,6 +48,36 @@ def grouplevel_permutation(G, Y, num):
     return None if ix is None else np.asarray(Y)[ix]
 
 
+def conditional_permutation_matrix(B, num):
+    """The transpose of ``conditional_permutation_indices`` as int32 [num x n] (row k = permutation
+    k, the layout ``cna_perm_stats`` consumes), drawn by the native restatement of numpy's legacy
+    generator: the same random stream bit for bit, with the transform, the per-column argsort and
+    the scatter running on all host threads.  Advances ``np.random``'s global state exactly like
+    the reference's calls."""
+    from .. import _lib
+    B = np.asarray(B)
+    batchind = [np.where(B == b)[0] for b in np.unique(B)]
+    off = np.zeros(len(batchind) + 1, dtype=np.int32)
+    np.cumsum([len(bi) for bi in batchind], out=off[1:])
+    return _lib.host_perm_blocks(off, np.concatenate(batchind), num)
+
+
+def grouplevel_permutation_matrix(G, Y, num):
+    """Transpose of ``grouplevel_permutation_indices`` as int32 [num x n] (or None)."""
+    from .. import _lib
+    G = np.asarray(G)
+    Y = np.asarray(Y)
+    Gu = np.unique(G)
+    rep = np.array([np.where(G == g)[0][0] for g in Gu])
+    Yg = Y[rep]
+    Gind = np.searchsorted(Gu, G)
+    if (Yg[Gind] != Y).any():
+        print("ERROR: the value of Y is not identical within each group of samples")
+        return None
+    order = _lib.host_perm_blocks(np.array([0, len(Yg)], dtype=np.int32), None, num)  # [num x donors]
+    return np.ascontiguousarray(rep[order][:, Gind], dtype=np.int32)
+
+
 def threshold_edges(t, atol=1e-8, rtol=1e-5):
     """``_stats.py:51``: histogram edges for ascending thresholds t: t^2 - atol - rtol * t^2."""
     t2 = np.asarray(t, dtype=np.float64) ** 2

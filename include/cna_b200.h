@@ -229,6 +229,28 @@ int cna_cell_fdr(const double *ncorr, const uint8_t *row_valid, int64_t n_rows,
                  double *fdr, void *stream);
 
 /* ------------------------------------------------------------------------------------------
+ * host-side permutation drawing (no GPU involved; runs on the caller's host threads)
+ * ------------------------------------------------------------------------------------------ */
+
+/* out[0..count) = the next `count` deviates of numpy's legacy global generator, i.e. what
+ * np.random.randn(count) would return for the RandomState (MT19937 key[624], pos, has_gauss,
+ * cached gauss) given by np.random.get_state(); the state is advanced in place so that
+ * np.random.set_state() continues the reference's stream.  n_threads <= 0: all host threads (<= 16).
+ * replaces: the np.random.randn calls at _stats.py:12 and :31 (bit-exact). */
+int cna_host_randn(uint32_t *key, int *pos, int *has_gauss, double *gauss, int64_t count, double *out,
+                   int n_threads);
+
+/* Permutation index matrix out [num x ld_out] int32 (row k = permutation k): for every block b
+ * (rows block_off[b]..block_off[b+1]) draws np.random.randn(rows_b, num) from the legacy stream and
+ * takes argsort(axis=0).  With src_pos (the concatenated sample positions of the blocks):
+ * out[k, src_pos[r0+t]] = src_pos[r0 + argsort_k[t]] (conditional_permutation, _stats.py:8-16);
+ * with src_pos == NULL: out[k, r0+t] = argsort_k[t] (grouplevel_permutation, _stats.py:31).
+ * replaces: _stats.py:11-16 and :31 (bit-exact permutations). */
+int cna_host_perm_blocks(uint32_t *key, int *pos, int *has_gauss, double *gauss, int n_blocks,
+                         const int32_t *block_off, const int32_t *src_pos, int64_t num, int32_t *out,
+                         int64_t ld_out, int n_threads);
+
+/* ------------------------------------------------------------------------------------------
  * utilities used by the data generator (not on the timed path)
  * ------------------------------------------------------------------------------------------ */
 

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/cna_b200.h but not exported"
     assert declared == set(_lib.EXPORTS)
-    assert lib.cna_abi_version() == 1
+    assert lib.cna_abi_version() == 2
     assert isinstance(lib.cna_last_error(), bytes)
 
 
@@ -183,3 +183,51 @@ def test_batch_segments():
     ub, order, off = _batch_segments(b)
     assert list(ub) == [0.0, 1.0, 2.0] and list(off) == [0, 2, 3, 6]
     assert [sorted(order[off[i]:off[i + 1]]) for i in range(3)] == [[1, 4], [3], [0, 2, 5]]
+
+
+def test_native_legacy_rng_is_bit_exact():
+    """csrc/perm_host.cu restates numpy's legacy global generator (MT19937 + polar Gaussian with a
+    cached deviate): same deviates, same state afterwards, for odd/even counts and a pending cache."""
+    from cna_b200 import _lib
+    for seed, count, pre in [(0, 100001, 0), (5, 7, 3), (1, 250000, 1), (2, 1, 0), (3, 2, 1), (4, 311, 2),
+                             (6, 624 * 3, 0), (7, 155, 0), (8, 156, 0), (9, 157, 1)]:
+        np.random.seed(seed)
+        np.random.randn(pre)
+        want, tail_w, u_w = np.random.randn(count), np.random.randn(5), np.random.rand(3)
+        np.random.seed(seed)
+        np.random.randn(pre)
+        got, tail_g, u_g = _lib.host_randn(count, n_threads=3), np.random.randn(5), np.random.rand(3)
+        np.testing.assert_array_equal(got, want)
+        np.testing.assert_array_equal(tail_g, tail_w)
+        np.testing.assert_array_equal(u_g, u_w)
+    np.random.seed(11)
+    want = np.concatenate([np.random.randn(k) for k in range(1, 120)])
+    np.random.seed(11)
+    got = np.concatenate([_lib.host_randn(k) for k in range(1, 120)])
+    np.testing.assert_array_equal(got, want)
+
+
+@pytest.mark.parametrize("n,nb,num", [(200, 4, 2000), (50, 1, 333), (333, 7, 257), (12, 12, 40)])
+def test_native_permutations_are_bit_exact(n, nb, num):
+    """Permutation index matrices from the native engine == the reference's numpy call sequence
+    (_stats.py:8-16 and :20-32), including the generator state left behind."""
+    from cna_b200.tl import _stats
+    rng = np.random.default_rng(n + nb)
+    B = rng.integers(0, nb, n)
+    B[:nb] = np.arange(nb)
+    np.random.seed(n)
+    want, after_w = _stats.conditional_permutation_indices(B, num), np.random.randn(4)
+    np.random.seed(n)
+    got, after_g = _stats.conditional_permutation_matrix(B, num), np.random.randn(4)
+    assert got.dtype == np.int32 and got.shape == (num, n)
+    np.testing.assert_array_equal(got, want.T)
+    np.testing.assert_array_equal(after_g, after_w)
+    G = np.arange(n) // 2
+    Y = (G % 3 == 0).astype(float)
+    np.random.seed(n + 1)
+    want = _stats.grouplevel_permutation_indices(G, Y, num)
+    np.random.seed(n + 1)
+    got = _stats.grouplevel_permutation_matrix(G, Y, num)
+    np.testing.assert_array_equal(got, want.T)
+    # phenotype that varies within a donor: the reference prints an error and returns None
+    assert _stats.grouplevel_permutation_matrix(G, rng.normal(size=n), num) is None
