@@ -75,7 +75,7 @@ _SIGNATURES = {
     "cna_gram_simt": [_VP, _I64, _I64, _INT, _VP, _VP],
     "cna_right_multiply": [_VP, _I64, _I64, _INT, _VP, _I64, _INT, _VP, _I64, _VP],
     "cna_perm_stats": [_VP, _VP, _I64, _INT, _VP, _VP, _INT, _VP, _INT, _VP, _INT, _VP, _VP, _VP,
-                       _I64, _INT, _VP],
+                       _I64, _INT, _VP, _VP, _I64, _VP],
     "cna_null_hist": [_VP, _I64, _I64, _INT, _VP, _I64, _INT, _VP, _INT, _DBL, _VP, _VP],
     "cna_obs_hist": [_VP, _VP, _I64, _VP, _VP, _INT, _VP, _VP, _VP],
     "cna_absmax": [_VP, _VP, _I64, _VP, _VP],
@@ -256,17 +256,24 @@ def right_multiply(x, n, b, n_out, out):
                                      _ptr(out, torch.float32, "out"), out.shape[1], _stream())
 
 
-def perm_stats(y, perm, C, W, Ut, ks, ssered, ssefull, ycond, n_local):
+def perm_stats(y, perm, C, W, Ut, ks, ssered, ssefull, ycond, n_local, planes=None):
+    """Ut / ks / ssefull may be None (conditioning only); ``planes`` = Planes [n_local x n] that
+    receive the conditioned phenotypes transposed (zero-initialised by the caller)."""
     K, n = perm.shape
     r = 0 if C is None else C.shape[1]
+    kmax = 0 if Ut is None else Ut.shape[0]
     _call("cna_perm_stats", _ptr(y, torch.float64, "y"), _ptr(perm, torch.int32, "perm"), K, n,
                                  _ptr(C, torch.float64, "C") if r else None,
                                  _ptr(W, torch.float64, "W") if r else None, r,
-                                 _ptr(Ut, torch.float64, "Ut"), Ut.shape[0], _ptr(ks, torch.int32, "ks"),
-                                 ks.numel(), _ptr(ssered, torch.float64, "ssered"),
-                                 _ptr(ssefull, torch.float64, "ssefull"),
+                                 _ptr(Ut, torch.float64, "Ut") if kmax else None, kmax,
+                                 _ptr(ks, torch.int32, "ks") if kmax else None, ks.numel() if kmax else 0,
+                                 _ptr(ssered, torch.float64, "ssered", allow_none=True),
+                                 _ptr(ssefull, torch.float64, "ssefull", allow_none=True),
                                  _ptr(ycond, torch.float32, "ycond", allow_none=True),
-                                 0 if ycond is None else ycond.shape[1], int(n_local), _stream())
+                                 0 if ycond is None else ycond.shape[1], int(n_local),
+                                 None if planes is None else _ptr(planes.hi, torch.float16, "yt_hi"),
+                                 None if planes is None else _ptr(planes.lo, torch.float16, "yt_lo"),
+                                 0 if planes is None else planes.ld, _stream())
 
 
 def null_hist(x, n, ycond, n_null, edges, edge0, hist):
@@ -305,10 +312,11 @@ class Planes:
     """fp16 hi/lo planes of an fp32 matrix (x = hi + lo to 2^-22): the operand format of the
     tcgen05 kernels.  ``t`` is one [2, rows, ld16] tensor (plane 0 = hi, 1 = lo)."""
 
-    def __init__(self, rows, cols, device):
+    def __init__(self, rows, cols, device, zero=False):
         self.rows, self.cols = int(rows), int(cols)
         self.ld = round_up(max(self.cols, 1), 16)
-        self.t = torch.empty((2, self.rows, self.ld), dtype=torch.float16, device=device)
+        alloc = torch.zeros if zero else torch.empty
+        self.t = alloc((2, self.rows, self.ld), dtype=torch.float16, device=device)
 
     @property
     def hi(self):

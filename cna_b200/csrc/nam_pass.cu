@@ -93,7 +93,9 @@ batch_kurtosis_kernel(const float *__restrict__ s, int64_t ld, int64_t n_rows,
 // ---------------------------------------------------------------------------------------------
 // fused select / centre / residualise / standardise / ncorr pass
 // ---------------------------------------------------------------------------------------------
-template <int NQ>
+// A warp owns R consecutive rows at a time: every W / C coefficient read from shared memory is used
+// for R rows, and the R independent shuffle reductions overlap each other's latency.
+template <int NQ, int R>
 __global__ void __launch_bounds__(256) resid_kernel(cna_resid_args a) {
     extern __shared__ double sm[];
     const int warps = blockDim.x >> 5;
@@ -103,8 +105,8 @@ __global__ void __launch_bounds__(256) resid_kernel(cna_resid_args a) {
     double *Ct = Wt + r * n;                 // [r][n]  (transposed copy of C [n x r])
     double *ys = Ct + r * n;                 // [n]
     double *invc = ys + n;                   // [n]
-    double *proj = invc + n;                 // [warps][r]
-    double *rowbuf = proj + warps * r;       // [warps][n]   (only when want_kurt)
+    double *proj = invc + n;                 // [warps][R][r]
+    double *rowbuf = proj + warps * R * r;   // [warps][n]   (only when want_kurt)
     double *means = rowbuf + (want_kurt ? warps * n : 0);  // [warps][nb]
     int *colmap = reinterpret_cast<int *>(means + (want_kurt ? warps * nb : 0));  // [n]
     int *seg_order = colmap + n;             // [n]
@@ -126,114 +128,154 @@ __global__ void __launch_bounds__(256) resid_kernel(cna_resid_args a) {
     __syncthreads();
 
     int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    double *pw = proj + w * r;
+    double *pw = proj + w * R * r;
     double *rb = rowbuf + w * n, *mb = means + w * nb;
     const double dn = double(n);
-    int64_t stride = int64_t(gridDim.x) * warps;
-    for (int64_t row = int64_t(blockIdx.x) * warps + w; row < a.n_rows; row += stride) {
-        const float *p = a.s + row * a.ld_s;
-        float *o = a.x_out ? a.x_out + row * a.ld_x : nullptr;
-        __half *ph = a.x16_hi ? static_cast<__half *>(a.x16_hi) + row * a.ld16 : nullptr;
-        __half *pl = a.x16_hi ? static_cast<__half *>(a.x16_lo) + row * a.ld16 : nullptr;
-        double x[NQ];
-        double sum = 0.0;
+    const int64_t stride = int64_t(gridDim.x) * warps * R;
+    for (int64_t row0 = (int64_t(blockIdx.x) * warps + w) * R; row0 < a.n_rows; row0 += stride) {
+        double x[R][NQ];
+        bool valid[R];
+        double sum[R], ss[R];
 #pragma unroll
-        for (int q = 0; q < NQ; ++q) {
-            int m = lane + 32 * q;
-            x[q] = (m < n) ? double(__ldg(p + colmap[m])) * invc[m] : 0.0;
-            sum += x[q];
-        }
-        double mean = warp_sum(sum) / dn;
-        double ss = 0.0;
-#pragma unroll
-        for (int q = 0; q < NQ; ++q) {
-            int m = lane + 32 * q;
-            x[q] = (m < n) ? x[q] - mean : 0.0;  // _nam.py:122
-            ss += x[q] * x[q];
-        }
-        double var0 = warp_sum(ss) / (dn - 1.0);
-        bool keep = a.row_keep ? (a.row_keep[row] != 0) : true;
-        bool valid = keep && !(var0 == 0.0);  // _association.py:182-185
-        if (!valid) {
+        for (int i = 0; i < R; ++i) {
+            const int64_t row = row0 + i;
+            const float *p = a.s + (row < a.n_rows ? row : row0) * a.ld_s;
+            sum[i] = 0.0;
 #pragma unroll
             for (int q = 0; q < NQ; ++q) {
                 int m = lane + 32 * q;
-                if (o && m < a.ld_x) o[m] = 0.f;
-                if (ph && m < a.ld16) {
-                    ph[m] = __float2half_rn(0.f);
-                    pl[m] = __float2half_rn(0.f);
-                }
+                x[i][q] = (m < n) ? double(__ldg(p + colmap[m])) * invc[m] : 0.0;
+                sum[i] += x[i][q];
             }
-            if (lane == 0) {
-                if (a.kurt) a.kurt[row] = nan("");
-                a.ncorr[row] = 0.0;
-                a.row_valid[row] = 0;
+        }
+#pragma unroll
+        for (int i = 0; i < R; ++i) sum[i] = warp_sum(sum[i]) / dn;
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+            ss[i] = 0.0;
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                int m = lane + 32 * q;
+                x[i][q] = (m < n) ? x[i][q] - sum[i] : 0.0;  // _nam.py:122
+                ss[i] += x[i][q] * x[i][q];
             }
-            continue;
+        }
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+            double var0 = warp_sum(ss[i]) / (dn - 1.0);
+            const int64_t row = row0 + i;
+            bool keep = (row < a.n_rows) && (a.row_keep ? (a.row_keep[row] != 0) : true);
+            valid[i] = keep && !(var0 == 0.0);  // _association.py:182-185
         }
         // rank-r update X <- X - (X Wt^T) C^T   (_nam.py:133-135 / :146-148 with M = I - C.W)
         for (int rr = 0; rr < r; ++rr) {
-            double acc = 0.0;
+            double acc[R];
+#pragma unroll
+            for (int i = 0; i < R; ++i) acc[i] = 0.0;
 #pragma unroll
             for (int q = 0; q < NQ; ++q) {
                 int m = lane + 32 * q;
-                if (m < n) acc += x[q] * Wt[rr * n + m];
+                double wv = (m < n) ? Wt[rr * n + m] : 0.0;
+#pragma unroll
+                for (int i = 0; i < R; ++i) acc[i] += x[i][q] * wv;
             }
-            acc = warp_sum(acc);
-            if (lane == 0) pw[rr] = acc;
+#pragma unroll
+            for (int i = 0; i < R; ++i) acc[i] = warp_sum(acc[i]);
+            if (lane == 0) {
+#pragma unroll
+                for (int i = 0; i < R; ++i) pw[i * r + rr] = acc[i];
+            }
         }
         __syncwarp();
         for (int rr = 0; rr < r; ++rr) {
-            double pr = pw[rr];
+            double pr[R];
+#pragma unroll
+            for (int i = 0; i < R; ++i) pr[i] = pw[i * r + rr];
 #pragma unroll
             for (int q = 0; q < NQ; ++q) {
                 int m = lane + 32 * q;
-                if (m < n) x[q] -= pr * Ct[rr * n + m];
+                double cv = (m < n) ? Ct[rr * n + m] : 0.0;
+#pragma unroll
+                for (int i = 0; i < R; ++i) x[i][q] -= pr[i] * cv;
             }
         }
         __syncwarp();
         if (want_kurt) {  // _nam.py:150-155
 #pragma unroll
-            for (int q = 0; q < NQ; ++q) {
-                int m = lane + 32 * q;
-                if (m < n) rb[m] = x[q];
+            for (int i = 0; i < R; ++i) {
+                const int64_t row = row0 + i;
+                if (row >= a.n_rows) break;  // uniform over the warp
+                if (!valid[i]) {
+                    if (lane == 0) a.kurt[row] = nan("");
+                    continue;
+                }
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) {
+                    int m = lane + 32 * q;
+                    if (m < n) rb[m] = x[i][q];
+                }
+                __syncwarp();
+                double k = batch_kurtosis_of_row(rb, mb, seg_order, seg_off, nb, lane);
+                if (lane == 0) a.kurt[row] = k;
+                __syncwarp();
             }
-            __syncwarp();
-            double k = batch_kurtosis_of_row(rb, mb, seg_order, seg_off, nb, lane);
-            if (lane == 0) a.kurt[row] = k;
         } else if (a.kurt && lane == 0) {
-            a.kurt[row] = nan("");
+#pragma unroll
+            for (int i = 0; i < R; ++i)
+                if (row0 + i < a.n_rows) a.kurt[row0 + i] = nan("");
         }
         // ddof=1 standardisation (_nam.py:159; pandas std recomputes the mean)
-        double s1 = 0.0;
+        double s1[R], s2[R], dot[R];
 #pragma unroll
-        for (int q = 0; q < NQ; ++q) s1 += x[q];
-        double mean2 = warp_sum(s1) / dn;
-        double s2 = 0.0;
+        for (int i = 0; i < R; ++i) {
+            s1[i] = 0.0;
 #pragma unroll
-        for (int q = 0; q < NQ; ++q) {
-            int m = lane + 32 * q;
-            double d = (m < n) ? x[q] - mean2 : 0.0;
-            s2 += d * d;
+            for (int q = 0; q < NQ; ++q) s1[i] += x[i][q];
         }
-        double sd = sqrt(warp_sum(s2) / (dn - 1.0));
-        double dot = 0.0;
 #pragma unroll
-        for (int q = 0; q < NQ; ++q) {
-            int m = lane + 32 * q;
-            double v = (m < n) ? x[q] / sd : 0.0;
-            if (m < n) dot += v * ys[m];
-            if (o && m < a.ld_x) o[m] = float(v);
-            if (ph && m < a.ld16) {  // v = hi + lo to 2^-22
-                __half h = __float2half_rn(float(v));
-                ph[m] = h;
-                pl[m] = __float2half_rn(float(v - double(__half2float(h))));
+        for (int i = 0; i < R; ++i) s1[i] = warp_sum(s1[i]) / dn;
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+            s2[i] = 0.0;
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                int m = lane + 32 * q;
+                double d = (m < n) ? x[i][q] - s1[i] : 0.0;
+                s2[i] += d * d;
             }
         }
-        dot = warp_sum(dot);
-        if (lane == 0) {
-            a.ncorr[row] = dot / dn;  // _association.py:77
-            a.row_valid[row] = 1;
+#pragma unroll
+        for (int i = 0; i < R; ++i) s2[i] = sqrt(warp_sum(s2[i]) / (dn - 1.0));
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+            const int64_t row = row0 + i;
+            dot[i] = 0.0;
+            if (row >= a.n_rows) continue;  // uniform over the warp
+            float *o = a.x_out ? a.x_out + row * a.ld_x : nullptr;
+            __half *ph = a.x16_hi ? static_cast<__half *>(a.x16_hi) + row * a.ld16 : nullptr;
+            __half *pl = a.x16_hi ? static_cast<__half *>(a.x16_lo) + row * a.ld16 : nullptr;
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                int m = lane + 32 * q;
+                double v = (m < n && valid[i]) ? x[i][q] / s2[i] : 0.0;  // rows of dropped cells are zero
+                if (m < n) dot[i] += v * ys[m];
+                if (o && m < a.ld_x) o[m] = float(v);
+                if (ph && m < a.ld16) {  // v = hi + lo to 2^-22
+                    __half h = __float2half_rn(float(v));
+                    ph[m] = h;
+                    pl[m] = __float2half_rn(float(v - double(__half2float(h))));
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+            const int64_t row = row0 + i;
+            if (row >= a.n_rows) continue;
+            double d = warp_sum(dot[i]);
+            if (lane == 0) {
+                a.ncorr[row] = valid[i] ? d / dn : 0.0;  // _association.py:77
+                a.row_valid[row] = valid[i] ? 1 : 0;
+            }
         }
     }
 }
@@ -279,27 +321,28 @@ int cna_resid_pass(const cna_resid_args *args, void *stream) {
     const int threads = 256, warps = threads / 32;
     const bool want_kurt = a.kurt && a.n_batches > 1;
     CNA_REQUIRE(!want_kurt || (a.seg_order && a.seg_off), "cna_resid_pass: batch segments missing");
-    size_t smem = sizeof(double) * (2 * size_t(a.r) * a.n + 2 * size_t(a.n) + size_t(warps) * a.r +
+    int nq = (a.n + 31) / 32;
+    const int R = nq <= 8 ? 4 : (nq <= 16 ? 2 : 1);  // rows per warp (register budget: R * NQ doubles)
+    size_t smem = sizeof(double) * (2 * size_t(a.r) * a.n + 2 * size_t(a.n) + size_t(warps) * R * a.r +
                                     (want_kurt ? size_t(warps) * (a.n + a.n_batches) : 0)) +
                   sizeof(int) * (2 * size_t(a.n) + a.n_batches + 2);
     CNA_REQUIRE(smem <= 200 * 1024,
                 "cna_resid_pass: n=%d, r=%d needs %zu bytes of shared memory (limit 200 KiB)", a.n, a.r, smem);
-    int64_t blocks_needed = (a.n_rows + warps - 1) / warps;
-    int64_t cap = int64_t(num_sms()) * 4;
+    int64_t blocks_needed = (a.n_rows + int64_t(warps) * R - 1) / (int64_t(warps) * R);
+    int64_t cap = int64_t(num_sms()) * 8;
     unsigned grid = unsigned(blocks_needed < cap ? blocks_needed : cap);
-    int nq = (a.n + 31) / 32;
     cudaStream_t st = as_stream(stream);
-#define CNA_RESID(NQ)                                                                              \
-    do {                                                                                           \
-        CNA_CUDA(cudaFuncSetAttribute(resid_kernel<NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                      int(smem)));                                                 \
-        resid_kernel<NQ><<<grid, threads, smem, st>>>(a);                                          \
+#define CNA_RESID(NQ, RR)                                                                              \
+    do {                                                                                               \
+        CNA_CUDA(cudaFuncSetAttribute(resid_kernel<NQ, RR>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                      int(smem)));                                                     \
+        resid_kernel<NQ, RR><<<grid, threads, smem, st>>>(a);                                          \
     } while (0)
-    if (nq <= 2) CNA_RESID(2);
-    else if (nq <= 4) CNA_RESID(4);
-    else if (nq <= 8) CNA_RESID(8);
-    else if (nq <= 16) CNA_RESID(16);
-    else CNA_RESID(32);
+    if (nq <= 2) CNA_RESID(2, 4);
+    else if (nq <= 4) CNA_RESID(4, 4);
+    else if (nq <= 8) CNA_RESID(8, 4);
+    else if (nq <= 16) CNA_RESID(16, 2);
+    else CNA_RESID(32, 1);
 #undef CNA_RESID
     CNA_LAUNCHED("resid_kernel");
     return CNA_OK;

@@ -5,6 +5,8 @@
 // permutation from the Python loop at :84, and :94-97 (conditioned null phenotypes for the
 // neighbourhood-level test).  The F survival function (scipy.special.fdtrc, :46) and the argmin over
 // ks stay with the caller: they are O(Nnull * len(ks)) scalar work.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace cna {
@@ -15,7 +17,8 @@ perm_stats_kernel(const double *__restrict__ y, const int32_t *__restrict__ perm
                   const double *__restrict__ C, const double *__restrict__ W, int r,
                   const double *__restrict__ Ut, int kmax, const int32_t *__restrict__ ks, int nks,
                   double *__restrict__ ssered, double *__restrict__ ssefull,
-                  float *__restrict__ ycond, int64_t ld_y, int n_local) {
+                  float *__restrict__ ycond, int64_t ld_y, int n_local, __half *__restrict__ yt_hi,
+                  __half *__restrict__ yt_lo, int64_t ld16) {
     extern __shared__ double sm[];
     double *ys = sm;               // [n]
     double *Ws = ys + n;           // [r][n]
@@ -83,13 +86,20 @@ perm_stats_kernel(const double *__restrict__ y, const int32_t *__restrict__ perm
             int m = lane + 32 * q;
             if (m < n) {
                 sr += z[q] * z[q];
-                if (k < n_local) ycond[int64_t(m) * ld_y + k] = float(z[q]);
+                if (k < n_local) {
+                    if (ycond) ycond[int64_t(m) * ld_y + k] = float(z[q]);
+                    if (yt_hi) {  // transposed fp16 hi/lo planes: the B operand of the tensor-core null GEMM
+                        __half h = __float2half_rn(float(z[q]));
+                        yt_hi[k * ld16 + m] = h;
+                        yt_lo[k * ld16 + m] = __float2half_rn(float(z[q] - double(__half2float(h))));
+                    }
+                }
             } else {
                 z[q] = 0.0;
             }
         }
         sr = warp_sum(sr);  // ssered = zc.zc  (_association.py:43)
-        if (lane == 0) ssered[k] = sr;
+        if (lane == 0 && ssered) ssered[k] = sr;
         // residual after regressing on the first j PCs, evaluated at j in ks (_association.py:35-42)
         int next = 0;
         for (int j = 0; j < kmax && next < nks; ++j) {
@@ -125,10 +135,13 @@ using namespace cna;
 extern "C" int cna_perm_stats(const double *y, const int32_t *perm, int64_t K, int n, const double *C,
                               const double *W, int r, const double *Ut, int kmax, const int32_t *ks,
                               int nks, double *ssered, double *ssefull, float *ycond, int64_t ld_y,
-                              int n_local, void *stream) {
-    CNA_REQUIRE(K >= 0 && n >= 2 && n <= 1024 && r >= 0 && kmax >= 1 && kmax <= n && nks >= 1,
+                              int n_local, void *yt_hi, void *yt_lo, int64_t ld16, void *stream) {
+    CNA_REQUIRE(K >= 0 && n >= 2 && n <= 1024 && r >= 0 && kmax >= 0 && kmax <= n && nks >= 0,
                 "cna_perm_stats: bad shape (K=%lld n=%d r=%d kmax=%d nks=%d)", (long long)K, n, r, kmax, nks);
-    CNA_REQUIRE(n_local == 0 || (ycond && ld_y >= n_local), "cna_perm_stats: ycond buffer too small");
+    CNA_REQUIRE(kmax == 0 || (Ut && ks && nks >= 1 && ssefull), "cna_perm_stats: PCs requested but Ut/ks/ssefull missing");
+    CNA_REQUIRE(n_local == 0 || ((ycond && ld_y >= n_local) || (yt_hi && yt_lo && ld16 >= n)),
+                "cna_perm_stats: conditioned-phenotype buffer missing or too small");
+    if (kmax == 0) nks = 0;
     if (K == 0) return CNA_OK;
     const int threads = 256, warps = threads / 32;
     size_t smem = sizeof(double) * (size_t(n) + 2 * size_t(r) * n + size_t(kmax) * n + size_t(warps) * r) +
@@ -144,7 +157,9 @@ extern "C" int cna_perm_stats(const double *y, const int32_t *perm, int64_t K, i
         CNA_CUDA(cudaFuncSetAttribute(perm_stats_kernel<NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                       int(smem)));                                                    \
         perm_stats_kernel<NQ><<<grid, threads, smem, st>>>(y, perm, K, n, C, W, r, Ut, kmax, ks, nks, \
-                                                            ssered, ssefull, ycond, ld_y, n_local);   \
+                                                            ssered, ssefull, ycond, ld_y, n_local,    \
+                                                            static_cast<__half *>(yt_hi),             \
+                                                            static_cast<__half *>(yt_lo), ld16);      \
     } while (0)
     if (nq <= 2) CNA_PERM(2);
     else if (nq <= 4) CNA_PERM(4);

@@ -13,14 +13,15 @@ import scipy.stats as st
 import torch
 
 from .. import _lib
-from . import _nam, _stats
+from . import _graph, _nam, _stats
 from ._graph import _to_dev
 from ._out import select_output
 from ._timing import mark, report
 
 
-def check_inputs(data, y, sid_name, batches, covs, donorids, allow_low_sample_size):
-    """``_association.py:131-173`` — same checks, exception types and messages."""
+def check_inputs(data, y, sid_name, batches, covs, donorids, allow_low_sample_size, present=None):
+    """``_association.py:131-173`` — same checks, exception types and messages.  ``present`` may
+    carry the already-known unique sample ids of ``data.obs[sid_name]``."""
     if not isinstance(y, pd.Series):
         raise TypeError(f"'y' must be a pandas Series, but got {type(y)}")
     if batches is not None and not isinstance(batches, pd.Series):
@@ -29,7 +30,8 @@ def check_inputs(data, y, sid_name, batches, covs, donorids, allow_low_sample_si
         raise TypeError(f"'covs' must be a pandas DataFrame, but got {type(covs)}")
     if donorids is not None and not isinstance(donorids, pd.Series):
         raise TypeError(f"'donorids' must be a pandas Series, but got {type(donorids)}")
-    present = data.obs[sid_name].unique()
+    if present is None:
+        present = data.obs[sid_name].unique()
     if not y.index.isin(present).all():
         print("WARNING: index of 'y' contains values not present in 'data[sid_name]'. "
               "These samples will be ignored.")
@@ -58,6 +60,23 @@ def check_inputs(data, y, sid_name, batches, covs, donorids, allow_low_sample_si
             "power, you can do so by invoking the association(...) function with the argument "
             "allow_low_sample_size=True.")
     return batches, filter_samples
+
+
+_PINNED = {}
+
+
+def _to_host_pinned(t):
+    """Device tensor -> numpy array through a cached page-locked staging buffer (a pageable D2H of
+    the two per-cell float64 columns costs more than the kernels that produced them).  The returned
+    array is a view of the staging buffer: consume it before the next call."""
+    key = (t.dtype, tuple(t.shape))
+    buf = _PINNED.get(key)
+    if buf is None:
+        _PINNED.clear()
+        buf = _PINNED[key] = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    buf.copy_(t, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return buf.numpy()
 
 
 def default_ks(n):
@@ -112,6 +131,10 @@ class _PermutationJob:
         self._thread = threading.Thread(target=work, name="cna-permutations", daemon=True)
         self._thread.start()
 
+    def cancel(self):
+        """Wait for the draws without using them (an error is propagating on the caller's thread)."""
+        self._thread.join()
+
     def result(self):
         self._thread.join()
         if self._exc is not None:
@@ -122,15 +145,69 @@ class _PermutationJob:
 
 
 def _association(res, perms, Nnull=1000, local_test=True, show_progress=False):
-    """``_association.py:10-129`` after seeding / permutation drawing (done by the caller so that
-    they overlap with the NAM kernels).  ``res`` carries the device-resident residualised NAM
-    (``res.x``), U, M, r, the standardised phenotype and ks."""
+    """``_nam.py:163`` (Gram + SVD of the residualised NAM) and ``_association.py:10-129`` after
+    seeding / permutation drawing (done by the caller so that they overlap with the NAM kernels).
+    ``res`` carries the device-resident residualised NAM (``res.planes`` / ``res.x``), M, r, the
+    standardised phenotype and ks; U, svs and the Gram are added to it.
+
+    Order of work: the Gram and max|ncorr| are launched and read back with one sync; the conditioned
+    null phenotypes (which need M but not U) and the null GEMM + histograms are launched next, so the
+    GPU works on them while the host does the n x n SVD; the PC regressions of all permutations
+    follow once U is known."""
     out = select_output(show_progress)
-    U, M, r, n = res.U, res.M, res.r, res.n
+    M, r, n = res.M, res.r, res.n
     dev = res.ncorr.device
     y = res.y_std
     ks = res.ks
     kmax = int(max(ks))
+    comm = res.comm
+    Kl = min(1000, Nnull) if local_test else 0
+
+    G_d = _nam.gram_device(res.x, n, comm=comm, planes=res.planes)
+    mx = torch.zeros(1, dtype=torch.float64, device=dev)
+    if local_test:
+        _lib.absmax(res.ncorr, res.valid, mx)
+        if comm is not None:
+            comm.all_reduce(mx, op="max")
+    Gh = G_d.cpu().numpy()
+    mark("gram on host")
+
+    # ---- permutations: indices from the host RNG (bit-exact), everything else on the device ----
+    if perms is not None:
+        perm_d = _to_dev(perms.result())
+    else:  # a shard other than rank 0: the indices are drawn once, by rank 0
+        perm_d = torch.empty((Nnull, n), dtype=torch.int32, device=dev)
+    if comm is not None:
+        comm.broadcast(perm_d, src=0)
+    mark("permutations uploaded")
+    y_d = _to_dev(y)
+    C_d = _to_dev(res.C) if r else None
+    W_d = _to_dev(np.ascontiguousarray(res.W_last)) if r else None
+
+    # ---- neighbourhood-level null (:92-103): launched before the SVD so the two overlap ----
+    fdrs, fdr_5p_t, fdr_10p_t = None, None, None
+    if local_test:
+        print("computing neighborhood-level FDRs", file=out)
+        maxcorr = max(float(mx.item()), 0.001)  # :101
+        thresholds = np.arange(maxcorr / 4, maxcorr, maxcorr / 400)  # :102
+        edges = _stats.threshold_edges(thresholds)
+        T = len(thresholds)
+        edges_d, thr_d = _to_dev(edges), _to_dev(thresholds)
+        hist = torch.zeros((Kl, T), dtype=torch.int32, device=dev)
+        obs = torch.zeros((2, T), dtype=torch.int32, device=dev)
+        # ycond_ = M.y_[:, :Kl] / std (ddof=1) (:94-97) as transposed fp16 hi/lo planes, then
+        # (cells x n) . (n x Kl) on the tensor cores with the histogram epilogue straight out of TMEM
+        ytp = _lib.Planes(Kl, n, dev, zero=True)
+        _lib.perm_stats(y_d, perm_d[:Kl], C_d, W_d, None, None, None, None, None, Kl, planes=ytp)
+        _lib.null_hist_tc(res.planes, n, ytp, Kl, edges_d, float(edges[0]), hist)
+        _lib.obs_hist(res.ncorr, res.valid, edges_d, thr_d, obs[0], obs[1])
+        if comm is not None:  # counts over all shards
+            comm.all_reduce(hist)
+            comm.all_reduce(obs)
+    mark("null kernels launched")
+
+    U, svs, res.G = _nam.svd_of_gram(Gh)  # _nam.py:105
+    res.U, res.svs = U, svs
 
     # ---- observed phenotype (:64-74): n-sized host arithmetic in float64 -----------------
     ycond = M.dot(y)
@@ -146,53 +223,12 @@ def _association(res, perms, Nnull=1000, local_test=True, show_progress=False):
     yhat = U[:, :k].dot(beta)
     r2_perpc = (beta / np.sqrt(ycond.dot(ycond))) ** 2  # :74
 
-    # ---- permutations: indices from the host RNG (bit-exact), everything else on the device ----
-    Kl = min(1000, Nnull) if local_test else 0
-    comm = res.comm
-    mark("observed stats done; waiting for permutations")
-    if perms is not None:
-        perm_d = _to_dev(perms.result())
-    else:  # a shard other than rank 0: the indices are drawn once, by rank 0
-        perm_d = torch.empty((Nnull, n), dtype=torch.int32, device=dev)
-    if comm is not None:
-        comm.broadcast(perm_d, src=0)
-    mark("permutations uploaded")
-    ld_y = _nam._round_up(max(Kl, 1), 4)
-    ycond_d = torch.zeros((_nam._round_up(n, 8), ld_y), dtype=torch.float32, device=dev) if Kl else None
+    # ---- PC regressions of every permuted phenotype (:84), then the global p-value (:85-88) ----
     ssered_d = torch.empty(Nnull, dtype=torch.float64, device=dev)
     ssefull_d = torch.empty((Nnull, len(ks)), dtype=torch.float64, device=dev)
-    y_d = _to_dev(y)
-    C_d = _to_dev(res.C) if r else None
-    W_d = _to_dev(np.ascontiguousarray(res.W_last)) if r else None
     Ut_d = _to_dev(np.ascontiguousarray(U[:, :kmax].T))
     ks_d = _to_dev(np.asarray(ks, dtype=np.int32))
-    _lib.perm_stats(y_d, perm_d, C_d, W_d, Ut_d, ks_d, ssered_d, ssefull_d, ycond_d, Kl)
-
-    # ---- neighbourhood-level null: launch before the host-side F tests so they overlap ----
-    fdrs, fdr_5p_t, fdr_10p_t = None, None, None
-    if local_test:
-        print("computing neighborhood-level FDRs", file=out)
-        mx = torch.zeros(1, dtype=torch.float64, device=dev)
-        _lib.absmax(res.ncorr, res.valid, mx)
-        if comm is not None:
-            comm.all_reduce(mx, op="max")
-        maxcorr = max(float(mx.item()), 0.001)  # :101
-        thresholds = np.arange(maxcorr / 4, maxcorr, maxcorr / 400)  # :102
-        edges = _stats.threshold_edges(thresholds)
-        T = len(thresholds)
-        edges_d, thr_d = _to_dev(edges), _to_dev(thresholds)
-        hist = torch.zeros((Kl, T), dtype=torch.int32, device=dev)
-        obs = torch.zeros((2, T), dtype=torch.int32, device=dev)
-        # (cells x n) . (n x Kl) on the tensor cores, histogram epilogue straight out of TMEM
-        ytp = _lib.split_f16(ycond_d, Kl, transpose=True)
-        _lib.null_hist_tc(res.planes, n, ytp, Kl, edges_d, float(edges[0]), hist)
-        _lib.obs_hist(res.ncorr, res.valid, edges_d, thr_d, obs[0], obs[1])
-        if comm is not None:  # counts over all shards
-            comm.all_reduce(hist)
-            comm.all_reduce(obs)
-
-    mark("null kernels launched")
-    # ---- global p-value (:84-88) ----
+    _lib.perm_stats(y_d, perm_d, C_d, W_d, Ut_d, ks_d, ssered_d, ssefull_d, None, 0)
     nullp, nullr2 = _f_pvalues(ssered_d.cpu().numpy(), ssefull_d.cpu().numpy(), ks, n, r)
     _, nullminps, nullr2s = _pick(nullp, nullr2, ks)
     nhit = int((nullminps <= p + 1e-8).sum())
@@ -228,8 +264,14 @@ def association(data, y, sid_name, batches=None, covs=None, donorids=None, ks=No
     if bad:  # the reference forwards **kwargs to _association(), which rejects anything else
         raise TypeError(f"_association() got an unexpected keyword argument '{sorted(bad)[0]}'")
     mark("association() entered")
+    for name, val, kind in (("y", y, pd.Series), ("batches", batches, pd.Series), ("covs", covs, pd.DataFrame),
+                            ("donorids", donorids, pd.Series)):
+        if val is not None and not isinstance(val, kind):  # :132-139, before any device work
+            raise TypeError(f"'{name}' must be a pandas {kind.__name__}, but got {type(val)}")
+    # one factorisation of the sample-id column serves the input checks (:140-143) and the NAM (:51)
+    codes = _graph.sample_codes(data, sid_name)
     batches, filter_samples = check_inputs(data, y, sid_name, batches, covs, donorids,
-                                           allow_low_sample_size)
+                                           allow_low_sample_size, present=codes[0])
     mark("check_inputs done")
     Nnull = kwargs.get("Nnull", 1000)
     local_test = kwargs.get("local_test", True)
@@ -247,11 +289,6 @@ def association(data, y, sid_name, batches=None, covs=None, donorids=None, ks=No
     ks_eff = default_ks(n) if ks is None else ks
     r = _nam.design_matrix(covs_f, batches_f, n)[0].shape[1]
 
-    # ---- launch the diffusion (asynchronous unless nsteps is None) ----
-    print("computing NAM", file=out)
-    stn = _nam._nam_device(data, sid_name, nsteps=nsteps, show_progress=show_progress)
-
-    mark("diffusion launched")
     if kwargs.get("seed") is not None:
         np.random.seed(kwargs["seed"])  # :15-16
     if max(ks_eff) + r >= n:  # :29-33 (the reference raises this after seeding, before any draw)
@@ -260,10 +297,21 @@ def association(data, y, sid_name, batches=None, covs=None, donorids=None, ks=No
             f"Currently it is {max(ks_eff) + r} while n is {n}. Either reduce the number of covariates "
             "or reduce the number of PCs to consider using the optional argument ks=[...].")
     perm_batches = np.ones(n) if kwargs.get("force_permute_all", False) else batches_f  # :17-18
-    comm = stn.comm
+    comm = getattr(data, "comm", None)
     if comm is not None and return_full:
         raise NotImplementedError("return_full=True is not supported on a cell-axis shard")
+    # the permutation draws only need the sample-level inputs: start them before any GPU work
     perms = _PermutationJob(y_std, perm_batches, donor_f, Nnull) if comm is None or comm.rank == 0 else None
+
+    # ---- launch the diffusion (asynchronous unless nsteps is None) ----
+    print("computing NAM", file=out)
+    try:
+        stn = _nam._nam_device(data, sid_name, nsteps=nsteps, show_progress=show_progress, codes=codes)
+    except BaseException:
+        if perms is not None:
+            perms.cancel()
+        raise
+    mark("diffusion launched")
 
     # ---- QC, residualisation, Gram + SVD ----
     _nam._qc_device(stn, batches, show_progress=show_progress)
@@ -274,11 +322,9 @@ def association(data, y, sid_name, batches=None, covs=None, donorids=None, ks=No
     mark("resid pass done")
     res.y_std = y_std
     res.ks = ks_eff
-    res.U, svs, res.G = _nam.gram_svd(res.x, n, comm=comm, planes=res.planes)  # _nam.py:163
-
-    mark("gram + svd done")
     print("performing association test", file=out)
     core = _association(res, perms, Nnull=Nnull, local_test=local_test, show_progress=show_progress)
+    svs = res.svs
 
     # ---- neighbourhood-level outputs (:228-237) ----
     N = stn.N
@@ -300,11 +346,11 @@ def association(data, y, sid_name, batches=None, covs=None, donorids=None, ks=No
         pad = torch.zeros((2, stn.rows_per), dtype=torch.float64, device=dev)
         pad[:, :N] = both
         both = comm.all_gather_rows(pad.t().contiguous())[: len(data.obs)].t()
-    both = both.cpu().numpy()
+    both = _to_host_pinned(both)
     mark("results on host")
-    data.obs[key_added] = both[0]
+    data.obs[key_added] = both[0].copy()  # `both` is a view of the reusable staging buffer
     if core.fdrs is not None:
-        data.obs[f"{key_added}_fdr"] = both[1]
+        data.obs[f"{key_added}_fdr"] = both[1].copy()
     if not return_full:
         mark("obs written")
         report()

@@ -126,11 +126,12 @@ def _r2_p20(s, old, S):
     return np.percentile(r2, 20)
 
 
-def _nam_device(data, sid_name, nsteps=None, maxnsteps=15, self_weight=1, show_progress=False):
-    """``_nam.py:44-76`` on the device.  The first step never materialises the one-hot matrix."""
+def _nam_device(data, sid_name, nsteps=None, maxnsteps=15, self_weight=1, show_progress=False, codes=None):
+    """``_nam.py:44-76`` on the device.  The first step never materialises the one-hot matrix.
+    ``codes`` = an already computed ``sample_codes(data, sid_name)``."""
     out = select_output(show_progress)
     g = graph_of(data)
-    labels, codes, counts = sample_codes(data, sid_name)
+    labels, codes, counts = codes if codes is not None else sample_codes(data, sid_name)
     S = len(labels)
     ld = _round_up(S, 8)
     dev = codes.device
@@ -276,10 +277,10 @@ def planes_of(x, n):
     return _lib.split_f16(x, n)
 
 
-def gram_svd(x, n, comm=None, planes=None):
-    """``_nam.py:105``: U, svs, _ = svd(NAM.NAM^T) with the Gram matrix contracted on the GPU
-    (tcgen05 kernel on the fp16 hi/lo planes when n <= 256, CUDA cores otherwise; summed over
-    shards when the cell axis is sharded)."""
+def gram_device(x, n, comm=None, planes=None):
+    """NAM.NAM^T of ``_nam.py:105`` as an [n x n] float64 device tensor (tcgen05 kernel on the fp16
+    hi/lo planes when n <= 256, CUDA cores otherwise; summed over shards when the cell axis is
+    sharded).  Asynchronous: nothing is copied to the host."""
     dev = x.device if x is not None else planes.t.device
     G = torch.zeros((n, n), dtype=torch.float64, device=dev)
     if n <= TC_GRAM_MAX_N:
@@ -288,12 +289,22 @@ def gram_svd(x, n, comm=None, planes=None):
         _lib.gram(x, n, G)
     if comm is not None:
         comm.all_reduce(G)
-    Gh = G.cpu().numpy()
-    mark("gram on host")
-    Gh = (Gh + Gh.T) / 2  # the kernel fills both triangles from the same products; keep it exact
+    return G
+
+
+def svd_of_gram(Gh):
+    """``_nam.py:105``: U, svs, _ = np.linalg.svd(Gram) on the host (n x n)."""
+    Gh = (Gh + Gh.T) / 2  # both triangles hold the same products up to summation order; keep it exact
     U, svs, _ = np.linalg.svd(Gh)
     mark("svd done")
     return U, svs, Gh
+
+
+def gram_svd(x, n, comm=None, planes=None):
+    G = gram_device(x, n, comm=comm, planes=planes)
+    Gh = G.cpu().numpy()
+    mark("gram on host")
+    return svd_of_gram(Gh)
 
 
 def nbhd_loadings(x, n, U, svs, rows=None, planes=None):

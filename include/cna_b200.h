@@ -156,8 +156,11 @@ int cna_right_multiply(const float *x, int64_t ld_x, int64_t n_rows, int n, cons
 
 /* For every permutation k (one warp each): z = y[perm[k,:]], zc = (I - C.W) z, zc /= std_ddof1(zc),
  * ssered[k] = |zc|^2, beta = Ut[:kmax] zc, ssefull[k, a] = |zc - U[:, :ks[a]] beta[:ks[a]]|^2.
- * The first n_local conditioned phenotypes are also written as fp32 columns of ycond
- * [ld_x rows x ld_y] for the neighbourhood-level null (_association.py:94-97).
+ * The first n_local conditioned phenotypes are also written for the neighbourhood-level null
+ * (_association.py:94-97): as fp32 columns of ycond [ld_x rows x ld_y] (may be NULL) and/or as
+ * TRANSPOSED fp16 hi/lo planes yt [n_local x ld16] (may be NULL; padding columns are the caller's
+ * zeros) for cna_null_hist_tc.  kmax = 0 skips the PC regressions (Ut, ks, ssefull may be NULL):
+ * the conditioned phenotypes do not depend on U, so the null GEMM can start before the SVD is done.
  * replaces: _stats.py:18 `Y[bix]`, _association.py:35-61 (`_reg`, `_stats`, `_minp_stats` up to the
  * F statistic) evaluated in a Python loop at _association.py:84.
  *   perm  [K x n] int32 (row k = sample indices of permutation k)
@@ -165,7 +168,7 @@ int cna_right_multiply(const float *x, int64_t ld_x, int64_t n_rows, int n, cons
 int cna_perm_stats(const double *y, const int32_t *perm, int64_t K, int n, const double *C,
                    const double *W, int r, const double *Ut, int kmax, const int32_t *ks, int nks,
                    double *ssered, double *ssefull, float *ycond, int64_t ld_y, int n_local,
-                   void *stream);
+                   void *yt_hi, void *yt_lo, int64_t ld16, void *stream);
 
 /* ------------------------------------------------------------------------------------------
  * neighbourhood-level null: GEMM with a threshold-histogram epilogue
