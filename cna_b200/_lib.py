@@ -81,6 +81,8 @@ _SIGNATURES = {
     "cna_absmax": [_VP, _VP, _I64, _VP, _VP],
     "cna_cell_fdr": [_VP, _VP, _I64, _VP, _VP, _INT, _VP, _VP, _VP],
     "cna_knn_bruteforce": [_VP, _I64, _INT, _INT, _VP, _VP, _VP],
+    "cna_bfs_expand": [_VP, _VP, _VP, _INT, _INT, _INT, _VP, _VP, _VP, _VP, _VP],
+    "cna_permute_csr": [_VP, _VP, _VP, _INT, _VP, _VP, _VP, _I64, _VP, _VP, _VP],
     "cna_host_randn": [_VP, _VP, _VP, _VP, _I64, _VP, _INT],
     "cna_host_perm_blocks": [_VP, _VP, _VP, _VP, _INT, _VP, _VP, _I64, _VP, _I64, _INT],
     "cna_split_f16": [_VP, _I64, _I64, _INT, _INT, _VP, _VP, _I64, _I64, _VP],
@@ -304,6 +306,20 @@ def cell_fdr(ncorr, row_valid, thresholds, prefix_min_fdr, coef, fdr):
                                _ptr(coef, torch.float64, "coef"), _ptr(fdr, torch.float64, "fdr"), _stream())
 
 
+def bfs_expand(indptr, indices, frontier, pos_base, next_level, level, first_parent, nxt, next_count):
+    _call("cna_bfs_expand", _ptr(indptr, torch.int32, "indptr"), _ptr(indices, torch.int32, "indices"),
+          _ptr(frontier, torch.int32, "frontier"), frontier.numel(), int(pos_base), int(next_level),
+          _ptr(level, torch.int32, "level"), _ptr(first_parent, torch.int32, "first_parent"),
+          _ptr(nxt, torch.int32, "next"), _ptr(next_count, torch.int32, "next_count"), _stream())
+
+
+def permute_csr(indptr, indices, data, order, inv, new_indptr, new_indices, new_data):
+    _call("cna_permute_csr", _ptr(indptr, torch.int32, "indptr"), _ptr(indices, torch.int32, "indices"),
+          _ptr(data, data.dtype, "data"), int(data.dtype == torch.float64), _ptr(order, torch.int64, "order"),
+          _ptr(inv, torch.int32, "inv"), _ptr(new_indptr, torch.int32, "new_indptr"), order.numel(),
+          _ptr(new_indices, torch.int32, "new_indices"), _ptr(new_data, data.dtype, "new_data"), _stream())
+
+
 def round_up(x, m):
     return (x + m - 1) // m * m
 
@@ -363,10 +379,11 @@ def right_multiply_tc(xp, n, btp, n_out, out):
 
 
 def null_hist_tc(xp, n, ytp, n_null, edges, edge0, hist):
+    """hist: int64 [n_edges], the threshold histogram summed over the n_null columns."""
     _call("cna_null_hist_tc", _ptr(xp.hi, torch.float16, "xh"), _ptr(xp.lo, torch.float16, "xl"), xp.ld,
           xp.rows, int(n), _ptr(ytp.hi, torch.float16, "yth"), _ptr(ytp.lo, torch.float16, "ytl"), ytp.ld,
           int(n_null), _ptr(edges, torch.float64, "edges"), edges.numel(), float(edge0),
-          _ptr(hist, torch.int32, "hist"), _stream())
+          _ptr(hist, torch.int64, "hist"), _stream())
 
 
 # ---------------------------------------------------------------------------------------------

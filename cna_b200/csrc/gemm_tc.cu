@@ -188,7 +188,7 @@ constexpr int kStepBytesA = kBM * 32;    // one k-step (16 fp16) of one plane of
 constexpr int kStepBytesB = kBN * 32;
 constexpr int kStageBytes = 2 * kStepBytesA + 2 * kStepBytesB;  // hi+lo of A and B: 24 KiB
 constexpr int kStages = 7;
-constexpr int kXbEpiWarps = 8;           // two warps per TMEM lane quarter, each owning half the columns
+constexpr int kXbEpiWarps = 16;          // four warps per TMEM lane quarter, each owning a quarter of the columns
 constexpr int kXbThreads = 64 + kXbEpiWarps * 32;
 constexpr int kQueue = 512;              // candidates of one 16-column batch of one warp (32 lanes x 16)
 constexpr uint32_t kSw32 = 6, kSw128 = 2;
@@ -205,7 +205,7 @@ struct XbTcArgs {
     // HIST
     const double *edges;
     int n_edges;
-    uint32_t *hist;
+    unsigned long long *hist;  // [n_edges], summed over all output columns
     double inv_n;
     float reject_below;
 };
@@ -223,8 +223,8 @@ xb_tc_kernel(const __grid_constant__ CUtensorMap tm_ah, const __grid_constant__ 
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
     float *guess = reinterpret_cast<float *>(tmem_slot + 2);              // [2]: sqrt(e_0), bins per unit sqrt
     float *queue_v = guess + 2;                                            // [warps][kQueue]
-    uint16_t *queue_c = reinterpret_cast<uint16_t *>(queue_v + kXbEpiWarps * kQueue);
-    double *edges_s = reinterpret_cast<double *>(queue_c + kXbEpiWarps * kQueue);
+    uint32_t *hist_s = reinterpret_cast<uint32_t *>(queue_v + kXbEpiWarps * kQueue);  // [n_edges] CTA-private
+    double *edges_s = reinterpret_cast<double *>(hist_s + ((a.n_edges + 1) & ~1));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_row_tiles = int((a.n_rows + kBM - 1) / kBM);
@@ -247,7 +247,10 @@ xb_tc_kernel(const __grid_constant__ CUtensorMap tm_ah, const __grid_constant__ 
     }
     if (warp == 1) tmem_alloc(tmem_slot, 512);
     if (E == Epi::HIST) {
-        for (int t = threadIdx.x; t < a.n_edges; t += blockDim.x) edges_s[t] = a.edges[t];
+        for (int t = threadIdx.x; t < a.n_edges; t += blockDim.x) {
+            edges_s[t] = a.edges[t];
+            hist_s[t] = 0;
+        }
         if (threadIdx.x == 32) {
             // the thresholds are (close to) an arithmetic progression, so sqrt(edge) is close to
             // linear in the bin index: a one-multiply first guess, corrected against the table
@@ -316,10 +319,10 @@ xb_tc_kernel(const __grid_constant__ CUtensorMap tm_ah, const __grid_constant__ 
                     }
                 }
         }
-    } else {  // ---- epilogue: warps 2..9; TMEM lane quarter = warp % 4, column half = (warp - 2) / 4 ----
-        const int q = warp & 3, half = (warp - 2) >> 2, ew = warp - 2;
+    } else {  // ---- epilogue: warps 2..17; TMEM lane quarter = warp % 4, column quarter = (warp - 2) / 4 ----
+        constexpr int kColsPerWarp = kBN / (kXbEpiWarps / 4);
+        const int q = warp & 3, part = (warp - 2) >> 2, ew = warp - 2;
         float *qv = queue_v + ew * kQueue;
-        uint16_t *qc = queue_c + ew * kQueue;
         const float g0 = (E == Epi::HIST) ? guess[0] : 0.f, g1 = (E == Epi::HIST) ? guess[1] : 0.f;
         int acc = 0;
         uint32_t acc_phase = 0;
@@ -330,7 +333,7 @@ xb_tc_kernel(const __grid_constant__ CUtensorMap tm_ah, const __grid_constant__ 
                 mbar_wait(tfull + acc, acc_phase);
                 tc_fence_after();
                 const uint32_t t0 = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * kBN);
-                for (int c0 = half * (kBN / 2); c0 < (half + 1) * (kBN / 2); c0 += 16) {
+                for (int c0 = part * kColsPerWarp; c0 < (part + 1) * kColsPerWarp; c0 += 16) {
                     const int col0 = nc * kBN + c0;
                     if (col0 >= a.n_out) break;  // uniform over the warp
                     uint32_t r[16];
@@ -364,13 +367,10 @@ xb_tc_kernel(const __grid_constant__ CUtensorMap tm_ah, const __grid_constant__ 
                         off -= cnt;
 #pragma unroll
                         for (int j = 0; j < 16; ++j)
-                            if (mask & (1u << j)) {
-                                qv[off] = __uint_as_float(r[j]);
-                                qc[off] = uint16_t(c0 + j);
-                                ++off;
-                            }
+                            if (mask & (1u << j)) qv[off++] = __uint_as_float(r[j]);
                         __syncwarp();
-                        // pass 2: all lanes busy on survivors: bin lookup + one atomic each
+                        // pass 2: all lanes busy on survivors: bin lookup + one shared-memory atomic each
+                        // (the FDR only needs the histogram summed over the null columns, _stats.py:79-80)
                         for (int i = lane; i < total; i += 32) {
                             double z = double(qv[i]) * a.inv_n;
                             double z2 = z * z;
@@ -379,7 +379,7 @@ xb_tc_kernel(const __grid_constant__ CUtensorMap tm_ah, const __grid_constant__ 
                             b = max(0, min(b, a.n_edges - 1));
                             while (b + 1 < a.n_edges && edges_s[b + 1] <= z2) ++b;  // largest b with edges[b] <= z2
                             while (b > 0 && edges_s[b] > z2) --b;
-                            atomicAdd(a.hist + int64_t(nc * kBN + qc[i]) * a.n_edges + b, 1u);
+                            atomicAdd(hist_s + b, 1u);
                         }
                         __syncwarp();
                     }
@@ -397,6 +397,9 @@ xb_tc_kernel(const __grid_constant__ CUtensorMap tm_ah, const __grid_constant__ 
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, 512);
+    if (E == Epi::HIST)  // a CTA sees < 2^32 products per bin between flushes (rows/148 x columns)
+        for (int t = threadIdx.x; t < a.n_edges; t += blockDim.x)
+            if (hist_s[t]) atomicAdd(a.hist + t, static_cast<unsigned long long>(hist_s[t]));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -633,8 +636,8 @@ static int xb_tc_launch(Epi epi, const void *xh, const void *xl, int64_t ld16, i
     a.n_rows = n_rows;
     a.n_ksteps = (n + 15) / 16;
     a.n_out = n_out;
-    size_t smem = size_t(kStages) * kStageBytes + 1024 + 256 + size_t(kXbEpiWarps) * kQueue * 6 +
-                  (epi == Epi::HIST ? sizeof(double) * a.n_edges : 0);
+    size_t smem = size_t(kStages) * kStageBytes + 1024 + 256 + size_t(kXbEpiWarps) * kQueue * 4 +
+                  (epi == Epi::HIST ? (sizeof(double) + sizeof(uint32_t)) * (a.n_edges + 2) : 0);
     int64_t tiles = (n_rows + kBM - 1) / kBM;
     unsigned grid = unsigned(tiles < num_sms() ? tiles : num_sms());
     if (epi == Epi::HIST) {
@@ -684,14 +687,15 @@ int cna_right_multiply_tc(const void *xh, const void *xl, int64_t ld16, int64_t 
 
 int cna_null_hist_tc(const void *xh, const void *xl, int64_t ld16, int64_t n_rows, int n, const void *yth,
                      const void *ytl, int64_t ld16_y, int n_null, const double *edges, int n_edges, double edge0,
-                     uint32_t *hist, void *stream) {
-    CNA_REQUIRE(n_edges > 0 && n_edges <= 2048, "cna_null_hist_tc: 1..2048 edges supported (got %d)", n_edges);
+                     uint64_t *hist, void *stream) {
+    CNA_REQUIRE(n_edges > 0 && n_edges <= 1024, "cna_null_hist_tc: 1..1024 edges supported (got %d)", n_edges);
+    CNA_REQUIRE(n_rows * int64_t(n_null) / 64 < (int64_t(1) << 32), "cna_null_hist_tc: too many products per CTA");
     CNA_REQUIRE(edges && hist, "cna_null_hist_tc: null pointer");
     if (n_rows == 0 || n_null == 0) return CNA_OK;
     XbTcArgs a{};
     a.edges = edges;
     a.n_edges = n_edges;
-    a.hist = hist;
+    a.hist = reinterpret_cast<unsigned long long *>(hist);
     a.inv_n = 1.0 / double(n);
     double rb = edge0 * double(n) * double(n) * (1.0 - 1e-5);
     a.reject_below = rb > 0.0 ? float(rb) * (1.0f - 1e-6f) : 0.f;

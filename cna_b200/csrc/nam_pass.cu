@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(256) resid_kernel(cna_resid_args a) {
             }
         }
 #pragma unroll
-        for (int i = 0; i < R; ++i) s2[i] = sqrt(warp_sum(s2[i]) / (dn - 1.0));
+        for (int i = 0; i < R; ++i) s2[i] = 1.0 / sqrt(warp_sum(s2[i]) / (dn - 1.0));  // 1 / std
 #pragma unroll
         for (int i = 0; i < R; ++i) {
             const int64_t row = row0 + i;
@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(256) resid_kernel(cna_resid_args a) {
 #pragma unroll
             for (int q = 0; q < NQ; ++q) {
                 int m = lane + 32 * q;
-                double v = (m < n && valid[i]) ? x[i][q] / s2[i] : 0.0;  // rows of dropped cells are zero
+                double v = (m < n && valid[i]) ? x[i][q] * s2[i] : 0.0;  // rows of dropped cells are zero
                 if (m < n) dot[i] += v * ys[m];
                 if (o && m < a.ld_x) o[m] = float(v);
                 if (ph && m < a.ld16) {  // v = hi + lo to 2^-22

@@ -131,6 +131,9 @@ class _PermutationJob:
         self._thread = threading.Thread(target=work, name="cna-permutations", daemon=True)
         self._thread.start()
 
+    def done(self):
+        return not self._thread.is_alive()
+
     def cancel(self):
         """Wait for the draws without using them (an error is propagating on the caller's thread)."""
         self._thread.join()
@@ -171,6 +174,12 @@ def _association(res, perms, Nnull=1000, local_test=True, show_progress=False):
             comm.all_reduce(mx, op="max")
     Gh = G_d.cpu().numpy()
     mark("gram on host")
+    # The n x n SVD needs only the Gram; the null kernels need only the permutations.  Whichever
+    # input is ready first goes first: if the draws are still running the SVD fills the wait,
+    # otherwise the null kernels are launched first and the SVD overlaps them.
+    svd = None
+    if perms is not None and not perms.done():
+        svd = _nam.svd_of_gram(Gh)  # _nam.py:105
 
     # ---- permutations: indices from the host RNG (bit-exact), everything else on the device ----
     if perms is not None:
@@ -193,7 +202,7 @@ def _association(res, perms, Nnull=1000, local_test=True, show_progress=False):
         edges = _stats.threshold_edges(thresholds)
         T = len(thresholds)
         edges_d, thr_d = _to_dev(edges), _to_dev(thresholds)
-        hist = torch.zeros((Kl, T), dtype=torch.int32, device=dev)
+        hist = torch.zeros(T, dtype=torch.int64, device=dev)  # summed over the Kl nulls
         obs = torch.zeros((2, T), dtype=torch.int32, device=dev)
         # ycond_ = M.y_[:, :Kl] / std (ddof=1) (:94-97) as transposed fp16 hi/lo planes, then
         # (cells x n) . (n x Kl) on the tensor cores with the histogram epilogue straight out of TMEM
@@ -206,7 +215,7 @@ def _association(res, perms, Nnull=1000, local_test=True, show_progress=False):
             comm.all_reduce(obs)
     mark("null kernels launched")
 
-    U, svs, res.G = _nam.svd_of_gram(Gh)  # _nam.py:105
+    U, svs, res.G = svd if svd is not None else _nam.svd_of_gram(Gh)  # _nam.py:105
     res.U, res.svs = U, svs
 
     # ---- observed phenotype (:64-74): n-sized host arithmetic in float64 -----------------
@@ -240,7 +249,7 @@ def _association(res, perms, Nnull=1000, local_test=True, show_progress=False):
     mark("global p done")
     if local_test:
         obs_h = obs.cpu().numpy()
-        fdr_vals = _stats.fdr_from_counts(hist.cpu().numpy(), obs_h[0])  # _stats.py:64-83
+        fdr_vals = _stats.fdr_from_counts(hist.cpu().numpy(), obs_h[0], n_null=Kl)  # _stats.py:64-83
         num_detected = _stats.tails_from_hist(obs_h[1].astype(np.int64))  # :105-108
         fdrs = pd.DataFrame({"threshold": thresholds, "fdr": fdr_vals, "num_detected": num_detected})
         if not np.min(fdrs.fdr) > 0.05:  # :111-114
@@ -341,12 +350,14 @@ def association(data, y, sid_name, batches=None, covs=None, donorids=None, ks=No
         thr = core.fdrs.threshold.to_numpy()
         pmin = np.fmin.accumulate(core.fdrs.fdr.to_numpy())  # Series.min() skips NaN
     _lib.cell_fdr(res.ncorr, res.valid, _to_dev(thr), _to_dev(pmin), coef_d, fdr_d)
-    both = torch.stack([coef_d, fdr_d])
+    both = torch.stack([coef_d, fdr_d], dim=1)  # [cells x 2]
     if comm is not None:  # every rank ends with the full per-cell columns
-        pad = torch.zeros((2, stn.rows_per), dtype=torch.float64, device=dev)
-        pad[:, :N] = both
-        both = comm.all_gather_rows(pad.t().contiguous())[: len(data.obs)].t()
-    both = _to_host_pinned(both)
+        pad = torch.zeros((stn.rows_per, 2), dtype=torch.float64, device=dev)
+        pad[:N] = both
+        both = comm.all_gather_rows(pad)[: len(data.obs)]
+    if stn.graph is not None:
+        both = stn.graph.unpermute(both)  # back to the caller's cell order
+    both = _to_host_pinned(both.t())
     mark("results on host")
     data.obs[key_added] = both[0].copy()  # `both` is a view of the reusable staging buffer
     if core.fdrs is not None:
@@ -357,17 +368,18 @@ def association(data, y, sid_name, batches=None, covs=None, donorids=None, ks=No
         return core.p
 
     # ---- full result surface (_nam.py:168-175, _association.py:223-225) ----
-    kept = res.valid.bool().cpu().numpy()
+    vmask = _nam.to_caller_order(stn, res.valid).bool()
+    kept = vmask.cpu().numpy()
     cells = data.obs.index[kept]
     pcs = ["PC" + str(i) for i in range(1, n + 1)]
     full = Namespace()
     full.M = pd.DataFrame(res.M, index=sids, columns=sids)
     full.r = res.r
-    vmask = res.valid.bool()
-    xk = res.x[vmask][:, :n]
+    xk = _nam.to_caller_order(stn, res.x)[vmask][:, :n]
     full.namresid = pd.DataFrame(xk.t().double().cpu().numpy(), index=sids, columns=cells)
     full.namresid_sampleXpc = pd.DataFrame(res.U, index=sids, columns=pcs)
-    V = _nam.nbhd_loadings(res.x, n, res.U, svs, rows=vmask, planes=res.planes)
+    V = _nam.nbhd_loadings(res.x, n, res.U, svs, planes=res.planes,
+                           rows=lambda v: _nam.to_caller_order(stn, v)[vmask])
     full.namresid_nbhdXpc = pd.DataFrame(V, index=cells, columns=pcs)
     full.namresid_svs = pd.Series(svs, index=pcs)[:npcs]
     full.namresid_varexp = pd.Series(svs / n / len(cells), index=pcs)
@@ -375,7 +387,7 @@ def association(data, y, sid_name, batches=None, covs=None, donorids=None, ks=No
     full.ncorrs = pd.Series(both[0][kept], index=cells)
     full.yresid = pd.Series(core.yresid, index=sids)
     cm = torch.as_tensor(colmap, device=dev, dtype=torch.long)
-    nam_sel = (stn.s[vmask][:, cm].double() * stn.inv_count[cm])
+    nam_sel = (_nam.to_caller_order(stn, stn.s)[vmask][:, cm].double() * stn.inv_count[cm])
     full.nam = pd.DataFrame(nam_sel.t().cpu().numpy(), index=sids, columns=cells)
     full.kept = kept
     return full

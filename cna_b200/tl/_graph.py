@@ -3,6 +3,7 @@
 Reference: ``src/cna/tools/_nam.py:12-19`` (get_connectivity), ``:28`` (column sums + self weight),
 ``:51-54`` (one-hot sample indicator and cells-per-sample counts).
 """
+import os
 import warnings
 
 import numpy as np
@@ -41,37 +42,139 @@ def _to_dev(arr, dtype=None):
     return t.to(device(), non_blocking=True)
 
 
+REORDER_MIN_CELLS = 150_000  # below this the whole diffusion state lives in L2 anyway
+
+
+def want_reorder(n_cells):
+    """Reorder by default only when the state cannot stay in L2; ``CNA_B200_REORDER=0/1`` forces."""
+    env = os.environ.get("CNA_B200_REORDER")
+    if env is not None:
+        return env.strip().lower() not in ("0", "", "false", "no")
+    return n_cells >= REORDER_MIN_CELLS
+
+
+def _bfs_far_node(indptr, indices, n, root, max_levels):
+    """Last node discovered by an (unsorted) breadth-first sweep from ``root``: one end of a long
+    shortest path, the usual pseudo-peripheral starting point for Cuthill-McKee."""
+    dev = indptr.device
+    level = torch.full((n,), -1, dtype=torch.int32, device=dev)
+    first_parent = torch.full((n,), 2 ** 31 - 1, dtype=torch.int32, device=dev)
+    bufs = [torch.empty(n, dtype=torch.int32, device=dev) for _ in range(2)]
+    count = torch.zeros(1, dtype=torch.int32, device=dev)
+    level[root] = 0
+    frontier = torch.tensor([root], dtype=torch.int32, device=dev)
+    for lvl in range(max_levels):
+        count.zero_()
+        nxt = bufs[lvl & 1]
+        _lib.bfs_expand(indptr, indices, frontier, 0, lvl + 1, level, first_parent, nxt, count)
+        c = int(count.item())
+        if c == 0:
+            break
+        frontier = nxt[:c]
+    return int(frontier.min().item())  # min: independent of the order of discovery
+
+
+def cuthill_mckee_order(indptr, indices, n, max_levels=4096, max_roots=8):
+    """Cuthill-McKee ordering of a symmetric CSR on the device (csrc/reorder.cu): breadth-first levels
+    from a pseudo-peripheral root, each level sorted by (position of its first parent, node id).
+    Returns (order int64 [n] new -> old, inv int32 [n] old -> new), or None when the graph is too
+    path-like to be worth it (more than ``max_levels`` levels).  Components beyond ``max_roots`` are
+    appended in their original order.  Deterministic: sets and sort keys do not depend on timing."""
+    dev = indptr.device
+    level = torch.full((n,), -1, dtype=torch.int32, device=dev)
+    first_parent = torch.full((n,), 2 ** 31 - 1, dtype=torch.int32, device=dev)
+    order = torch.empty(n, dtype=torch.int64, device=dev)
+    nxt = torch.empty(n, dtype=torch.int32, device=dev)
+    count = torch.zeros(1, dtype=torch.int32, device=dev)
+    deg = (indptr[1:] - indptr[:-1]).long()
+    placed, lvl = 0, 0
+    for attempt in range(max_roots):
+        if placed >= n:
+            break
+        big = torch.iinfo(torch.int64).max
+        root = int(torch.where(level < 0, deg, torch.full_like(deg, big)).argmin().item())
+        if attempt == 0:  # the giant component: start from the far end of a long shortest path
+            root = _bfs_far_node(indptr, indices, n, root, max_levels)
+        level[root] = lvl
+        frontier = torch.tensor([root], dtype=torch.int32, device=dev)
+        order[placed] = root
+        pos_base, placed = placed, placed + 1
+        while True:
+            count.zero_()
+            _lib.bfs_expand(indptr, indices, frontier, pos_base, lvl + 1, level, first_parent, nxt, count)
+            c = int(count.item())
+            if c == 0:
+                break
+            cand = nxt[:c].long()
+            nodes = torch.sort((first_parent[cand].long() << 32) | cand).values & 0xFFFFFFFF
+            order[placed:placed + c] = nodes
+            frontier = nodes.to(torch.int32)
+            pos_base, placed, lvl = placed, placed + c, lvl + 1
+            if lvl > max_levels:
+                return None
+        lvl += 1
+    if placed < n:
+        order[placed:] = torch.nonzero(level < 0).reshape(-1)
+    inv = torch.empty(n, dtype=torch.int32, device=dev)
+    inv[order] = torch.arange(n, dtype=torch.int32, device=dev)
+    return order, inv
+
+
 class DeviceGraph:
     """CSR adjacency resident in HBM: int32 indptr / indices plus the raw edge data.  The
     normalised edge values ``A_ij / (colsum_j + w)`` and the diagonal ``w / (colsum_i + w)`` are
-    derived per (self_weight, dtype) and cached."""
+    derived per (self_weight, dtype) and cached.
 
-    def __init__(self, A, shard=None):
-        """``shard`` = (comm, row0, row1, rows_per) keeps only rows [row0, row1) on this device
-        (cell-axis sharding, ``cna_b200.sharded``); column indices stay global."""
+    Large graphs are stored in a Cuthill-McKee cell order (``order``: new -> old, ``inv``: old ->
+    new; both None when the original order is kept).  Everything row-indexed on the device is in the
+    new order; the host boundary (``unpermute``) restores the caller's order."""
+
+    def __init__(self, A, shard=None, reorder=None):
+        """``shard`` = (comm, row0, row1, rows_per) keeps only rows [row0, row1) (of the stored
+        order) on this device (cell-axis sharding, ``cna_b200.sharded``); column indices stay
+        global."""
         if not sp.issparse(A):
             raise TypeError("connectivities must be a scipy sparse matrix")
         A = A.tocsr()
         if A.shape[0] != A.shape[1]:
             raise ValueError("connectivities must be square")
         self.n_total = A.shape[0]
+        if len(A.indices) >= 2 ** 31:
+            raise ValueError("graphs with >= 2^31 stored edges are not supported")
+        indptr = _to_dev(A.indptr, torch.int32)
+        indices = _to_dev(A.indices, torch.int32)
+        data = A.data if A.data.dtype in (np.float32, np.float64) else A.data.astype(np.float64)
+        data = _to_dev(data)
+        self.order = self.inv = None
+        if (want_reorder(self.n_total) if reorder is None else reorder) and self.n_total > 1:
+            res = cuthill_mckee_order(indptr, indices, self.n_total)
+            if res is not None:
+                self.order, self.inv = res
+                deg = (indptr[1:] - indptr[:-1])[self.order]
+                new_indptr = torch.zeros(self.n_total + 1, dtype=torch.int32, device=indptr.device)
+                new_indptr[1:] = torch.cumsum(deg, 0)
+                new_indices, new_data = torch.empty_like(indices), torch.empty_like(data)
+                _lib.permute_csr(indptr, indices, data, self.order, self.inv, new_indptr, new_indices, new_data)
+                indptr, indices, data = new_indptr, new_indices, new_data
         if shard is None:
-            self.comm, self.row0, self.rows_per = None, 0, A.shape[0]
-            indptr, indices, data = A.indptr, A.indices, A.data
+            self.comm, self.row0, self.rows_per = None, 0, self.n_total
         else:
-            from ..sharded import slice_csr
             self.comm, self.row0, row1, self.rows_per = shard
-            indptr, indices, data = slice_csr(A, self.row0, row1)
-        if len(indices) >= 2 ** 31:
-            raise ValueError("graphs with >= 2^31 stored edges per GPU must be sharded further")
-        self.n = len(indptr) - 1  # rows held by this device
-        self.nnz = int(len(indices))
-        self.indptr = _to_dev(indptr, torch.int32)
-        self.indices = _to_dev(indices, torch.int32)
-        if data.dtype not in (np.float32, np.float64):
-            data = data.astype(np.float64)
-        self.data = _to_dev(data)
+            e0, e1 = int(indptr[self.row0].item()), int(indptr[row1].item())
+            indptr = (indptr[self.row0:row1 + 1] - e0).contiguous()
+            indices, data = indices[e0:e1].clone(), data[e0:e1].clone()
+        self.n = indptr.numel() - 1  # rows held by this device
+        self.nnz = int(indices.numel())
+        self.indptr, self.indices, self.data = indptr, indices, data
         self._scaled = {}
+
+    def permute(self, t):
+        """Rows of ``t`` (one per cell, caller's order) -> stored order."""
+        return t if self.order is None else t.index_select(0, self.order)
+
+    def unpermute(self, t):
+        """Rows of ``t`` (one per cell, stored order, all cells) -> the caller's order."""
+        return t if self.inv is None else t.index_select(0, self.inv.long())
 
     def scaled(self, self_weight=1, dtype=torch.float32):
         key = (float(self_weight), dtype)

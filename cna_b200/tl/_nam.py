@@ -71,7 +71,7 @@ def diffuse_stepwise(data, s, maxnsteps=15, show_progress=False, self_weight=1):
         dtype = torch.float64
     if cur.dim() != 2 or cur.shape[0] != g.n:
         raise ValueError("s must be a 2-D array with one row per cell")  # colsums[:,None] needs 2-D
-    cur = cur.contiguous()
+    cur = g.permute(cur.contiguous())
     vals, diag = g.scaled(self_weight, dtype)
     for i in range(maxnsteps):
         print("\ttaking step", i + 1, file=out)
@@ -79,9 +79,9 @@ def diffuse_stepwise(data, s, maxnsteps=15, show_progress=False, self_weight=1):
         _lib.diffuse_step(g.indptr, g.indices, vals, diag, cur, nxt, cur.shape[1])
         cur = nxt
         if on_device:
-            yield cur
+            yield g.unpermute(cur)
         else:
-            res = cur.cpu().numpy()
+            res = g.unpermute(cur).cpu().numpy()
             yield pd.DataFrame(res, index=frame.index, columns=frame.columns) if frame is not None else res
 
 
@@ -112,6 +112,7 @@ class NamState:
         self.comm = None  # set for cell-axis shards (cna_b200.sharded)
         self.row0 = 0
         self.rows_per = s.shape[0]
+        self.graph = None  # DeviceGraph whose (possibly reordered) row order the state follows
 
     @property
     def N(self):
@@ -143,8 +144,9 @@ def _nam_device(data, sid_name, nsteps=None, maxnsteps=15, self_weight=1, show_p
     # touches only its first g.n
     cur = torch.zeros((g.rows_per, ld), dtype=torch.float32, device=dev)
     nxt = torch.zeros((g.rows_per, ld), dtype=torch.float32, device=dev)
-    st = NamState(cur[: g.n], S, labels, counts, data.obs.index[g.row0: g.row0 + g.n])
-    st.comm, st.row0, st.rows_per = comm, g.row0, g.rows_per
+    codes = g.permute(codes)  # device rows follow the graph's stored cell order
+    st = NamState(cur[: g.n], S, labels, counts, data.obs.index)
+    st.comm, st.row0, st.rows_per, st.graph = comm, g.row0, g.rows_per, g
     need_stats = nsteps is None or show_progress
     kurt = torch.empty(g.n, dtype=torch.float64, device=dev) if need_stats else None
     old = None
@@ -228,18 +230,25 @@ def nam(data, sid_name, batches=None, nsteps=None, self_weight=1, max_frac_pcs=0
     return nam_frame(st, sid_name), keep_mask(st)
 
 
+def to_caller_order(st, t):
+    """Per-cell device tensor in the state's row order -> the caller's cell order (all cells)."""
+    if st.comm is not None:
+        raise NotImplementedError("per-cell matrices of a cell-axis shard are not gathered")
+    return t if st.graph is None else st.graph.unpermute(t)
+
+
 def keep_mask(st):
     if st.keep is None:
         return np.repeat(True, st.N)
-    return st.keep.bool().cpu().numpy()
+    return to_caller_order(st, st.keep).bool().cpu().numpy()
 
 
 def nam_frame(st, sid_name, rows=None, cols=None):
     """Materialise (a part of) the QC'd NAM as the reference's samples x cells DataFrame."""
-    x = st.s[:, :st.S].double() * st.inv_count  # _nam.py:73
+    x = to_caller_order(st, st.s)[:, :st.S].double() * st.inv_count  # _nam.py:73
     keep = keep_mask(st)
     if st.keep is not None:
-        x = x[st.keep.bool()]
+        x = x[torch.as_tensor(keep, device=x.device)]
     arr = x.t().contiguous().cpu().numpy()
     df = pd.DataFrame(arr, index=st.labels, columns=st.cell_index[keep], dtype=float)
     df.index.name = sid_name  # _nam.py:74
@@ -321,10 +330,10 @@ def nbhd_loadings(x, n, U, svs, rows=None, planes=None):
     _lib.right_multiply_tc(xp, n, utp, n, out)
     with np.errstate(divide="ignore", invalid="ignore"):
         scale = _to_dev(1.0 / np.sqrt(svs))
-    V = out[:, :n].double() * scale
-    if rows is not None:
-        V = V[rows]
-    return V.cpu().numpy()
+    V = out[:, :n]
+    if rows is not None:  # a row selector: boolean mask / index tensor, or a callable
+        V = rows(V) if callable(rows) else V[rows]
+    return (V.double() * scale).cpu().numpy()
 
 
 # ---------------------------------------------------------------------------------------------

@@ -89,9 +89,15 @@ def tails_from_hist(hist):
     return np.flip(np.cumsum(np.flip(hist, axis=-1), axis=-1), axis=-1)
 
 
-def fdr_from_counts(null_hist, rank_hist):
-    """``_stats.py:64-83`` from binned counts: fdr_i = mean_k(tails[k, i] / ranks[i])."""
+def fdr_from_counts(null_hist, rank_hist, n_null=None):
+    """``_stats.py:64-83`` from binned counts: fdr_i = mean_k(tails[k, i] / ranks[i]).
+
+    ``null_hist`` is either the per-null table [n_null x T] or, with ``n_null`` given, its sum over
+    the nulls [T]: the mean over k of tails[k, i] / ranks[i] is (sum_k tails[k, i]) / (n_null *
+    ranks[i]) (equal up to the rounding of n_null float64 divisions, ~1e-16 relative)."""
     tails = tails_from_hist(np.asarray(null_hist, dtype=np.int64))
     ranks = tails_from_hist(np.asarray(rank_hist, dtype=np.int64))
     with np.errstate(divide="ignore", invalid="ignore"):
+        if n_null is not None:
+            return tails / ranks / n_null
         return (tails / ranks).mean(axis=0)

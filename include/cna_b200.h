@@ -206,11 +206,15 @@ int cna_right_multiply_tc(const void *xh, const void *xl, int64_t ld16, int64_t 
                           const void *bth, const void *btl, int64_t ld16_b, int n_out, float *out,
                           int64_t ld_out, void *stream);
 
-/* Same contract as cna_null_hist with the conditioned phenotypes given TRANSPOSED as fp16 planes
- * yt [n_null x ld16_y].  replaces: _association.py:99 + _stats.py:52-54. */
+/* The histogram of cna_null_hist SUMMED over the null columns: hist[b] (uint64, [n_edges], zeroed
+ * by the caller) += #{(cell i, null k): edges[b] <= z_ik^2 < edges[b+1]}, with the conditioned
+ * phenotypes given TRANSPOSED as fp16 planes yt [n_null x ld16_y].  The reference's FDR is
+ * mean_k(tails[k, i] / ranks[i]) (_stats.py:79-80), which only depends on sum_k tails[k, i], so the
+ * per-null table never needs to exist; counts stay in shared memory until the kernel ends.
+ * replaces: _association.py:99 + _stats.py:52-59 + :79-80. */
 int cna_null_hist_tc(const void *xh, const void *xl, int64_t ld16, int64_t n_rows, int n,
                      const void *yth, const void *ytl, int64_t ld16_y, int n_null, const double *edges,
-                     int n_edges, double edge0, uint32_t *hist, void *stream);
+                     int n_edges, double edge0, uint64_t *hist, void *stream);
 
 /* Histograms of the observed coefficients against the same edges and the strict thresholds:
  * rank_hist[b] += #{i valid: edges[b] <= ncorr_i^2 < edges[b+1]} (last bin closed),
@@ -230,6 +234,25 @@ int cna_absmax(const double *v, const uint8_t *row_valid, int64_t n_rows, double
 int cna_cell_fdr(const double *ncorr, const uint8_t *row_valid, int64_t n_rows,
                  const double *thresholds, const double *prefix_min_fdr, int n_thr, double *coef,
                  double *fdr, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * locality-restoring cell order (no reference counterpart: a property of the HBM layout)
+ * ------------------------------------------------------------------------------------------ */
+
+/* One breadth-first level of a Cuthill-McKee ordering.  frontier[0..n_front) are the nodes of the
+ * current level in their final order (positions pos_base + i).  Every neighbour with level == -1 is
+ * claimed (level <- next_level, appended to next[], *next_count incremented) and first_parent[v] <-
+ * min(first_parent[v], position of the parent).  The caller sorts next[] by (first_parent, id). */
+int cna_bfs_expand(const int32_t *indptr, const int32_t *indices, const int32_t *frontier, int n_front,
+                   int pos_base, int next_level, int32_t *level, int32_t *first_parent, int32_t *next,
+                   int32_t *next_count, void *stream);
+
+/* Symmetric permutation of a CSR: row i of the result is row order[i] of the input with its column
+ * ids renamed through inv (inv[order[i]] = i); edges keep their order inside a row, so downstream
+ * sums are performed in the original order.  new_indptr = prefix sums of the permuted row lengths. */
+int cna_permute_csr(const int32_t *indptr, const int32_t *indices, const void *data, int is_f64,
+                    const int64_t *order, const int32_t *inv, const int32_t *new_indptr, int64_t n_rows,
+                    int32_t *new_indices, void *new_data, void *stream);
 
 /* ------------------------------------------------------------------------------------------
  * host-side permutation drawing (no GPU involved; runs on the caller's host threads)

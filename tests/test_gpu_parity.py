@@ -311,6 +311,62 @@ def test_resid_pass_gram_null_vs_oracle(cna, N, n, S, r, nb):
     np.testing.assert_array_equal(np.isnan(coef.cpu().numpy()), ~valid)
 
 
+def test_cell_reordering_is_transparent(cna, demo, synth, monkeypatch):
+    """The Cuthill-McKee cell order (tl/_graph.py, csrc/reorder.cu) only renames cells on the device:
+    forced on for the small golden graphs, every output must still match the reference, and the
+    diffusion must agree with the run in the original order to rounding of the edge normalisation
+    (rows keep their edges in the original order, so the sums themselves are performed identically)."""
+    import torch
+    from cna_b200.tl._graph import DeviceGraph
+    A = cases.demo_anndata().obsp["connectivities"]
+    gr = DeviceGraph(A, reorder=True)
+    N = A.shape[0]
+    order, inv = gr.order.cpu().numpy(), gr.inv.cpu().numpy()
+    assert sorted(order.tolist()) == list(range(N)) and (inv[order] == np.arange(N)).all()
+    # locality: the reordered graph is banded
+    Ap = sp.csr_matrix((gr.data.cpu().numpy(), gr.indices.cpu().numpy(), gr.indptr.cpu().numpy()), shape=A.shape)
+    assert abs(Ap - A[order][:, order]).max() == 0
+    rows = np.repeat(np.arange(N), np.diff(Ap.indptr))
+    assert np.mean(np.abs(rows - Ap.indices)) < 0.5 * np.mean(np.abs(np.repeat(np.arange(N), np.diff(A.indptr)) - A.indices))
+
+    class D:
+        pass
+    rng = np.random.default_rng(0)
+    s0 = rng.normal(size=(N, 3))
+    d = D()
+    d.obsp = {"connectivities": A}
+    monkeypatch.setenv("CNA_B200_REORDER", "0")
+    plain = cna.tl.diffuse(d, s0, 2)
+    monkeypatch.setenv("CNA_B200_REORDER", "1")
+    reord = cna.tl.diffuse(d, s0, 2)
+    # same sums in the same order; only the column sums (fp64 atomics) differ in the last bits
+    np.testing.assert_allclose(plain, reord, rtol=1e-11, atol=1e-15)
+    for name in list(cases.DEMO_CASES)[:3]:
+        arrays, scalars = demo
+        spec = cases.DEMO_CASES[name]
+        data, kwargs = cases.build_demo_case(cases.load_demo_graph(), spec)
+        res, warns = helpers.run_association(cna.tl.association, data, kwargs, spec.get("np_seed"))
+        helpers.assert_matches_golden(res, data, kwargs.get("key_added", "coef"), arrays, scalars, name,
+                                      warns=warns, rtol=RTOL, atol=1e-9, fp32=True)
+    for name in list(cases.SYNTH_CASES):
+        arrays, scalars = synth
+        spec = cases.SYNTH_CASES[name]
+        data, kwargs = cases.build_synth_case(spec, helpers.synth_raw(arrays, name))
+        res, warns = helpers.run_association(cna.tl.association, data, kwargs)
+        helpers.assert_matches_golden(res, data, "coef", arrays, scalars, name, warns=warns, rtol=RTOL,
+                                      atol=1e-9, fp32=True)
+    # nam() / svd_nam on the reordered graph: labels and keep mask in the caller's order
+    ref_spec = dict(y="case", covs=["male"], batches="batch")
+    data, kw = cases.build_demo_case(cases.load_demo_graph(), ref_spec)
+    monkeypatch.setenv("CNA_B200_REORDER", "1")
+    nam_r, keep_r = cna.tl.nam(data, "id", batches=kw["batches"], nsteps=3)
+    monkeypatch.setenv("CNA_B200_REORDER", "0")
+    nam_p, keep_p = cna.tl.nam(data, "id", batches=kw["batches"], nsteps=3)
+    np.testing.assert_array_equal(keep_r, keep_p)
+    assert (nam_r.columns == nam_p.columns).all()
+    np.testing.assert_allclose(nam_r.to_numpy(), nam_p.to_numpy(), rtol=1e-6, atol=1e-12)
+
+
 def _default_ks(n):
     from cna_b200.tl._association import default_ks
     return default_ks(n)

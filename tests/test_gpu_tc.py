@@ -113,17 +113,25 @@ def test_null_hist_tc(lib, N, n, Kl):
     edges = _stats.threshold_edges(thr)
     xp = lib.split_f16(_padded(x), n)
     ytp = lib.split_f16(_padded(yc, 4), Kl, transpose=True)
-    hist = torch.zeros((Kl, len(thr)), dtype=torch.int32, device="cuda")
+    hist = torch.zeros(len(thr), dtype=torch.int64, device="cuda")
+    hist[0] = 3  # the kernel accumulates
     lib.null_hist_tc(xp, n, ytp, Kl, _dev(edges), float(edges[0]), hist)
-    tails = _stats.tails_from_hist(hist.cpu().numpy().astype(np.int64))
+    hs = hist.cpu().numpy()
+    hs[0] -= 3
+    tails_sum = _stats.tails_from_hist(hs)  # summed over the Kl nulls
     lo = np.stack([(z2 >= e * (1 + 1e-5)).sum(0) for e in edges], axis=1)
     hi = np.stack([(z2 >= e * (1 - 1e-5)).sum(0) for e in edges], axis=1)
-    assert (tails >= lo).all() and (tails <= hi).all()
-    assert tails.sum() > 0
+    assert (tails_sum >= lo.sum(0)).all() and (tails_sum <= hi.sum(0)).all()
+    assert tails_sum.sum() > 0
     # same counts as the CUDA-core kernel up to the same knife edge
     ycp = torch.zeros((xp.ld if False else (n + 7) // 8 * 8, (Kl + 3) // 4 * 4), dtype=torch.float32, device="cuda")
     ycp[:n, :Kl] = _dev(yc)
-    hist2 = torch.zeros_like(hist)
+    hist2 = torch.zeros((Kl, len(thr)), dtype=torch.int32, device="cuda")
     lib.null_hist(_padded(x), n, ycp, Kl, _dev(edges), float(edges[0]), hist2)
     t2 = _stats.tails_from_hist(hist2.cpu().numpy().astype(np.int64))
     assert (t2 >= lo).all() and (t2 <= hi).all()
+    # the summed table gives the same FDR as the per-null one
+    h2 = hist2.cpu().numpy().astype(np.int64)
+    rank_hist = h2[0] + 1
+    np.testing.assert_allclose(_stats.fdr_from_counts(h2.sum(0), rank_hist, n_null=Kl),
+                               _stats.fdr_from_counts(h2, rank_hist), rtol=1e-12)
