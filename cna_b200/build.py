@@ -24,7 +24,6 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC",
-    "-Xcompiler", "-ffp-contract=off",  # perm_host.cu restates numpy's RNG arithmetic literally
     "-Xptxas", "-v",
     "--expt-relaxed-constexpr",
 ]
@@ -37,13 +36,18 @@ def _nvcc():
     raise RuntimeError("nvcc not found (need CUDA 12.9 for sm_100a)")
 
 
+# host-only translation units (perm_host.cpp restates numpy's RNG arithmetic literally: baseline
+# x86-64 code generation, no FMA contraction, so that every double matches numpy's bit for bit)
+GXX_FLAGS = ["-O3", "-std=c++17", "-fPIC", "-ffp-contract=off", "-pthread"]
+
+
 def sources():
-    return sorted(f for f in os.listdir(SRC) if f.endswith(".cu"))
+    return sorted(f for f in os.listdir(SRC) if f.endswith((".cu", ".cpp")))
 
 
 def _digest():
     h = hashlib.sha256()
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(" ".join(NVCC_FLAGS + GXX_FLAGS).encode())
     files = [os.path.join(SRC, f) for f in sorted(os.listdir(SRC))] + \
             [os.path.join(INCLUDE, f) for f in sorted(os.listdir(INCLUDE))]
     for path in files:
@@ -62,9 +66,15 @@ def build(force=False, verbose=False):
         return LIB
     nvcc = _nvcc()
 
+    cuda_inc = os.path.join(os.path.dirname(os.path.dirname(os.path.realpath(nvcc))), "include")
+
     def compile_one(name):
-        obj = os.path.join(OUT, name[:-3] + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, "-I", INCLUDE, "-c", os.path.join(SRC, name), "-o", obj]
+        obj = os.path.join(OUT, os.path.splitext(name)[0] + ".o")
+        if name.endswith(".cpp"):
+            cmd = [os.environ.get("CXX", "g++"), *GXX_FLAGS, "-I", INCLUDE, "-I", cuda_inc, "-c",
+                   os.path.join(SRC, name), "-o", obj]
+        else:
+            cmd = [nvcc, *NVCC_FLAGS, "-I", INCLUDE, "-c", os.path.join(SRC, name), "-o", obj]
         res = subprocess.run(cmd, capture_output=True, text=True)
         with open(obj[:-2] + ".ptxas.log", "w") as fh:
             fh.write(res.stderr)
