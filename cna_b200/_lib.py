@@ -85,13 +85,15 @@ _SIGNATURES = {
     "cna_permute_csr": [_VP, _VP, _VP, _INT, _VP, _VP, _VP, _I64, _VP, _VP, _VP],
     "cna_host_randn": [_VP, _VP, _VP, _VP, _I64, _VP, _INT],
     "cna_host_perm_blocks": [_VP, _VP, _VP, _VP, _INT, _VP, _VP, _I64, _VP, _I64, _INT],
+    "cna_host_perm_done": [_VP],
+    "cna_host_perm_wait": [_VP],
     "cna_split_f16": [_VP, _I64, _I64, _INT, _INT, _VP, _VP, _I64, _I64, _VP],
     "cna_gram_tc": [_VP, _VP, _I64, _I64, _INT, _VP, _VP, _I64, _VP],
     "cna_right_multiply_tc": [_VP, _VP, _I64, _I64, _INT, _VP, _VP, _I64, _INT, _VP, _I64, _VP],
     "cna_null_hist_tc": [_VP, _VP, _I64, _I64, _INT, _VP, _VP, _I64, _INT, _VP, _INT, _DBL, _VP, _VP],
 }
 EXPORTS = sorted(list(_SIGNATURES) + ["cna_abi_version", "cna_last_error", "cna_launch_count",
-                                      "cna_gram_tc_workspace"])
+                                      "cna_gram_tc_workspace", "cna_host_perm_blocks_async"])
 
 
 def _declare(lib):
@@ -103,6 +105,8 @@ def _declare(lib):
     lib.cna_launch_count.argtypes = []
     lib.cna_gram_tc_workspace.restype = ctypes.c_int64
     lib.cna_gram_tc_workspace.argtypes = [ctypes.c_int]
+    lib.cna_host_perm_blocks_async.restype = ctypes.c_void_p
+    lib.cna_host_perm_blocks_async.argtypes = _SIGNATURES["cna_host_perm_blocks"]
     for name, args in _SIGNATURES.items():
         fn = getattr(lib, name)
         fn.restype = ctypes.c_int
@@ -438,6 +442,35 @@ def host_perm_blocks(block_off, src_pos, num, n_threads=0):
         _host_call("cna_host_perm_blocks", *st.args(), len(block_off) - 1, block_off.ctypes.data,
                    None if sp is None else sp.ctypes.data, int(num), out.ctypes.data, total, int(n_threads))
     return out
+
+
+class HostPermJob:
+    """``host_perm_blocks`` running on a library-owned thread.  numpy's global generator must not
+    be touched between construction and ``result()``, which writes the advanced state back."""
+
+    def __init__(self, block_off, src_pos, num, n_threads=0):
+        import numpy as np
+        self.block_off = np.ascontiguousarray(block_off, dtype=np.int32)
+        self.src_pos = None if src_pos is None else np.ascontiguousarray(src_pos, dtype=np.int32)
+        total = int(self.block_off[-1])
+        self.out = np.empty((int(num), total), dtype=np.int32)
+        self.state = _LegacyState().__enter__()
+        self.handle = load().cna_host_perm_blocks_async(
+            *self.state.args(), len(self.block_off) - 1, self.block_off.ctypes.data,
+            None if self.src_pos is None else self.src_pos.ctypes.data, int(num), self.out.ctypes.data, total,
+            int(n_threads))
+
+    def done(self):
+        return self.handle is None or bool(load().cna_host_perm_done(self.handle))
+
+    def result(self):
+        if self.handle is not None:
+            rc = load().cna_host_perm_wait(self.handle)
+            self.handle = None
+            self.state.__exit__(None, None, None)
+            if rc != 0:
+                raise CnaError(f"cna_host_perm_blocks failed ({rc}): {load().cna_last_error().decode()}")
+        return self.out
 
 
 def knn_bruteforce(points, k):

@@ -21,6 +21,7 @@
 #include <immintrin.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <chrono>
 #include <cstdint>
@@ -341,6 +342,40 @@ int cna_host_perm_blocks(uint32_t *key, int *pos, int *has_gauss, double *gauss,
     if (timing_on())
         fprintf(stderr, "[cna timing] host_perm_blocks: argsort + scatter %.2f ms (%d threads)\n", now_ms() - t_sort, n_threads);
     return CNA_OK;
+}
+
+// Asynchronous form: the draw runs on a library-owned thread (no Python thread, hence no waiting for
+// the interpreter lock on either side); cna_host_perm_wait joins it and returns its status.
+struct PermJob {
+    std::thread th;
+    std::atomic<int> finished{0};
+    int rc = 0;
+};
+
+void *cna_host_perm_blocks_async(uint32_t *key, int *pos, int *has_gauss, double *gauss, int n_blocks,
+                                 const int32_t *block_off, const int32_t *src_pos, int64_t num, int32_t *out,
+                                 int64_t ld_out, int n_threads) {
+    PermJob *job = new PermJob();
+    job->th = std::thread([=] {
+        job->rc = cna_host_perm_blocks(key, pos, has_gauss, gauss, n_blocks, block_off, src_pos, num, out, ld_out,
+                                       n_threads);
+        job->finished.store(1, std::memory_order_release);
+    });
+    return job;
+}
+
+int cna_host_perm_done(void *handle) {
+    PermJob *job = static_cast<PermJob *>(handle);
+    return job ? job->finished.load(std::memory_order_acquire) : 1;
+}
+
+int cna_host_perm_wait(void *handle) {
+    PermJob *job = static_cast<PermJob *>(handle);
+    if (!job) return cna::set_error(CNA_ERR_INVALID, "cna_host_perm_wait: null handle");
+    if (job->th.joinable()) job->th.join();
+    int rc = job->rc;
+    delete job;
+    return rc;
 }
 
 }  // extern "C"

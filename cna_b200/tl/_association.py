@@ -86,12 +86,30 @@ def default_ks(n):
     return np.arange(incr, maxnpcs + 1, incr)
 
 
+_POOL = None
+
+
+def _f_sf(f, dfn, dfd):
+    """``st.f.sf`` (:46).  scipy's incomplete-beta ufunc releases the GIL, so large inputs are
+    evaluated in row chunks on a small thread pool (same function, same bits)."""
+    global _POOL
+    if f.shape[0] < 2048:
+        return st.f.sf(f, dfn, dfd)
+    if _POOL is None:
+        from concurrent.futures import ThreadPoolExecutor
+        import os
+        _POOL = ThreadPoolExecutor(max_workers=max(1, min(8, (os.cpu_count() or 2) // 2)))
+    chunks = np.array_split(np.arange(f.shape[0]), _POOL._max_workers)
+    parts = list(_POOL.map(lambda ix: st.f.sf(f[ix[0]:ix[-1] + 1], dfn, dfd), [c for c in chunks if len(c)]))
+    return np.concatenate(parts, axis=0)
+
+
 def _f_pvalues(ssered, ssefull, ks, n, r):
     """``_association.py:41-48`` vectorised over permutations: returns (p, r2), each [K x len(ks)]."""
     ks = np.asarray(ks, dtype=np.float64)
     with np.errstate(divide="ignore", invalid="ignore"):
         f = ((ssered[:, None] - ssefull) / ks) / (ssefull / n)  # :45 (divides by n, not dof)
-        p = st.f.sf(f, ks, n - (1 + r + ks))  # :46
+        p = _f_sf(f, ks, n - (1 + r + ks))  # :46
         r2 = 1 - ssefull / ssered[:, None]  # :47
     return p, r2
 
@@ -102,49 +120,6 @@ def _pick(p, r2, ks):
         pick = np.nanargmin(p, axis=1)
     rows = np.arange(p.shape[0])
     return np.asarray(ks)[pick], p[rows, pick], r2[rows, pick]
-
-
-class _PermutationJob:
-    """Draws the permutation index matrix on a helper thread while the GPU builds the NAM.
-
-    The draws reproduce the reference's exact sequence of legacy-RNG calls on the *global* numpy
-    state (``_stats.py:8-16`` / ``:31``) through the native restatement in ``csrc/perm_host.cu``
-    (ctypes releases the GIL), so they overlap with the diffusion kernels.  The caller must not
-    touch ``np.random`` until ``result()`` has returned."""
-
-    def __init__(self, y_std, batches, donorids, Nnull):
-        import threading
-        self._out = None
-        self._exc = None
-
-        def work():
-            mark("perm thread start")
-            try:
-                if donorids is not None:  # _association.py:80-83
-                    self._out = _stats.grouplevel_permutation_matrix(donorids, y_std, Nnull)
-                else:
-                    self._out = _stats.conditional_permutation_matrix(batches, Nnull)
-            except BaseException as exc:  # re-raised on the caller's thread
-                self._exc = exc
-            mark("perm thread done")
-
-        self._thread = threading.Thread(target=work, name="cna-permutations", daemon=True)
-        self._thread.start()
-
-    def done(self):
-        return not self._thread.is_alive()
-
-    def cancel(self):
-        """Wait for the draws without using them (an error is propagating on the caller's thread)."""
-        self._thread.join()
-
-    def result(self):
-        self._thread.join()
-        if self._exc is not None:
-            raise self._exc
-        if self._out is None:
-            raise TypeError("'NoneType' object is not subscriptable")  # what the reference dies with
-        return self._out
 
 
 def _association(res, perms, Nnull=1000, local_test=True, show_progress=False):
@@ -193,7 +168,24 @@ def _association(res, perms, Nnull=1000, local_test=True, show_progress=False):
     C_d = _to_dev(res.C) if r else None
     W_d = _to_dev(np.ascontiguousarray(res.W_last)) if r else None
 
-    # ---- neighbourhood-level null (:92-103): launched before the SVD so the two overlap ----
+    def launch_pc_regressions(U):
+        """PC regressions of every permuted phenotype (:84) -> device SSEs (asynchronous)."""
+        ssered_d = torch.empty(Nnull, dtype=torch.float64, device=dev)
+        ssefull_d = torch.empty((Nnull, len(ks)), dtype=torch.float64, device=dev)
+        Ut_d = _to_dev(np.ascontiguousarray(U[:, :kmax].T))
+        ks_d = _to_dev(np.asarray(ks, dtype=np.int32))
+        _lib.perm_stats(y_d, perm_d, C_d, W_d, Ut_d, ks_d, ssered_d, ssefull_d, None, 0)
+        return ssered_d, ssefull_d
+
+    # With U already known the (tiny) PC-regression kernel goes first and its SSEs come back before
+    # the null GEMM starts, so the host-side F tests overlap the null GEMM; otherwise the null GEMM is
+    # launched first and overlaps the SVD.
+    sse_host = None
+    if svd is not None:
+        sse_d = launch_pc_regressions(svd[0])
+        sse_host = (sse_d[0].cpu().numpy(), sse_d[1].cpu().numpy())
+
+    # ---- neighbourhood-level null (:92-103) ----
     fdrs, fdr_5p_t, fdr_10p_t = None, None, None
     if local_test:
         print("computing neighborhood-level FDRs", file=out)
@@ -232,13 +224,11 @@ def _association(res, perms, Nnull=1000, local_test=True, show_progress=False):
     yhat = U[:, :k].dot(beta)
     r2_perpc = (beta / np.sqrt(ycond.dot(ycond))) ** 2  # :74
 
-    # ---- PC regressions of every permuted phenotype (:84), then the global p-value (:85-88) ----
-    ssered_d = torch.empty(Nnull, dtype=torch.float64, device=dev)
-    ssefull_d = torch.empty((Nnull, len(ks)), dtype=torch.float64, device=dev)
-    Ut_d = _to_dev(np.ascontiguousarray(U[:, :kmax].T))
-    ks_d = _to_dev(np.asarray(ks, dtype=np.int32))
-    _lib.perm_stats(y_d, perm_d, C_d, W_d, Ut_d, ks_d, ssered_d, ssefull_d, None, 0)
-    nullp, nullr2 = _f_pvalues(ssered_d.cpu().numpy(), ssefull_d.cpu().numpy(), ks, n, r)
+    # ---- the global p-value (:84-88) ----
+    if sse_host is None:
+        sse_d = launch_pc_regressions(U)
+        sse_host = (sse_d[0].cpu().numpy(), sse_d[1].cpu().numpy())
+    nullp, nullr2 = _f_pvalues(sse_host[0], sse_host[1], ks, n, r)
     _, nullminps, nullr2s = _pick(nullp, nullr2, ks)
     nhit = int((nullminps <= p + 1e-8).sum())
     pfinal = (nhit + 1) / (Nnull + 1)
@@ -310,7 +300,9 @@ def association(data, y, sid_name, batches=None, covs=None, donorids=None, ks=No
     if comm is not None and return_full:
         raise NotImplementedError("return_full=True is not supported on a cell-axis shard")
     # the permutation draws only need the sample-level inputs: start them before any GPU work
-    perms = _PermutationJob(y_std, perm_batches, donor_f, Nnull) if comm is None or comm.rank == 0 else None
+    perms = (_stats.PermutationDraw(y_std, perm_batches, donor_f, Nnull)
+             if comm is None or comm.rank == 0 else None)
+    mark("permutation draw started")
 
     # ---- launch the diffusion (asynchronous unless nsteps is None) ----
     print("computing NAM", file=out)

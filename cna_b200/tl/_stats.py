@@ -48,6 +48,56 @@ def grouplevel_permutation(G, Y, num):
     return None if ix is None else np.asarray(Y)[ix]
 
 
+def _batch_blocks(B):
+    B = np.asarray(B)
+    batchind = [np.where(B == b)[0] for b in np.unique(B)]
+    off = np.zeros(len(batchind) + 1, dtype=np.int32)
+    np.cumsum([len(bi) for bi in batchind], out=off[1:])
+    return off, np.concatenate(batchind)
+
+
+class PermutationDraw:
+    """Asynchronous ``conditional_permutation_matrix`` / ``grouplevel_permutation_matrix``: the
+    draws run on a thread owned by the native library while the caller drives the GPU.  numpy's
+    global generator must not be used until ``result()`` has returned (it is advanced there exactly
+    as the reference's calls would have advanced it)."""
+
+    def __init__(self, y_std, batches, donorids, num):
+        from .. import _lib
+        self._map = None
+        self._fail = False
+        if donorids is not None:  # _stats.py:20-32
+            G, Y = np.asarray(donorids), np.asarray(y_std)
+            Gu = np.unique(G)
+            rep = np.array([np.where(G == g)[0][0] for g in Gu])
+            Gind = np.searchsorted(Gu, G)
+            if (Y[rep][Gind] != Y).any():
+                print("ERROR: the value of Y is not identical within each group of samples")
+                self._fail, self._job = True, None
+                return
+            self._map = (rep, Gind)
+            self._job = _lib.HostPermJob(np.array([0, len(rep)], dtype=np.int32), None, num)
+        else:  # _stats.py:4-18
+            off, pos = _batch_blocks(batches)
+            self._job = _lib.HostPermJob(off, pos, num)
+
+    def done(self):
+        return self._job is None or self._job.done()
+
+    def cancel(self):
+        if self._job is not None:
+            self._job.result()
+
+    def result(self):
+        if self._fail:
+            raise TypeError("'NoneType' object is not subscriptable")  # what the reference dies with
+        out = self._job.result()
+        if self._map is not None:
+            rep, Gind = self._map
+            out = np.ascontiguousarray(rep[out][:, Gind], dtype=np.int32)
+        return out
+
+
 def conditional_permutation_matrix(B, num):
     """The transpose of ``conditional_permutation_indices`` as int32 [num x n] (row k = permutation
     k, the layout ``cna_perm_stats`` consumes), drawn by the native restatement of numpy's legacy

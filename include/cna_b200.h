@@ -276,6 +276,15 @@ int cna_host_perm_blocks(uint32_t *key, int *pos, int *has_gauss, double *gauss,
                          const int32_t *block_off, const int32_t *src_pos, int64_t num, int32_t *out,
                          int64_t ld_out, int n_threads);
 
+/* Asynchronous form of cna_host_perm_blocks: the draw runs on a thread owned by the library and
+ * every buffer (including the four state words) must stay alive until cna_host_perm_wait, which
+ * joins the thread, frees the handle and returns the status.  cna_host_perm_done polls (1 = finished). */
+void *cna_host_perm_blocks_async(uint32_t *key, int *pos, int *has_gauss, double *gauss, int n_blocks,
+                                 const int32_t *block_off, const int32_t *src_pos, int64_t num,
+                                 int32_t *out, int64_t ld_out, int n_threads);
+int cna_host_perm_done(void *handle);
+int cna_host_perm_wait(void *handle);
+
 /* ------------------------------------------------------------------------------------------
  * utilities used by the data generator (not on the timed path)
  * ------------------------------------------------------------------------------------------ */

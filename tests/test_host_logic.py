@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol():
     from cna_b200 import _lib
     lib = _lib.load()
     header = open(os.path.join(ROOT, "include", "cna_b200.h")).read()
-    declared = set(re.findall(r"^(?:int|int64_t|const char \*)\s*\*?\s*(cna_\w+)\s*\(", header, flags=re.M))
+    declared = set(re.findall(r"^(?:int|int64_t|const char \*|void \*)\s*\*?\s*(cna_\w+)\s*\(", header, flags=re.M))
     assert len(declared) >= 20
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/cna_b200.h but not exported"
@@ -82,7 +82,7 @@ def test_check_inputs_matches_oracle():
 
 def test_permutation_indices_are_bit_exact():
     from cna_b200.tl import _stats
-    from cna_b200.tl._association import _PermutationJob
+    from cna_b200.tl._stats import PermutationDraw as _PermutationJob
     rng = np.random.default_rng(0)
     B = rng.integers(0, 4, 57)
     Y = rng.normal(size=57)
