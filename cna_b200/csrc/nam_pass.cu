@@ -9,7 +9,6 @@
 // Reference: src/cna/tools/_nam.py:78-99 (QC), :118-159 (_resid_nam), _association.py:175-185
 // (reindex, filter, zero-variance drop), :77 (ncorrs).
 #include <cuda_fp16.h>
-#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -281,179 +280,6 @@ __global__ void __launch_bounds__(256) resid_kernel(cna_resid_args a) {
     }
 }
 
-// ---------------------------------------------------------------------------------------------
-// The same pass, tile version: a CTA stages 64 rows in shared memory and four threads share a row
-// (interleaved columns m = q + 4j).  Compared with the warp-per-row kernel above this removes the
-// 5-step warp reductions (two xor-shuffles per reduction instead of ten), makes every W / C
-// coefficient load a 32-byte broadcast shared by 8 rows, and writes the outputs with fully
-// coalesced row stores: ~5x fewer issued instructions (the warp kernel is issue-bound: 1756
-// warp-instructions per row, profiles/).  Used whenever r <= 16 and the tile fits in shared memory.
-// ---------------------------------------------------------------------------------------------
-constexpr int kTileRows = 64;
-
-__device__ __forceinline__ double quad_sum(double v) {
-    v += __shfl_xor_sync(kFull, v, 1);
-    v += __shfl_xor_sync(kFull, v, 2);
-    return v;
-}
-
-template <int RMAX>
-__global__ void __launch_bounds__(256) resid_tile_kernel(cna_resid_args a, int stride) {
-    extern __shared__ double sm[];
-    const int n = a.n, r = a.r, nb = a.n_batches;
-    const bool want_kurt = (a.kurt != nullptr) && nb > 1;
-    double *Wt = sm;                          // [r][n]
-    double *Ct = Wt + r * n;                  // [r][n]
-    double *ys = Ct + r * n;                  // [n]
-    double *invc = ys + n;                    // [n]
-    double *bsum = invc + n;                  // [256 threads][nb] private batch sums (want_kurt)
-    double *binv = bsum + (want_kurt ? 256 * nb : 0);        // [nb] 1 / samples in batch
-    float *raw = reinterpret_cast<float *>(binv + (want_kurt ? nb : 0));  // [kTileRows][stride]
-    int *colmap = reinterpret_cast<int *>(raw + kTileRows * stride);      // [n]
-    uint8_t *bidx = reinterpret_cast<uint8_t *>(colmap + n);              // [n] batch of each column
-    for (int t = threadIdx.x; t < r * n; t += blockDim.x) {
-        Wt[t] = a.Wt[t];
-        Ct[t] = a.C[(t % n) * r + t / n];
-    }
-    for (int t = threadIdx.x; t < n; t += blockDim.x) {
-        int c = a.colmap[t];
-        colmap[t] = c;
-        ys[t] = a.y[t];
-        invc[t] = a.inv_count[c];
-    }
-    if (want_kurt) {
-        for (int b = threadIdx.x; b < nb; b += blockDim.x) {
-            int t0 = a.seg_off[b], t1 = a.seg_off[b + 1];
-            binv[b] = 1.0 / double(t1 - t0);
-            for (int t = t0; t < t1; ++t) bidx[a.seg_order[t]] = uint8_t(b);
-        }
-        for (int t = threadIdx.x; t < 256 * nb; t += blockDim.x) bsum[t] = 0.0;
-    }
-    __syncthreads();
-
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int lr = threadIdx.x >> 2, qd = threadIdx.x & 3;  // local row, quarter
-    const double dn = double(n);
-    const int64_t n_tiles = (a.n_rows + kTileRows - 1) / kTileRows;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int64_t row0 = tile * kTileRows;
-        // ---- stage the selected columns of 64 rows (a warp per row, lanes over columns) ----
-        for (int rr = warp; rr < kTileRows; rr += 8) {
-            const int64_t row = row0 + rr;
-            if (row < a.n_rows) {
-                const float *p = a.s + row * a.ld_s;
-                for (int m = lane; m < n; m += 32) raw[rr * stride + m] = __ldg(p + colmap[m]);
-            } else {
-                for (int m = lane; m < n; m += 32) raw[rr * stride + m] = 0.f;
-            }
-        }
-        __syncthreads();
-        const int64_t row = row0 + lr;
-        float *xr = raw + lr * stride;
-        // pass A: mean (_nam.py:122)
-        double sum = 0.0;
-        for (int m = qd; m < n; m += 4) sum += double(xr[m]) * invc[m];
-        const double mean = quad_sum(sum) / dn;
-        // pass B: variance of the centred row and the r projections X.Wt^T (_nam.py:133 / :146)
-        double ss = 0.0, proj[RMAX > 0 ? RMAX : 1];
-#pragma unroll
-        for (int k = 0; k < RMAX; ++k) proj[k] = 0.0;
-        for (int m = qd; m < n; m += 4) {
-            const double xc = double(xr[m]) * invc[m] - mean;
-            ss += xc * xc;
-#pragma unroll
-            for (int k = 0; k < RMAX; ++k)
-                if (k < r) proj[k] += xc * Wt[k * n + m];
-        }
-        ss = quad_sum(ss);
-#pragma unroll
-        for (int k = 0; k < RMAX; ++k)
-            if (k < r) proj[k] = quad_sum(proj[k]);
-        const bool keep = (row < a.n_rows) && (a.row_keep ? (a.row_keep[row] != 0) : true);
-        const bool valid = keep && !(ss / (dn - 1.0) == 0.0);  // _association.py:182-185
-        // pass C: moments (and batch sums) of the residualised row x' = xc - proj.C^T
-        double s1 = 0.0, s2 = 0.0;
-        for (int m = qd; m < n; m += 4) {
-            double x = double(xr[m]) * invc[m] - mean;
-#pragma unroll
-            for (int k = 0; k < RMAX; ++k)
-                if (k < r) x -= proj[k] * Ct[k * n + m];
-            s1 += x;
-            s2 += x * x;
-            if (want_kurt) bsum[threadIdx.x * nb + bidx[m]] += x;  // this thread's quarter of the row
-        }
-        s1 = quad_sum(s1);
-        s2 = quad_sum(s2);
-        const double mean2 = s1 / dn;  // pandas std recomputes the mean (_nam.py:159)
-        const double inv_sd = 1.0 / sqrt((s2 - dn * mean2 * mean2) / (dn - 1.0));
-        if (want_kurt) {  // _nam.py:150-155 (Pearson kurtosis of the per-batch means)
-            __syncwarp();
-            if (qd == 0) {  // quarters are summed in a fixed order: deterministic
-                double *q0 = bsum + threadIdx.x * nb;
-                for (int b = 0; b < nb; ++b) {
-                    q0[b] = ((q0[b] + q0[nb + b]) + q0[2 * nb + b]) + q0[3 * nb + b];
-                    q0[nb + b] = q0[2 * nb + b] = q0[3 * nb + b] = 0.0;
-                }
-                double k = nan("");
-                if (valid) {
-                    double mm = 0.0;
-                    for (int b = 0; b < nb; ++b) mm += q0[b] * binv[b];
-                    mm /= nb;
-                    double m2 = 0.0, m4 = 0.0;
-                    for (int b = 0; b < nb; ++b) {
-                        double d = q0[b] * binv[b] - mm;
-                        m2 += d * d;
-                        m4 += d * d * d * d;
-                    }
-                    k = kurtosis_from_moments(mm, m2 / nb, m4 / nb, false);
-                }
-                if (row < a.n_rows) a.kurt[row] = k;
-                for (int b = 0; b < nb; ++b) q0[b] = 0.0;
-            }
-        } else if (a.kurt && qd == 0 && row < a.n_rows) {
-            a.kurt[row] = nan("");
-        }
-        // pass D: standardise (ddof=1), coefficient (_association.py:77), outputs back into the tile
-        double dot = 0.0;
-        for (int m = qd; m < n; m += 4) {
-            double x = double(xr[m]) * invc[m] - mean;
-#pragma unroll
-            for (int k = 0; k < RMAX; ++k)
-                if (k < r) x -= proj[k] * Ct[k * n + m];
-            const double v = valid ? x * inv_sd : 0.0;  // rows of dropped cells are zero
-            dot += v * ys[m];
-            xr[m] = float(v);
-        }
-        dot = quad_sum(dot);
-        if (qd == 0 && row < a.n_rows) {
-            a.ncorr[row] = valid ? dot / dn : 0.0;
-            a.row_valid[row] = valid ? 1 : 0;
-        }
-        __syncthreads();
-        // ---- coalesced stores: a warp per row ----
-        for (int rr = warp; rr < kTileRows; rr += 8) {
-            const int64_t orow = row0 + rr;
-            if (orow >= a.n_rows) break;
-            const float *src = raw + rr * stride;
-            if (a.x_out) {
-                float *o = a.x_out + orow * a.ld_x;
-                for (int m = lane; m < a.ld_x; m += 32) o[m] = (m < n) ? src[m] : 0.f;
-            }
-            if (a.x16_hi) {  // v = hi + lo to 2^-22
-                __half *ph = static_cast<__half *>(a.x16_hi) + orow * a.ld16;
-                __half *pl = static_cast<__half *>(a.x16_lo) + orow * a.ld16;
-                for (int m = lane; m < a.ld16; m += 32) {
-                    float v = (m < n) ? src[m] : 0.f;
-                    __half h = __float2half_rn(v);
-                    ph[m] = h;
-                    pl[m] = __float2half_rn(v - __half2float(h));
-                }
-            }
-        }
-        __syncthreads();
-    }
-}
-
 }  // namespace cna
 
 using namespace cna;
@@ -492,36 +318,6 @@ int cna_resid_pass(const cna_resid_args *args, void *stream) {
                 "cna_resid_pass: bad fp16 planes (ld16=%lld n=%d)", (long long)a.ld16, a.n);
     CNA_REQUIRE(a.r == 0 || (a.C && a.Wt), "cna_resid_pass: C/Wt missing");
     if (a.n_rows == 0) return CNA_OK;
-    {   // tile kernel (four threads per row) whenever its shared-memory tile fits
-        const bool wk = a.kurt && a.n_batches > 1;
-        CNA_REQUIRE(!wk || (a.seg_order && a.seg_off), "cna_resid_pass: batch segments missing");
-        int stride = a.n;
-        while (stride % 8 != 4) ++stride;  // quarter-interleaved reads of 8 rows hit 32 distinct banks
-        size_t smem_t = sizeof(double) * (2 * size_t(a.r) * a.n + 2 * size_t(a.n) +
-                                          (wk ? size_t(256) * a.n_batches + a.n_batches : 0)) +
-                        sizeof(float) * size_t(kTileRows) * stride + sizeof(int) * size_t(a.n) +
-                        ((a.n + 3) & ~3) + 16;
-        if (a.r <= 16 && a.n_batches <= 255 && smem_t <= 100 * 1024 && !getenv("CNA_B200_RESID_WARP")) {
-            int64_t tiles = (a.n_rows + kTileRows - 1) / kTileRows;
-            int64_t cap = int64_t(num_sms()) * 3;
-            unsigned grid = unsigned(tiles < cap ? tiles : cap);
-            cudaStream_t st = as_stream(stream);
-#define CNA_RESID_TILE(RM)                                                                                   \
-    do {                                                                                                     \
-        CNA_CUDA(cudaFuncSetAttribute(resid_tile_kernel<RM>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
-                                      int(smem_t)));                                                         \
-        resid_tile_kernel<RM><<<grid, 256, smem_t, st>>>(a, stride);                                         \
-    } while (0)
-            if (a.r == 0) CNA_RESID_TILE(0);
-            else if (a.r <= 2) CNA_RESID_TILE(2);
-            else if (a.r <= 4) CNA_RESID_TILE(4);
-            else if (a.r <= 8) CNA_RESID_TILE(8);
-            else CNA_RESID_TILE(16);
-#undef CNA_RESID_TILE
-            CNA_LAUNCHED("resid_tile_kernel");
-            return CNA_OK;
-        }
-    }
     const int threads = 256, warps = threads / 32;
     const bool want_kurt = a.kurt && a.n_batches > 1;
     CNA_REQUIRE(!want_kurt || (a.seg_order && a.seg_off), "cna_resid_pass: batch segments missing");

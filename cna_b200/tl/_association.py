@@ -351,9 +351,9 @@ def association(data, y, sid_name, batches=None, covs=None, donorids=None, ks=No
         both = stn.graph.unpermute(both)  # back to the caller's cell order
     both = _to_host_pinned(both.t())
     mark("results on host")
-    data.obs[key_added] = both[0].copy()  # `both` is a view of the reusable staging buffer
+    data.obs[key_added] = both[0]  # pandas copies on assignment (`both` is the reusable staging buffer)
     if core.fdrs is not None:
-        data.obs[f"{key_added}_fdr"] = both[1].copy()
+        data.obs[f"{key_added}_fdr"] = both[1]
     if not return_full:
         mark("obs written")
         report()

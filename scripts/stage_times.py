@@ -30,3 +30,32 @@ if len(sys.argv) > 2:
             torch.cuda.synchronize()
             print("----", mode)
             cna.tl.association(obj, **kw)
+
+# ---- host-side pieces in isolation (this box's cores) ----
+import time  # noqa: E402
+
+import numpy as np  # noqa: E402
+
+from cna_b200 import _lib  # noqa: E402
+from cna_b200.tl import _stats  # noqa: E402
+
+B = np.asarray(meta.batch)
+for nt in (0, 4, 8, 16):
+    off, pos = _stats._batch_blocks(B)
+    np.random.seed(0)
+    t = time.perf_counter()
+    _lib.host_perm_blocks(off, pos, K, nt)
+    print(f"host_perm_blocks n_threads={nt}: {(time.perf_counter() - t) * 1e3:.1f} ms")
+G = np.random.default_rng(0).normal(size=(S, 4 * S))
+G = G @ G.T
+from threadpoolctl import threadpool_limits  # noqa: E402
+for lim in (None, 1, 4):
+    for _ in range(2):
+        t = time.perf_counter()
+        if lim is None:
+            np.linalg.svd(G)
+        else:
+            with threadpool_limits(limits=lim, user_api="blas"):
+                np.linalg.svd(G)
+        dt = (time.perf_counter() - t) * 1e3
+    print(f"svd {S}x{S} blas threads={lim}: {dt:.2f} ms")

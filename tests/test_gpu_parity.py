@@ -367,6 +367,20 @@ def test_cell_reordering_is_transparent(cna, demo, synth, monkeypatch):
     np.testing.assert_allclose(nam_r.to_numpy(), nam_p.to_numpy(), rtol=1e-6, atol=1e-12)
 
 
+def test_obs_columns_do_not_alias_the_staging_buffer(cna):
+    """The per-cell results travel through a reusable pinned staging buffer: a second call must not
+    change the columns written by the first."""
+    data, kw = cases.build_demo_case(cases.load_demo_graph(), dict(y="case", batches="batch", nsteps=2,
+                                                                    Nnull=50, seed=1))
+    cna.tl.association(data, key_added="first", **{k: v for k, v in kw.items() if k != "key_added"})
+    first = data.obs["first"].to_numpy().copy()
+    kw2 = dict(kw)
+    kw2["y"] = -kw["y"]
+    cna.tl.association(data, key_added="second", **{k: v for k, v in kw2.items() if k != "key_added"})
+    np.testing.assert_array_equal(data.obs["first"].to_numpy(), first)
+    np.testing.assert_allclose(data.obs["second"].to_numpy(), -first, rtol=1e-12, atol=1e-15)
+
+
 def _default_ks(n):
     from cna_b200.tl._association import default_ks
     return default_ks(n)
