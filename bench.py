@@ -244,6 +244,10 @@ def rooflines(prof, steps, N, S, n, nnz, K, Kl, s_steps, peaks):
 
 
 def run_ours(args):
+    # stdout carries exactly one JSON line: anything libraries print there (NCCL's version banner,
+    # warnings) goes to stderr instead
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
 
@@ -325,7 +329,8 @@ def run_ours(args):
         dist.destroy_process_group()
         return
     peaks = measured_peaks()
-    roofs = rooflines(prof, args.steps, N, S, n, nnz, K, Kl, s_steps, peaks)
+    # per-kernel work of one launch = this rank's share of the cells (and of the stored edges)
+    roofs = rooflines(prof, args.steps, N // world, S, n, nnz // world, K, Kl, s_steps, peaks)
     spmm = next((r for r in roofs if r["kernel"] == "cna_diffuse_step_f32"), None)
     primary = None
     if spmm:
@@ -347,7 +352,7 @@ def run_ours(args):
         t = time_cpu_arm(cdata, ckw, 1, 0)
         line["cpu_baseline"] = {"value": len(cdata.obs) / t[0], "unit": "cells/s", "cores": cpu_threads(),
                                 "kind": "port", "sample": sample, "seconds": t[0]}
-    print(json.dumps(line))
+    os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 

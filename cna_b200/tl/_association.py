@@ -154,7 +154,7 @@ def _association(res, perms, Nnull=1000, local_test=True, show_progress=False):
     # otherwise the null kernels are launched first and the SVD overlaps them.
     svd = None
     if perms is not None and not perms.done():
-        svd = _nam.svd_of_gram(Gh)  # _nam.py:105
+        svd = _nam.svd_of_gram(Gh, top=res.svd_top)  # _nam.py:105
 
     # ---- permutations: indices from the host RNG (bit-exact), everything else on the device ----
     if perms is not None:
@@ -207,7 +207,7 @@ def _association(res, perms, Nnull=1000, local_test=True, show_progress=False):
             comm.all_reduce(obs)
     mark("null kernels launched")
 
-    U, svs, res.G = svd if svd is not None else _nam.svd_of_gram(Gh)  # _nam.py:105
+    U, svs, res.G = svd if svd is not None else _nam.svd_of_gram(Gh, top=res.svd_top)  # _nam.py:105
     res.U, res.svs = U, svs
 
     # ---- observed phenotype (:64-74): n-sized host arithmetic in float64 -----------------
@@ -323,6 +323,8 @@ def association(data, y, sid_name, batches=None, covs=None, donorids=None, ks=No
     mark("resid pass done")
     res.y_std = y_std
     res.ks = ks_eff
+    # only the leading max(ks) components are read unless the full result surface is requested
+    res.svd_top = None if return_full else int(max(ks_eff))
     print("performing association test", file=out)
     core = _association(res, perms, Nnull=Nnull, local_test=local_test, show_progress=show_progress)
     svs = res.svs

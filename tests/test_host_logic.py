@@ -231,3 +231,21 @@ def test_native_permutations_are_bit_exact(n, nb, num):
     np.testing.assert_array_equal(got, want.T)
     # phenotype that varies within a donor: the reference prints an error and returns None
     assert _stats.grouplevel_permutation_matrix(G, rng.normal(size=n), num) is None
+
+
+def test_leading_eigenpairs_match_full_svd():
+    """svd_of_gram(top=k): same leading singular values and the same projectors U_k U_k^T as the
+    reference's full np.linalg.svd of the Gram (_nam.py:105); column signs are free."""
+    from cna_b200.tl._nam import svd_of_gram
+    rng = np.random.default_rng(0)
+    X = rng.normal(size=(120, 5000))
+    X -= X.mean(axis=0)
+    G = X @ X.T
+    U, svs, _ = np.linalg.svd(G)
+    Ut, st, _ = svd_of_gram(G, top=16)
+    np.testing.assert_allclose(st[:16], svs[:16], rtol=1e-12)
+    assert (st[16:] == 0).all() and (Ut[:, 16:] == 0).all()
+    for k in (1, 4, 16):
+        np.testing.assert_allclose(Ut[:, :k] @ Ut[:, :k].T, U[:, :k] @ U[:, :k].T, atol=1e-10)
+    Uf, sf, _ = svd_of_gram(G)
+    np.testing.assert_array_equal(sf, svs)
