@@ -76,6 +76,7 @@ _SIGNATURES = {
     "cna_right_multiply": [_VP, _I64, _I64, _INT, _VP, _I64, _INT, _VP, _I64, _VP],
     "cna_perm_stats": [_VP, _VP, _I64, _INT, _VP, _VP, _INT, _VP, _INT, _VP, _INT, _VP, _VP, _VP,
                        _I64, _INT, _VP, _VP, _I64, _VP],
+    "cna_perm_minp": [_VP, _VP, _I64, _VP, _INT, _INT, _INT, _VP, _VP, _VP, _VP],
     "cna_null_hist": [_VP, _I64, _I64, _INT, _VP, _I64, _INT, _VP, _INT, _DBL, _VP, _VP],
     "cna_obs_hist": [_VP, _VP, _I64, _VP, _VP, _INT, _VP, _VP, _VP],
     "cna_absmax": [_VP, _VP, _I64, _VP, _VP],
@@ -282,6 +283,13 @@ def perm_stats(y, perm, C, W, Ut, ks, ssered, ssefull, ycond, n_local, planes=No
                                  0 if planes is None else planes.ld, _stream())
 
 
+def perm_minp(ssered, ssefull, ks, n, r, minp, argk, r2):
+    _call("cna_perm_minp", _ptr(ssered, torch.float64, "ssered"), _ptr(ssefull, torch.float64, "ssefull"),
+          ssered.numel(), _ptr(ks, torch.int32, "ks"), ks.numel(), int(n), int(r),
+          _ptr(minp, torch.float64, "minp"), _ptr(argk, torch.int32, "argk"), _ptr(r2, torch.float64, "r2"),
+          _stream())
+
+
 def null_hist(x, n, ycond, n_null, edges, edge0, hist):
     _call("cna_null_hist", _ptr(x, torch.float32, "x"), x.shape[1], x.shape[0], int(n),
                                 _ptr(ycond, torch.float32, "ycond"), ycond.shape[1], int(n_null),
@@ -453,7 +461,9 @@ class HostPermJob:
         self.block_off = np.ascontiguousarray(block_off, dtype=np.int32)
         self.src_pos = None if src_pos is None else np.ascontiguousarray(src_pos, dtype=np.int32)
         total = int(self.block_off[-1])
-        self.out = np.empty((int(num), total), dtype=np.int32)
+        # page-locked when a GPU is present: the index matrix goes straight to the device afterwards
+        self.out_t = torch.empty((int(num), total), dtype=torch.int32, pin_memory=torch.cuda.is_available())
+        self.out = self.out_t.numpy()
         self.state = _LegacyState().__enter__()
         self.handle = load().cna_host_perm_blocks_async(
             *self.state.args(), len(self.block_off) - 1, self.block_off.ctypes.data,
@@ -471,6 +481,11 @@ class HostPermJob:
             if rc != 0:
                 raise CnaError(f"cna_host_perm_blocks failed ({rc}): {load().cna_last_error().decode()}")
         return self.out
+
+    def result_tensor(self):
+        """The (pinned) host tensor behind ``result()``."""
+        self.result()
+        return self.out_t
 
 
 def knn_bruteforce(points, k):

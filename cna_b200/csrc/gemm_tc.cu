@@ -224,7 +224,9 @@ xb_tc_kernel(const __grid_constant__ CUtensorMap tm_ah, const __grid_constant__ 
     float *guess = reinterpret_cast<float *>(tmem_slot + 2);              // [2]: sqrt(e_0), bins per unit sqrt
     float *queue_v = guess + 2;                                            // [warps][kQueue]
     uint32_t *hist_s = reinterpret_cast<uint32_t *>(queue_v + kXbEpiWarps * kQueue);  // [n_edges] CTA-private
-    double *edges_s = reinterpret_cast<double *>(hist_s + ((a.n_edges + 1) & ~1));
+    float *elo_s = reinterpret_cast<float *>(hist_s + a.n_edges);  // [n_edges] edge b, nudged up
+    float *ehi_s = elo_s + a.n_edges;                               // [n_edges] edge b+1, nudged down
+    double *edges_s = reinterpret_cast<double *>(ehi_s + a.n_edges + (a.n_edges & 1));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_row_tiles = int((a.n_rows + kBM - 1) / kBM);
@@ -250,6 +252,10 @@ xb_tc_kernel(const __grid_constant__ CUtensorMap tm_ah, const __grid_constant__ 
         for (int t = threadIdx.x; t < a.n_edges; t += blockDim.x) {
             edges_s[t] = a.edges[t];
             hist_s[t] = 0;
+            // fp32 copies with a 2e-6 relative guard band (the fp32 value of z^2 carries < 3e-7 of
+            // rounding): a product strictly inside (elo[b], ehi[b]) is in bin b beyond doubt
+            elo_s[t] = float(a.edges[t] * (1.0 + 2e-6));
+            ehi_s[t] = (t + 1 < a.n_edges) ? float(a.edges[t + 1] * (1.0 - 2e-6)) : 3.0e38f;
         }
         if (threadIdx.x == 32) {
             // the thresholds are (close to) an arithmetic progression, so sqrt(edge) is close to
@@ -324,6 +330,7 @@ xb_tc_kernel(const __grid_constant__ CUtensorMap tm_ah, const __grid_constant__ 
         const int q = warp & 3, part = (warp - 2) >> 2, ew = warp - 2;
         float *qv = queue_v + ew * kQueue;
         const float g0 = (E == Epi::HIST) ? guess[0] : 0.f, g1 = (E == Epi::HIST) ? guess[1] : 0.f;
+        const float inv_n_f = float(a.inv_n);
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int rt = blockIdx.x; rt < n_row_tiles; rt += gridDim.x) {
@@ -372,13 +379,18 @@ xb_tc_kernel(const __grid_constant__ CUtensorMap tm_ah, const __grid_constant__ 
                         // pass 2: all lanes busy on survivors: bin lookup + one shared-memory atomic each
                         // (the FDR only needs the histogram summed over the null columns, _stats.py:79-80)
                         for (int i = lane; i < total; i += 32) {
-                            double z = double(qv[i]) * a.inv_n;
-                            double z2 = z * z;
-                            if (!(z2 >= edges_s[0])) continue;
-                            int b = int((sqrtf(float(z2)) - g0) * g1);
+                            const float vf = qv[i];
+                            const float zf = vf * inv_n_f, z2f = zf * zf;
+                            int b = int((sqrtf(z2f) - g0) * g1);
                             b = max(0, min(b, a.n_edges - 1));
-                            while (b + 1 < a.n_edges && edges_s[b + 1] <= z2) ++b;  // largest b with edges[b] <= z2
-                            while (b > 0 && edges_s[b] > z2) --b;
+                            if (!(z2f > elo_s[b] && z2f < ehi_s[b])) {
+                                // within rounding distance of an edge (or a missed guess): decide in fp64
+                                const double z = double(vf) * a.inv_n;
+                                const double z2 = z * z;
+                                if (!(z2 >= edges_s[0])) continue;
+                                while (b + 1 < a.n_edges && edges_s[b + 1] <= z2) ++b;  // largest b with edges[b] <= z2
+                                while (b > 0 && edges_s[b] > z2) --b;
+                            }
                             atomicAdd(hist_s + b, 1u);
                         }
                         __syncwarp();
@@ -637,7 +649,7 @@ static int xb_tc_launch(Epi epi, const void *xh, const void *xl, int64_t ld16, i
     a.n_ksteps = (n + 15) / 16;
     a.n_out = n_out;
     size_t smem = size_t(kStages) * kStageBytes + 1024 + 256 + size_t(kXbEpiWarps) * kQueue * 4 +
-                  (epi == Epi::HIST ? (sizeof(double) + sizeof(uint32_t)) * (a.n_edges + 2) : 0);
+                  (epi == Epi::HIST ? (sizeof(double) + sizeof(uint32_t) + 2 * sizeof(float)) * (a.n_edges + 2) : 0);
     int64_t tiles = (n_rows + kBM - 1) / kBM;
     unsigned grid = unsigned(tiles < num_sms() ? tiles : num_sms());
     if (epi == Epi::HIST) {

@@ -128,9 +128,91 @@ perm_stats_kernel(const double *__restrict__ y, const int32_t *__restrict__ perm
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// F survival function and min-p over ks for every permutation (_association.py:45-46, :53-60)
+// ---------------------------------------------------------------------------------------------
+// Continued fraction of the incomplete beta function (modified Lentz), evaluated in fp64.
+__device__ double betacf(double a, double b, double x) {
+    const double tiny = 1e-300, eps = 1e-16;
+    const double qab = a + b, qap = a + 1.0, qam = a - 1.0;
+    double c = 1.0, d = 1.0 - qab * x / qap;
+    if (fabs(d) < tiny) d = tiny;
+    d = 1.0 / d;
+    double h = d;
+    for (int m = 1; m <= 500; ++m) {
+        const double m2 = 2.0 * m;
+        double aa = m * (b - m) * x / ((qam + m2) * (a + m2));
+        d = 1.0 + aa * d;
+        if (fabs(d) < tiny) d = tiny;
+        c = 1.0 + aa / c;
+        if (fabs(c) < tiny) c = tiny;
+        d = 1.0 / d;
+        h *= d * c;
+        aa = -(a + m) * (qab + m) * x / ((a + m2) * (qap + m2));
+        d = 1.0 + aa * d;
+        if (fabs(d) < tiny) d = tiny;
+        c = 1.0 + aa / c;
+        if (fabs(c) < tiny) c = tiny;
+        d = 1.0 / d;
+        const double del = d * c;
+        h *= del;
+        if (fabs(del - 1.0) < eps) break;
+    }
+    return h;
+}
+
+// Regularised incomplete beta I_x(a, b).
+__device__ double reg_inc_beta(double a, double b, double x) {
+    if (!(x > 0.0)) return 0.0;
+    if (!(x < 1.0)) return 1.0;
+    const double lbt = lgamma(a + b) - lgamma(a) - lgamma(b) + a * log(x) + b * log1p(-x);
+    const double bt = exp(lbt);
+    if (x < (a + 1.0) / (a + b + 2.0)) return bt * betacf(a, b, x) / a;
+    return 1.0 - bt * betacf(b, a, 1.0 - x) / b;
+}
+
+// scipy.special.fdtrc(dfn, dfd, f) = I_{dfd / (dfd + dfn f)}(dfd / 2, dfn / 2); 1 for f <= 0, NaN in -> NaN
+__device__ double f_survival(double dfn, double dfd, double f) {
+    if (f != f) return f;
+    if (!(f > 0.0)) return 1.0;
+    if (isinf(f)) return 0.0;
+    return reg_inc_beta(0.5 * dfd, 0.5 * dfn, dfd / (dfd + dfn * f));
+}
+
+__global__ void minp_kernel(const double *__restrict__ ssered, const double *__restrict__ ssefull, int64_t K,
+                            const int32_t *__restrict__ ks, int nks, int n, int r, double *__restrict__ minp,
+                            int32_t *__restrict__ argk, double *__restrict__ r2) {
+    int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= K) return;
+    const double red = ssered[i];
+    double best = nan("");
+    int best_a = -1;
+    for (int a = 0; a < nks; ++a) {
+        const double k = double(ks[a]), full = ssefull[i * nks + a];
+        const double f = ((red - full) / k) / (full / double(n));  // :45 (divides by n, not dof)
+        const double p = f_survival(k, double(n - (1 + r + ks[a])), f);
+        if (p == p && (best_a < 0 || p < best)) {  // nanargmin: first minimum, NaNs skipped
+            best = p;
+            best_a = a;
+        }
+    }
+    minp[i] = best;
+    argk[i] = best_a;
+    r2[i] = best_a >= 0 ? 1.0 - ssefull[i * nks + best_a] / red : nan("");
+}
+
 }  // namespace cna
 
 using namespace cna;
+
+extern "C" int cna_perm_minp(const double *ssered, const double *ssefull, int64_t K, const int32_t *ks, int nks,
+                             int n, int r, double *minp, int32_t *argk, double *r2, void *stream) {
+    CNA_REQUIRE(K >= 0 && nks >= 1 && ssered && ssefull && ks && minp && argk && r2, "cna_perm_minp: bad arguments");
+    if (K == 0) return CNA_OK;
+    minp_kernel<<<unsigned((K + 127) / 128), 128, 0, as_stream(stream)>>>(ssered, ssefull, K, ks, nks, n, r, minp, argk, r2);
+    CNA_LAUNCHED("minp_kernel");
+    return CNA_OK;
+}
 
 extern "C" int cna_perm_stats(const double *y, const int32_t *perm, int64_t K, int n, const double *C,
                               const double *W, int r, const double *Ut, int kmax, const int32_t *ks,

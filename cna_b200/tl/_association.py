@@ -158,7 +158,7 @@ def _association(res, perms, Nnull=1000, local_test=True, show_progress=False):
 
     # ---- permutations: indices from the host RNG (bit-exact), everything else on the device ----
     if perms is not None:
-        perm_d = _to_dev(perms.result())
+        perm_d = perms.result_device(dev)
     else:  # a shard other than rank 0: the indices are drawn once, by rank 0
         perm_d = torch.empty((Nnull, n), dtype=torch.int32, device=dev)
     if comm is not None:
@@ -168,22 +168,34 @@ def _association(res, perms, Nnull=1000, local_test=True, show_progress=False):
     C_d = _to_dev(res.C) if r else None
     W_d = _to_dev(np.ascontiguousarray(res.W_last)) if r else None
 
+    want_null_table = res.svd_top is None  # full result surface: every null p-value from scipy
+
     def launch_pc_regressions(U):
-        """PC regressions of every permuted phenotype (:84) -> device SSEs (asynchronous)."""
+        """PC regressions of every permuted phenotype (:84) -> SSEs and, unless the full table of null
+        p-values is wanted on the host, the F survival function + min over ks on the device."""
         ssered_d = torch.empty(Nnull, dtype=torch.float64, device=dev)
         ssefull_d = torch.empty((Nnull, len(ks)), dtype=torch.float64, device=dev)
         Ut_d = _to_dev(np.ascontiguousarray(U[:, :kmax].T))
         ks_d = _to_dev(np.asarray(ks, dtype=np.int32))
         _lib.perm_stats(y_d, perm_d, C_d, W_d, Ut_d, ks_d, ssered_d, ssefull_d, None, 0)
-        return ssered_d, ssefull_d
+        if want_null_table:
+            return ssered_d, ssefull_d, None
+        minp_d = torch.empty(Nnull, dtype=torch.float64, device=dev)
+        argk_d = torch.empty(Nnull, dtype=torch.int32, device=dev)
+        r2_d = torch.empty(Nnull, dtype=torch.float64, device=dev)
+        _lib.perm_minp(ssered_d, ssefull_d, ks_d, n, r, minp_d, argk_d, r2_d)
+        return ssered_d, ssefull_d, (minp_d, r2_d)
 
-    # With U already known the (tiny) PC-regression kernel goes first and its SSEs come back before
-    # the null GEMM starts, so the host-side F tests overlap the null GEMM; otherwise the null GEMM is
-    # launched first and overlaps the SVD.
+    def fetch(sse_d):
+        if sse_d[2] is None:
+            return (sse_d[0].cpu().numpy(), sse_d[1].cpu().numpy(), None)
+        return (sse_d[0], sse_d[1], (sse_d[2][0].cpu().numpy(), sse_d[2][1].cpu().numpy()))
+
+    # With U already known the (tiny) PC-regression kernels go first and their results come back
+    # before the null GEMM starts; otherwise the null GEMM is launched first and overlaps the SVD.
     sse_host = None
     if svd is not None:
-        sse_d = launch_pc_regressions(svd[0])
-        sse_host = (sse_d[0].cpu().numpy(), sse_d[1].cpu().numpy())
+        sse_host = fetch(launch_pc_regressions(svd[0]))
 
     # ---- neighbourhood-level null (:92-103) ----
     fdrs, fdr_5p_t, fdr_10p_t = None, None, None
@@ -226,10 +238,21 @@ def _association(res, perms, Nnull=1000, local_test=True, show_progress=False):
 
     # ---- the global p-value (:84-88) ----
     if sse_host is None:
-        sse_d = launch_pc_regressions(U)
-        sse_host = (sse_d[0].cpu().numpy(), sse_d[1].cpu().numpy())
-    nullp, nullr2 = _f_pvalues(sse_host[0], sse_host[1], ks, n, r)
-    _, nullminps, nullr2s = _pick(nullp, nullr2, ks)
+        sse_host = fetch(launch_pc_regressions(U))
+    if sse_host[2] is None:
+        nullp, nullr2 = _f_pvalues(sse_host[0], sse_host[1], ks, n, r)
+        _, nullminps, nullr2s = _pick(nullp, nullr2, ks)
+    else:
+        # min-p per permutation from the device (fp64 incomplete beta, ~1e-13 of scipy); the few that
+        # fall within 1e-9 relative of the decision threshold are re-evaluated with scipy so that the
+        # count below is exactly the reference's
+        nullminps, nullr2s = sse_host[2]
+        thr = p + 1e-8
+        near = np.abs(nullminps - thr) <= 1e-9 * thr
+        if near.any():
+            ix = torch.as_tensor(np.nonzero(near)[0], device=dev)
+            pp, rr2 = _f_pvalues(sse_host[0][ix].cpu().numpy(), sse_host[1][ix].cpu().numpy(), ks, n, r)
+            _, nullminps[near], nullr2s[near] = _pick(pp, rr2, ks)
     nhit = int((nullminps <= p + 1e-8).sum())
     pfinal = (nhit + 1) / (Nnull + 1)
     if nhit == 0:
@@ -242,10 +265,10 @@ def _association(res, perms, Nnull=1000, local_test=True, show_progress=False):
         fdr_vals = _stats.fdr_from_counts(hist.cpu().numpy(), obs_h[0], n_null=Kl)  # _stats.py:64-83
         num_detected = _stats.tails_from_hist(obs_h[1].astype(np.int64))  # :105-108
         fdrs = pd.DataFrame({"threshold": thresholds, "fdr": fdr_vals, "num_detected": num_detected})
-        if not np.min(fdrs.fdr) > 0.05:  # :111-114
-            fdr_5p_t = fdrs[fdrs.fdr <= 0.05].iloc[0].threshold
-        if not np.min(fdrs.fdr) > 0.1:  # :115-118
-            fdr_10p_t = fdrs[fdrs.fdr <= 0.1].iloc[0].threshold
+        if not np.nanmin(fdr_vals) > 0.05:  # :111-114 (Series.min skips NaN; first row with fdr <= 0.05)
+            fdr_5p_t = thresholds[np.nonzero(fdr_vals <= 0.05)[0][0]]
+        if not np.nanmin(fdr_vals) > 0.1:  # :115-118
+            fdr_10p_t = thresholds[np.nonzero(fdr_vals <= 0.1)[0][0]]
 
     return Namespace(p=pfinal, nullminps=nullminps, k=k, ncorrs=None, fdrs=fdrs,
                      fdr_5p_t=fdr_5p_t, fdr_10p_t=fdr_10p_t, yresid_hat=yhat, yresid=ycond,

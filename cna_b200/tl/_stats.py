@@ -97,6 +97,13 @@ class PermutationDraw:
             out = np.ascontiguousarray(rep[out][:, Gind], dtype=np.int32)
         return out
 
+    def result_device(self, device):
+        """The index matrix as an int32 device tensor (asynchronous copy out of pinned memory)."""
+        if self._map is not None or self._fail:
+            import torch
+            return torch.from_numpy(self.result()).to(device, non_blocking=True)
+        return self._job.result_tensor().to(device, non_blocking=True)
+
 
 def conditional_permutation_matrix(B, num):
     """The transpose of ``conditional_permutation_indices`` as int32 [num x n] (row k = permutation

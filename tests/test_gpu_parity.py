@@ -436,3 +436,40 @@ def test_large_size_properties(cna):
     np.testing.assert_array_equal(data.obs["coef_fdr"].to_numpy(), f1)
     assert np.all(np.diff(r1.fdrs.num_detected.to_numpy()) <= 0)               # tail counts are sorted
     assert ((f1 >= 0) & (f1 <= 1) | np.isnan(f1)).all()
+
+
+@pytest.mark.parametrize("n,r,ks", [(200, 5, [4, 8, 12, 16]), (50, 6, [1, 2, 3, 4]), (37, 0, [1, 3, 4]),
+                                    (500, 12, [10, 20, 30, 40]), (12, 1, [1])])
+def test_device_f_survival_matches_scipy(cna, n, r, ks):
+    """cna_perm_minp: F survival function (incomplete beta continued fraction, fp64) and the min over
+    ks, against scipy.stats.f.sf / nanargmin (_association.py:45-46, :53-60)."""
+    import scipy.stats as st
+    import torch
+    from cna_b200 import _lib
+    rng = np.random.default_rng(n + r)
+    K = 4000
+    ssered = rng.uniform(0.5 * n, 1.5 * n, K)
+    # r2 from tiny to ~1 (log-uniform in 1 - r2 as well), non-increasing SSE along ks
+    frac = np.sort(rng.uniform(0, 1, (K, len(ks))), axis=1)[:, ::-1] ** rng.integers(1, 12, (K, 1))
+    ssefull = ssered[:, None] * np.clip(frac, 1e-12, 1.0)
+    ssefull[0] = ssered[0]                 # f = 0  -> p = 1
+    ssefull[1, -1] = 0.0                   # f = inf -> p = 0
+    ksa = np.asarray(ks, dtype=np.float64)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        f = ((ssered[:, None] - ssefull) / ksa) / (ssefull / n)
+        want = st.f.sf(f, ksa, n - (1 + r + ksa))
+    dev = "cuda"
+    minp = torch.empty(K, dtype=torch.float64, device=dev)
+    argk = torch.empty(K, dtype=torch.int32, device=dev)
+    r2 = torch.empty(K, dtype=torch.float64, device=dev)
+    _lib.perm_minp(torch.as_tensor(ssered, device=dev), torch.as_tensor(np.ascontiguousarray(ssefull), device=dev),
+                   torch.as_tensor(np.asarray(ks, dtype=np.int32), device=dev), n, r, minp, argk, r2)
+    got, ga = minp.cpu().numpy(), argk.cpu().numpy()
+    wmin = np.nanmin(want, axis=1)
+    np.testing.assert_allclose(got, wmin, rtol=1e-10, atol=1e-300)
+    # the chosen k agrees wherever the two smallest p-values are not within rounding of each other
+    srt = np.sort(want, axis=1)
+    clear = (len(ks) == 1) | (srt[:, min(1, len(ks) - 1)] > srt[:, 0] * (1 + 1e-9))
+    np.testing.assert_array_equal(ga[clear], np.nanargmin(want, axis=1)[clear])
+    rows = np.arange(K)
+    np.testing.assert_allclose(r2.cpu().numpy(), 1 - ssefull[rows, ga] / ssered, rtol=1e-14)
