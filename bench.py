@@ -46,6 +46,9 @@ CONFIGS = {
 METRIC = "cells/sec through nam()+association(), 1M cells/200 samples/10k perms"
 # CPU sample: same samples / k / steps, cells and permutations scaled down by the same factor
 CPU_SAMPLE_SCALE = 20
+# DRAM traffic of one SpMM launch at config C from the committed `ncu --set full` capture
+# (profiles/r01b_ncu_full_summary.txt: 2.600 GB read + 0.780 GB written; 31.6 GB before the reordering)
+SPMM_DRAM_TRAFFIC_GB = 3.380
 
 
 def parse_args():
@@ -336,7 +339,11 @@ def run_ours(args):
     if spmm:
         primary = {"kernel": "cna_diffuse_step_f32 (CSR SpMM diffusion step)", "bound": "hbm",
                    "achieved": spmm["achieved"], "peak": spmm["peak"], "unit": "GB/s", "frac": spmm["frac"],
-                   "traffic": None, "peak_source": peaks["source"] + " (MEASURED_PEAKS.json hbm_gbs)"}
+                   "traffic": SPMM_DRAM_TRAFFIC_GB if (args.config == "C" and world == 1) else None,
+                   "traffic_unit": "GB per launch (dram__bytes_read.sum + dram__bytes_write.sum, "
+                                   "profiles/r01b_ncu_full_summary.txt)",
+                   "algorithmic_gb": spmm["algorithmic_bytes"] / 1e9,
+                   "peak_source": peaks["source"] + " (MEASURED_PEAKS.json hbm_gbs)"}
     line = {
         "metric": METRIC, "value": N * args.steps / (ms * 1e-3), "unit": "cells/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,

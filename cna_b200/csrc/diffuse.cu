@@ -10,8 +10,6 @@
 // the (index, value) pairs of the row are read coalesced 32 at a time and broadcast with shuffles,
 // and four gathered source rows are kept in flight per lane.  Accumulation is in CSR order, the
 // order scipy's csr_matvecs uses.
-#include <stdlib.h>
-
 #include "common.cuh"
 
 namespace cna {
@@ -102,21 +100,17 @@ onehot_step_kernel(const int32_t *__restrict__ indptr, const int32_t *__restrict
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ float4 ldg4(const float4 *p) { return __ldg(p); }
 
-// A CTA owns `rows_per_cta` consecutive rows and its 8 warps sweep them 8 at a time, so that the rows
-// in flight on an SM are neighbours in the (locality-ordered) graph and share gathered rows in L1.
 template <int NV>
 __global__ void __launch_bounds__(256)
 spmm_f32_kernel(const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices,
                 const float *__restrict__ vals, const float *__restrict__ diag,
                 const float *__restrict__ in, float *__restrict__ out, int64_t n_rows, int nvec,
-                int64_t ld4, int64_t in_row_offset, int rows_per_cta) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+                int64_t ld4, int64_t in_row_offset) {
+    int64_t row = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (row >= n_rows) return;
     const float4 *in4 = reinterpret_cast<const float4 *>(in);
     float4 *out4 = reinterpret_cast<float4 *>(out);
-    const int64_t cta_row0 = int64_t(blockIdx.x) * rows_per_cta;
-  for (int sweep = 0; sweep < rows_per_cta; sweep += 8) {
-    const int64_t row = cta_row0 + sweep + warp;
-    if (row >= n_rows) return;
     int e0 = indptr[row], e1 = indptr[row + 1];
     float4 acc[NV];
 #pragma unroll
@@ -176,7 +170,6 @@ spmm_f32_kernel(const int32_t *__restrict__ indptr, const int32_t *__restrict__ 
             out4[row * ld4 + c] = acc[q];
         }
     }
-  }
 }
 
 // generic scalar kernel: any element type, any column count (public cna.tl.diffuse on user vectors)
@@ -303,14 +296,8 @@ int cna_diffuse_step_f32(const int32_t *indptr, const int32_t *indices, const fl
     int nvec = (n_cols + 3) / 4;
     if (vec_ok && nvec <= 128) {
         int64_t ld4 = ld / 4;
-        static const int rows_per_cta = [] {
-            const char *e = getenv("CNA_B200_SPMM_ROWS");
-            int v = e ? atoi(e) : 8;
-            return (v >= 8 && v % 8 == 0) ? v : 8;
-        }();
-        grid = unsigned((n_rows + rows_per_cta - 1) / rows_per_cta);
 #define CNA_SPMM(NV) \
-    spmm_f32_kernel<NV><<<grid, 256, 0, st>>>(indptr, indices, vals, diag, in, out, n_rows, nvec, ld4, in_row_offset, rows_per_cta)
+    spmm_f32_kernel<NV><<<grid, 256, 0, st>>>(indptr, indices, vals, diag, in, out, n_rows, nvec, ld4, in_row_offset)
         if (nvec <= 32) CNA_SPMM(1);
         else if (nvec <= 64) CNA_SPMM(2);
         else if (nvec <= 96) CNA_SPMM(3);
