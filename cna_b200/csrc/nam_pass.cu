@@ -95,7 +95,11 @@ batch_kurtosis_kernel(const float *__restrict__ s, int64_t ld, int64_t n_rows,
 // ---------------------------------------------------------------------------------------------
 // A warp owns R consecutive rows at a time: every W / C coefficient read from shared memory is used
 // for R rows, and the R independent shuffle reductions overlap each other's latency.
-template <int NQ, int R>
+// EXACT: NQ == ceil(n / 32), so only the last column group can run past n (the bounds checks of
+// the others fold away at compile time).  RT > 0: r <= RT and the loops over the r design columns
+// are fully unrolled (uniform `rr < r` guards); RT == 0: runtime loops.
+#define CNA_IN(q, m) ((EXACT && (q) < NQ - 1) || (m) < n)
+template <int NQ, int R, bool EXACT, int RT>
 __global__ void __launch_bounds__(256) resid_kernel(cna_resid_args a) {
     extern __shared__ double sm[];
     const int warps = blockDim.x >> 5;
@@ -144,7 +148,7 @@ __global__ void __launch_bounds__(256) resid_kernel(cna_resid_args a) {
 #pragma unroll
             for (int q = 0; q < NQ; ++q) {
                 int m = lane + 32 * q;
-                x[i][q] = (m < n) ? double(__ldg(p + colmap[m])) * invc[m] : 0.0;
+                x[i][q] = CNA_IN(q, m) ? double(__ldg(p + colmap[m])) * invc[m] : 0.0;
                 sum[i] += x[i][q];
             }
         }
@@ -156,7 +160,7 @@ __global__ void __launch_bounds__(256) resid_kernel(cna_resid_args a) {
 #pragma unroll
             for (int q = 0; q < NQ; ++q) {
                 int m = lane + 32 * q;
-                x[i][q] = (m < n) ? x[i][q] - sum[i] : 0.0;  // _nam.py:122
+                x[i][q] = CNA_IN(q, m) ? x[i][q] - sum[i] : 0.0;  // _nam.py:122
                 ss[i] += x[i][q] * x[i][q];
             }
         }
@@ -168,14 +172,14 @@ __global__ void __launch_bounds__(256) resid_kernel(cna_resid_args a) {
             valid[i] = keep && !(var0 == 0.0);  // _association.py:182-185
         }
         // rank-r update X <- X - (X Wt^T) C^T   (_nam.py:133-135 / :146-148 with M = I - C.W)
-        for (int rr = 0; rr < r; ++rr) {
+        auto project = [&](int rr) {
             double acc[R];
 #pragma unroll
             for (int i = 0; i < R; ++i) acc[i] = 0.0;
 #pragma unroll
             for (int q = 0; q < NQ; ++q) {
                 int m = lane + 32 * q;
-                double wv = (m < n) ? Wt[rr * n + m] : 0.0;
+                double wv = CNA_IN(q, m) ? Wt[rr * n + m] : 0.0;
 #pragma unroll
                 for (int i = 0; i < R; ++i) acc[i] += x[i][q] * wv;
             }
@@ -185,19 +189,33 @@ __global__ void __launch_bounds__(256) resid_kernel(cna_resid_args a) {
 #pragma unroll
                 for (int i = 0; i < R; ++i) pw[i * r + rr] = acc[i];
             }
-        }
-        __syncwarp();
-        for (int rr = 0; rr < r; ++rr) {
+        };
+        auto update = [&](int rr) {
             double pr[R];
 #pragma unroll
             for (int i = 0; i < R; ++i) pr[i] = pw[i * r + rr];
 #pragma unroll
             for (int q = 0; q < NQ; ++q) {
                 int m = lane + 32 * q;
-                double cv = (m < n) ? Ct[rr * n + m] : 0.0;
+                double cv = CNA_IN(q, m) ? Ct[rr * n + m] : 0.0;
 #pragma unroll
                 for (int i = 0; i < R; ++i) x[i][q] -= pr[i] * cv;
             }
+        };
+        if (RT > 0) {
+#pragma unroll
+            for (int rr = 0; rr < RT; ++rr)
+                if (rr < r) project(rr);
+        } else {
+            for (int rr = 0; rr < r; ++rr) project(rr);
+        }
+        __syncwarp();
+        if (RT > 0) {
+#pragma unroll
+            for (int rr = 0; rr < RT; ++rr)
+                if (rr < r) update(rr);
+        } else {
+            for (int rr = 0; rr < r; ++rr) update(rr);
         }
         __syncwarp();
         if (want_kurt) {  // _nam.py:150-155
@@ -212,7 +230,7 @@ __global__ void __launch_bounds__(256) resid_kernel(cna_resid_args a) {
 #pragma unroll
                 for (int q = 0; q < NQ; ++q) {
                     int m = lane + 32 * q;
-                    if (m < n) rb[m] = x[i][q];
+                    if (CNA_IN(q, m)) rb[m] = x[i][q];
                 }
                 __syncwarp();
                 double k = batch_kurtosis_of_row(rb, mb, seg_order, seg_off, nb, lane);
@@ -240,7 +258,7 @@ __global__ void __launch_bounds__(256) resid_kernel(cna_resid_args a) {
 #pragma unroll
             for (int q = 0; q < NQ; ++q) {
                 int m = lane + 32 * q;
-                double d = (m < n) ? x[i][q] - s1[i] : 0.0;
+                double d = CNA_IN(q, m) ? x[i][q] - s1[i] : 0.0;
                 s2[i] += d * d;
             }
         }
@@ -257,8 +275,8 @@ __global__ void __launch_bounds__(256) resid_kernel(cna_resid_args a) {
 #pragma unroll
             for (int q = 0; q < NQ; ++q) {
                 int m = lane + 32 * q;
-                double v = (m < n && valid[i]) ? x[i][q] * s2[i] : 0.0;  // rows of dropped cells are zero
-                if (m < n) dot[i] += v * ys[m];
+                double v = (CNA_IN(q, m) && valid[i]) ? x[i][q] * s2[i] : 0.0;  // rows of dropped cells are zero
+                if (CNA_IN(q, m)) dot[i] += v * ys[m];
                 if (o && m < a.ld_x) o[m] = float(v);
                 if (ph && m < a.ld16) {  // v = hi + lo to 2^-22
                     __half h = __float2half_rn(float(v));
@@ -332,17 +350,31 @@ int cna_resid_pass(const cna_resid_args *args, void *stream) {
     int64_t cap = int64_t(num_sms()) * 8;
     unsigned grid = unsigned(blocks_needed < cap ? blocks_needed : cap);
     cudaStream_t st = as_stream(stream);
-#define CNA_RESID(NQ, RR)                                                                              \
-    do {                                                                                               \
-        CNA_CUDA(cudaFuncSetAttribute(resid_kernel<NQ, RR>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                      int(smem)));                                                     \
-        resid_kernel<NQ, RR><<<grid, threads, smem, st>>>(a);                                          \
+#define CNA_RESID(NQ, RR, EX, RT)                                                                          \
+    do {                                                                                                   \
+        CNA_CUDA(cudaFuncSetAttribute(resid_kernel<NQ, RR, EX, RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                      int(smem)));                                                         \
+        resid_kernel<NQ, RR, EX, RT><<<grid, threads, smem, st>>>(a);                                      \
     } while (0)
-    if (nq <= 2) CNA_RESID(2, 4);
-    else if (nq <= 4) CNA_RESID(4, 4);
-    else if (nq <= 8) CNA_RESID(8, 4);
-    else if (nq <= 16) CNA_RESID(16, 2);
-    else CNA_RESID(32, 1);
+#define CNA_RESID_EXACT(NQ)                 \
+    do {                                    \
+        if (a.r <= 8) CNA_RESID(NQ, 4, true, 8); \
+        else CNA_RESID(NQ, 4, true, 0);     \
+    } while (0)
+    switch (nq <= 8 ? nq : 0) {
+        case 1: CNA_RESID_EXACT(1); break;
+        case 2: CNA_RESID_EXACT(2); break;
+        case 3: CNA_RESID_EXACT(3); break;
+        case 4: CNA_RESID_EXACT(4); break;
+        case 5: CNA_RESID_EXACT(5); break;
+        case 6: CNA_RESID_EXACT(6); break;
+        case 7: CNA_RESID_EXACT(7); break;
+        case 8: CNA_RESID_EXACT(8); break;
+        default:
+            if (nq <= 16) CNA_RESID(16, 2, false, 0);
+            else CNA_RESID(32, 1, false, 0);
+    }
+#undef CNA_RESID_EXACT
 #undef CNA_RESID
     CNA_LAUNCHED("resid_kernel");
     return CNA_OK;
