@@ -100,7 +100,7 @@ static inline int default_threads() {
     // NAM, i.e. before the caller needs its cores for the n x n SVD
     unsigned hw = std::thread::hardware_concurrency();
     int t = hw > 2 ? int(hw) - 1 : 1;
-    return t > 32 ? 32 : t;
+    return t > 64 ? 64 : t;
 }
 
 template <typename F>

@@ -4,7 +4,7 @@ import os
 import threading
 import time
 
-ENABLED = bool(os.environ.get("CNA_B200_TIMING"))
+ENABLED = bool(os.environ.get("CNA_B200_TIMING")) and os.environ.get("RANK", "0") == "0"
 _marks = []
 _lock = threading.Lock()
 
