@@ -87,6 +87,16 @@ def default_ks(n):
 
 
 _POOL = None
+_HELPER = None
+
+
+def _helper_pool():
+    global _HELPER
+    if _HELPER is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _HELPER = ThreadPoolExecutor(max_workers=1, thread_name_prefix="cna-svd")
+    return _HELPER
+
 
 
 def _f_sf(f, dfn, dfd):
@@ -149,12 +159,10 @@ def _association(res, perms, Nnull=1000, local_test=True, show_progress=False):
             comm.all_reduce(mx, op="max")
     Gh = G_d.cpu().numpy()
     mark("gram on host")
-    # The n x n SVD needs only the Gram; the null kernels need only the permutations.  Whichever
-    # input is ready first goes first: if the draws are still running the SVD fills the wait,
-    # otherwise the null kernels are launched first and the SVD overlaps them.
-    svd = None
-    if perms is not None and not perms.done():
-        svd = _nam.svd_of_gram(Gh, top=res.svd_top)  # _nam.py:105
+    # The n x n SVD needs only the Gram and the null kernels only the permutations: the SVD runs on a
+    # helper thread (LAPACK releases the GIL) while this thread waits for the draws and launches the
+    # null kernels, whichever of the two inputs is ready first.
+    svd_future = _helper_pool().submit(_nam.svd_of_gram, Gh, res.svd_top)  # _nam.py:105
 
     # ---- permutations: indices from the host RNG (bit-exact), everything else on the device ----
     if perms is not None:
@@ -191,12 +199,6 @@ def _association(res, perms, Nnull=1000, local_test=True, show_progress=False):
             return (sse_d[0].cpu().numpy(), sse_d[1].cpu().numpy(), None)
         return (sse_d[0], sse_d[1], (sse_d[2][0].cpu().numpy(), sse_d[2][1].cpu().numpy()))
 
-    # With U already known the (tiny) PC-regression kernels go first and their results come back
-    # before the null GEMM starts; otherwise the null GEMM is launched first and overlaps the SVD.
-    sse_host = None
-    if svd is not None:
-        sse_host = fetch(launch_pc_regressions(svd[0]))
-
     # ---- neighbourhood-level null (:92-103) ----
     fdrs, fdr_5p_t, fdr_10p_t = None, None, None
     if local_test:
@@ -219,7 +221,7 @@ def _association(res, perms, Nnull=1000, local_test=True, show_progress=False):
             comm.all_reduce(obs)
     mark("null kernels launched")
 
-    U, svs, res.G = svd if svd is not None else _nam.svd_of_gram(Gh, top=res.svd_top)  # _nam.py:105
+    U, svs, res.G = svd_future.result()
     res.U, res.svs = U, svs
 
     # ---- observed phenotype (:64-74): n-sized host arithmetic in float64 -----------------
@@ -237,8 +239,7 @@ def _association(res, perms, Nnull=1000, local_test=True, show_progress=False):
     r2_perpc = (beta / np.sqrt(ycond.dot(ycond))) ** 2  # :74
 
     # ---- the global p-value (:84-88) ----
-    if sse_host is None:
-        sse_host = fetch(launch_pc_regressions(U))
+    sse_host = fetch(launch_pc_regressions(U))
     if sse_host[2] is None:
         nullp, nullr2 = _f_pvalues(sse_host[0], sse_host[1], ks, n, r)
         _, nullminps, nullr2s = _pick(nullp, nullr2, ks)

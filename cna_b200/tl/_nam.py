@@ -301,26 +301,46 @@ def gram_device(x, n, comm=None, planes=None):
     return G
 
 
+_BLAS = None
+
+
+def _single_threaded_blas():
+    """Context manager pinning the BLAS/LAPACK thread pool to one thread.  The n x n decomposition is
+    a few ms of work on one core; with OpenBLAS's default (one spinning thread per core) it collapses
+    to 10x that when the permutation draw is using the same cores."""
+    global _BLAS
+    try:
+        if _BLAS is None:
+            from threadpoolctl import ThreadpoolController
+            _BLAS = ThreadpoolController()
+        return _BLAS.limit(limits=1, user_api="blas")
+    except Exception:  # threadpoolctl missing: run with whatever the BLAS does by default
+        import contextlib
+        return contextlib.nullcontext()
+
+
 def svd_of_gram(Gh, top=None):
     """``_nam.py:105``: U, svs, _ = np.linalg.svd(Gram) on the host (n x n).
 
     ``top`` = number of leading components the caller will actually read.  The association test
     uses U[:, :max(ks)] only (as the projector U_k U_k^T, so the sign of a column is irrelevant) and
     never the trailing ~85 % of the decomposition, so unless the full result surface is requested
-    the leading eigenpairs of the symmetric PSD Gram are computed with LAPACK's dsyevr instead of a
-    full dgesdd: same subspaces and singular values to ~1e-15, a quarter of the time.  The returned
-    arrays keep the full shapes (trailing columns / values are zero and must not be read)."""
+    the symmetric PSD Gram is eigen-decomposed (numpy's LAPACK dsyevd, which — unlike scipy's f2py
+    wrappers — releases the GIL, so it can run beside the thread that launches the null kernels)
+    instead of a full dgesdd: same subspaces and singular values to ~1e-15 in less than half the
+    time.  The returned arrays keep the full shapes (trailing columns / values are zero and must not
+    be read)."""
     Gh = (Gh + Gh.T) / 2  # both triangles hold the same products up to summation order; keep it exact
     n = Gh.shape[0]
-    if top is None or top >= n:
-        U, svs, _ = np.linalg.svd(Gh)
-    else:
-        import scipy.linalg
-        w, v = scipy.linalg.eigh(Gh, subset_by_index=[n - top, n - 1], driver="evr")
-        U = np.zeros((n, n))
-        svs = np.zeros(n)
-        U[:, :top] = v[:, ::-1]
-        svs[:top] = np.maximum(w[::-1], 0.0)
+    with _single_threaded_blas():
+        if top is None or top >= n:
+            U, svs, _ = np.linalg.svd(Gh)
+        else:
+            w, v = np.linalg.eigh(Gh)  # ascending
+            U = np.zeros((n, n))
+            svs = np.zeros(n)
+            U[:, :top] = v[:, ::-1][:, :top]
+            svs[:top] = np.maximum(w[::-1][:top], 0.0)
     mark("svd done")
     return U, svs, Gh
 
