@@ -474,3 +474,51 @@ def test_device_f_survival_matches_scipy(cna, n, r, ks):
     np.testing.assert_array_equal(ga[clear], np.nanargmin(want, axis=1)[clear])
     rows = np.arange(K)
     np.testing.assert_allclose(r2.cpu().numpy(), 1 - ssefull[rows, ga] / ssered, rtol=1e-14)
+
+
+@pytest.mark.parametrize("N,S,k,nsteps", [(30_000, 500, 15, 3), (40_000, 64, 10, None)])
+def test_end_to_end_vs_oracle_at_other_shapes(cna, N, S, k, nsteps):
+    """Whole association() against the oracle on seeded synthetic data at shapes the golden fixtures
+    do not cover: 500 samples (config E's sample count: n > 256 takes the CUDA-core Gram, the
+    null GEMM runs 32 k-steps, 16 column groups in the row pass) and the kurtosis auto-stop rule
+    (nsteps=None) on a graph large enough to be stored in the reordered cell order."""
+    import warnings
+    from cna_b200 import synth
+    from oracle import cna_oracle as orc
+    data, meta = synth.make_dataset(N, S, k, seed=3, dim=8)
+    kw = dict(y=meta.case, sid_name="id", batches=meta.batch, covs=meta[["age"]], nsteps=nsteps, Nnull=300, seed=4)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        d_cpu = type(data)(data.obs.copy(), data.obsp["connectivities"])
+        want = orc.association(d_cpu, return_full=True, **kw)
+        import os
+        old = os.environ.get("CNA_B200_REORDER")
+        os.environ["CNA_B200_REORDER"] = "1"
+        try:
+            d_gpu = type(data)(data.obs.copy(), data.obsp["connectivities"])
+            got = cna.tl.association(d_gpu, return_full=True, **kw)
+            d_gpu2 = type(data)(data.obs.copy(), data.obsp["connectivities"])
+            p_fast = cna.tl.association(d_gpu2, **kw)  # device F survival + leading eigenpairs only
+        finally:
+            if old is None:
+                os.environ.pop("CNA_B200_REORDER", None)
+            else:
+                os.environ["CNA_B200_REORDER"] = old
+    assert got.p == want.p == p_fast
+    assert int(got.k) == int(want.k) and list(got.ks) == list(want.ks) and got.r == want.r
+    np.testing.assert_array_equal(got.kept, want.kept)
+    np.testing.assert_allclose(got.ncorrs.to_numpy(), want.ncorrs.to_numpy(), rtol=RTOL, atol=1e-6)
+    npc = min(len(got.namresid_svs), 10)
+    np.testing.assert_allclose(got.namresid_svs.to_numpy()[:npc], want.namresid_svs.to_numpy()[:npc], rtol=RTOL)
+    np.testing.assert_allclose(got.nullminps, want.nullminps, rtol=1e-4, atol=1e-12)
+    np.testing.assert_allclose(got.r2, want.r2, rtol=RTOL)
+    a, b = d_gpu.obs["coef_fdr"].to_numpy(), d_cpu.obs["coef_fdr"].to_numpy()
+    c = d_gpu2.obs["coef_fdr"].to_numpy()
+    np.testing.assert_array_equal(a, c)
+    np.testing.assert_array_equal(d_gpu.obs["coef"].to_numpy(), d_gpu2.obs["coef"].to_numpy())
+    # FDR-passing sets agree except for cells whose |coefficient| is within rounding of the threshold
+    for level, thr in ((0.05, want.fdr_5p_t), (0.1, want.fdr_10p_t)):
+        if thr is None:
+            continue
+        edge = np.abs(np.abs(np.nan_to_num(d_cpu.obs["coef"].to_numpy())) - thr) < 1e-5 * max(thr, 1e-3)
+        assert ((a <= level) == (b <= level))[~edge].all()

@@ -249,3 +249,23 @@ def test_leading_eigenpairs_match_full_svd():
         np.testing.assert_allclose(Ut[:, :k] @ Ut[:, :k].T, U[:, :k] @ U[:, :k].T, atol=1e-10)
     Uf, sf, _ = svd_of_gram(G)
     np.testing.assert_array_equal(sf, svs)
+
+
+def test_obs_to_sample_matches_reference_semantics():
+    """cna.ut.obs_to_sample (utils/multisample.py:4-11): groupby-aggregate, index = ids in order of
+    first appearance; against the reference itself when it is mounted."""
+    import cna_b200 as cna
+    from tests.golden import cases
+    d = cases.demo_anndata()
+    got = cna.ut.obs_to_sample(d, ["case", "male", "batch"], "id")
+    assert list(got.index) == list(d.obs["id"].unique()) and list(got.columns) == ["case", "male", "batch"]
+    np.testing.assert_array_equal(got["case"].to_numpy(), d.obs.groupby("id")["case"].mean().reindex(got.index).to_numpy())
+    one = cna.ut.obs_to_sample(d, "batch", "id", aggregate="max")
+    assert list(one.columns) == ["batch"]
+    ref_dir = "/root/reference/src/cna/utils"
+    if os.path.isdir(ref_dir):
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("_ref_multisample", os.path.join(ref_dir, "multisample.py"))
+        ref = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(ref)
+        pd.testing.assert_frame_equal(got, ref.obs_to_sample(d, ["case", "male", "batch"], "id"))
