@@ -487,6 +487,15 @@ class HostPermJob:
         self.result()
         return self.out_t
 
+    def __del__(self):
+        # the library thread writes into buffers owned by this object: never let them be freed
+        # (an exception unwinding the caller, interpreter shutdown) before it has finished
+        try:
+            if getattr(self, "handle", None) is not None:
+                self.result()
+        except Exception:
+            pass
+
 
 def knn_bruteforce(points, k):
     """points: [n, dim] float32 CUDA tensor.  Returns (idx int64 [n, k], dist2 float32 [n, k])."""

@@ -414,6 +414,9 @@ def resid_nam_device(st, colmap, covs, batches, y_std, ridges=None, show_progres
     C, nb = design_matrix(covs, batches, n)
     r = C.shape[1]
     ld = _round_up(n, 8)
+    # the fp32 matrix is only needed for the full result surface and for the CUDA-core Gram that
+    # takes over beyond the tensor-core kernel's 256-sample limit
+    want_x = want_x or n > TC_GRAM_MAX_N
     x = torch.empty((st.N, ld), dtype=torch.float32, device=dev) if want_x else None
     planes = _lib.Planes(st.N, n, dev)
     ncorr = torch.empty(st.N, dtype=torch.float64, device=dev)

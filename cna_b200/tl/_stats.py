@@ -112,11 +112,8 @@ def conditional_permutation_matrix(B, num):
     the scatter running on all host threads.  Advances ``np.random``'s global state exactly like
     the reference's calls."""
     from .. import _lib
-    B = np.asarray(B)
-    batchind = [np.where(B == b)[0] for b in np.unique(B)]
-    off = np.zeros(len(batchind) + 1, dtype=np.int32)
-    np.cumsum([len(bi) for bi in batchind], out=off[1:])
-    return _lib.host_perm_blocks(off, np.concatenate(batchind), num)
+    off, pos = _batch_blocks(B)
+    return _lib.host_perm_blocks(off, pos, num)
 
 
 def grouplevel_permutation_matrix(G, Y, num):
