@@ -373,7 +373,7 @@ def gram_tc(xp, n, out):
     """out[n x n] (fp64) += X^T X on the tensor cores; xp = Planes of X."""
     need = int(load().cna_gram_tc_workspace(int(n)))
     if need < 0:
-        raise CnaError(f"cna_gram_tc: n={n} not supported (n <= 256)")
+        raise CnaError(f"cna_gram_tc: n={n} not supported (n <= 512)")
     key = (xp.t.device, need)
     ws = _GRAM_WS.get(key)
     if ws is None:

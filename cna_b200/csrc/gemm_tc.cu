@@ -417,38 +417,54 @@ xb_tc_kernel(const __grid_constant__ CUtensorMap tm_ah, const __grid_constant__ 
 // ---------------------------------------------------------------------------------------------
 // Gram: G += X^T X, contraction over cells
 // ---------------------------------------------------------------------------------------------
-// Output tiles: m-tile 0 = samples [0,128) x all n16 columns; m-tile 1 = samples [128,256) x columns
-// [128, n16) only (the block below the diagonal is the transpose of what m-tile 0 already holds).
-// TMEM columns: [0, n16) for m-tile 0, [n16, n16 + n1) for m-tile 1.
+// Output tiles: m-tile t = samples [128t, 128t+128) x columns [128t, n16) (the blocks below the
+// diagonal are transposes of blocks above it).  TMEM has 512 fp32 columns per SM, so the CTAs are
+// split into groups; a group owns consecutive m-tiles whose widths sum to <= 512 columns
+// (n <= 256: one group {0,1}, every CTA reads X once; n = 500: groups {0}, {1}, {2,3}) and a share
+// of the CTAs proportional to its MMA work, and streams only the 64-sample boxes its tiles touch.
 //
 // fp32 accumulation in TMEM truncates (measured: -3.2e-8 relative per accumulation step on an
 // all-positive sum), so the accumulators are flushed into fp64 every kGChunkStages * 32 = 256 cells
 // (48 steps, bias ~1.5e-6 on the diagonal, inside the 1e-5 budget with margin).
 constexpr int kGK = 32;                       // cells per stage (two k-steps)
 constexpr int kGBoxBytes = kGK * 128;         // 64 samples x 32 cells of fp16
-constexpr int kGMaxBoxes = 4;                 // up to 256 samples
-constexpr int kGStages = 6;
+constexpr int kGRingBytes = 192 * 1024;       // operand ring: 6 stages of 4 boxes ... 3 stages of 8
+constexpr int kGMaxStages = 6;
 constexpr int kGChunkStages = 8;
 constexpr int kGEpiWarps = 16;
 constexpr int kGThreads = 64 + kGEpiWarps * 32;
+constexpr int kGMaxGroups = 4;
+
+struct GramGroup {
+    int mt0, n_mt;      // m-tiles [mt0, mt0 + n_mt)
+    int box0, n_boxes;  // 64-sample boxes [box0, box0 + n_boxes) streamed by this group
+    int width;          // TMEM / scratch columns: sum over its tiles of (n16 - 128 t)
+    int cta0, n_ctas;   // CTAs [cta0, cta0 + n_ctas)
+    int64_t scratch_off;  // doubles
+};
 
 struct GramTcArgs {
     int64_t n_rows;
-    int n16;        // samples rounded up to 16 (UMMA N of m-tile 0)
-    int n1;         // columns of m-tile 1: n16 - 128, or 0
-    int n_boxes;    // ceil(n16 / 64)
-    double *scratch;  // [gridDim.x][n16 + n1][128]
+    int n16;        // samples rounded up to 16
+    int n_groups;
+    GramGroup g[kGMaxGroups];
+    double *scratch;  // per CTA: [width of its group][128]
 };
 
 __global__ void __launch_bounds__(kGThreads, 1)
 gram_tc_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ CUtensorMap tm_l, GramTcArgs a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const int plane_bytes = a.n_boxes * kGBoxBytes;
+    int gi = 0;
+    while (gi + 1 < a.n_groups && int(blockIdx.x) >= a.g[gi + 1].cta0) ++gi;
+    const GramGroup grp = a.g[gi];
+    const int local = int(blockIdx.x) - grp.cta0;  // this CTA takes chunks local, local + n_ctas, ...
+    const int plane_bytes = grp.n_boxes * kGBoxBytes;
     const int stage_bytes = 2 * plane_bytes;
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem + kGStages * 2 * kGMaxBoxes * kGBoxBytes);
-    uint64_t *empty = full + kGStages;
-    uint64_t *tfull = empty + kGStages;
+    const int n_stages_ring = min(kGMaxStages, kGRingBytes / stage_bytes);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + kGRingBytes);
+    uint64_t *empty = full + kGMaxStages;
+    uint64_t *tfull = empty + kGMaxStages;
     uint64_t *tempty = tfull + 1;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 1);
 
@@ -457,7 +473,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__
     const int64_t n_chunks = (n_stages_total + kGChunkStages - 1) / kGChunkStages;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kGStages; ++s) {
+        for (int s = 0; s < kGMaxStages; ++s) {
             mbar_init(full + s, 1);
             mbar_init(empty + s, 1);
         }
@@ -477,18 +493,19 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__
         if (lane == 0) {  // ---- TMA producer ----
             int stage = 0;
             uint32_t phase = 0;
-            for (int64_t ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
+            for (int64_t ch = local; ch < n_chunks; ch += grp.n_ctas) {
                 int64_t s0 = ch * kGChunkStages, s1 = s0 + kGChunkStages;
                 if (s1 > n_stages_total) s1 = n_stages_total;
                 for (int64_t s = s0; s < s1; ++s) {
                     mbar_wait(empty + stage, phase ^ 1);
                     uint8_t *st = smem + stage * stage_bytes;
                     mbar_expect_tx(full + stage, uint32_t(stage_bytes));
-                    for (int b = 0; b < a.n_boxes; ++b) {
-                        tma_load_2d(st + b * kGBoxBytes, &tm_h, b * 64, int(s * kGK), full + stage);
-                        tma_load_2d(st + plane_bytes + b * kGBoxBytes, &tm_l, b * 64, int(s * kGK), full + stage);
+                    for (int b = 0; b < grp.n_boxes; ++b) {
+                        const int c0 = (grp.box0 + b) * 64;
+                        tma_load_2d(st + b * kGBoxBytes, &tm_h, c0, int(s * kGK), full + stage);
+                        tma_load_2d(st + plane_bytes + b * kGBoxBytes, &tm_l, c0, int(s * kGK), full + stage);
                     }
-                    if (++stage == kGStages) {
+                    if (++stage == n_stages_ring) {
                         stage = 0;
                         phase ^= 1;
                     }
@@ -497,11 +514,9 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__
         }
     } else if (warp == 1) {
         if (lane == 0) {  // ---- MMA issuer ----
-            const uint32_t idesc0 = instr_desc_f16(128, a.n16, 1, 1);
-            const uint32_t idesc1 = instr_desc_f16(128, a.n1 > 0 ? a.n1 : 16, 1, 1);
             int stage = 0;
             uint32_t phase = 0, acc_phase = 0;
-            for (int64_t ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
+            for (int64_t ch = local; ch < n_chunks; ch += grp.n_ctas) {
                 int64_t s0 = ch * kGChunkStages, s1 = s0 + kGChunkStages;
                 if (s1 > n_stages_total) s1 = n_stages_total;
                 mbar_wait(tempty, acc_phase ^ 1);
@@ -516,25 +531,30 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__
                         // groups 1024 B (SBO) apart; a k-step of 16 cells is 2048 B
                         const uint32_t koff = ks * 2048;
                         const uint32_t first = (s == s0 && ks == 0) ? 0u : 1u;
-                        {  // m-tile 0: samples [0,128) x [0,n16)
-                            const uint64_t ah = smem_desc(sh + koff, kGBoxBytes, 1024, kSw128);
-                            const uint64_t al = smem_desc(sl + koff, kGBoxBytes, 1024, kSw128);
-                            umma_f16(tmem_base, al, ah, idesc0, first);  // small terms first
-                            umma_f16(tmem_base, ah, al, idesc0, 1);
-                            umma_f16(tmem_base, ah, ah, idesc0, 1);
-                        }
-                        if (a.n1 > 0) {  // m-tile 1: samples [128,256) x [128,n16)
-                            const uint32_t moff = 2 * kGBoxBytes;
-                            const uint64_t ah = smem_desc(sh + moff + koff, kGBoxBytes, 1024, kSw128);
-                            const uint64_t al = smem_desc(sl + moff + koff, kGBoxBytes, 1024, kSw128);
-                            const uint32_t d = tmem_base + uint32_t(a.n16);
-                            umma_f16(d, al, ah, idesc1, first);
-                            umma_f16(d, ah, al, idesc1, 1);
-                            umma_f16(d, ah, ah, idesc1, 1);
+                        uint32_t col = 0;  // TMEM column of the current tile
+                        for (int t = 0; t < grp.n_mt; ++t) {
+                            const int mt = grp.mt0 + t, width = a.n16 - 128 * mt;
+                            const uint32_t aoff = uint32_t(2 * mt - grp.box0) * kGBoxBytes;
+                            const uint64_t ah = smem_desc(sh + aoff + koff, kGBoxBytes, 1024, kSw128);
+                            const uint64_t al = smem_desc(sl + aoff + koff, kGBoxBytes, 1024, kSw128);
+                            // B = columns [128 mt, n16): the same boxes as A onwards, at most 256
+                            // columns (4 boxes) per instruction
+                            for (int c0 = 0; c0 < width; c0 += 256) {
+                                const int nn = min(256, width - c0);
+                                const uint32_t boff = aoff + uint32_t(c0 / 64) * kGBoxBytes;
+                                const uint64_t bh = smem_desc(sh + boff + koff, kGBoxBytes, 1024, kSw128);
+                                const uint64_t bl = smem_desc(sl + boff + koff, kGBoxBytes, 1024, kSw128);
+                                const uint32_t idesc = instr_desc_f16(128, nn, 1, 1);
+                                const uint32_t d = tmem_base + col + uint32_t(c0);
+                                umma_f16(d, al, bh, idesc, first);  // small terms first
+                                umma_f16(d, ah, bl, idesc, 1);
+                                umma_f16(d, ah, bh, idesc, 1);
+                            }
+                            col += uint32_t(width);
                         }
                     }
                     umma_commit(empty + stage);
-                    if (++stage == kGStages) {
+                    if (++stage == n_stages_ring) {
                         stage = 0;
                         phase ^= 1;
                     }
@@ -545,14 +565,14 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__
         }
     } else {  // ---- epilogue: 16 warps; lane quarter = warp % 4, column groups dealt round-robin ----
         const int q = warp & 3, part = (warp - 2) >> 2;
-        const int n_groups = (a.n16 + a.n1) / 16;
-        double *mine = a.scratch + int64_t(blockIdx.x) * (a.n16 + a.n1) * 128;
+        const int n_colgroups = grp.width / 16;
+        double *mine = a.scratch + grp.scratch_off + int64_t(local) * grp.width * 128;
         uint32_t acc_phase = 0;
         bool first = true;
-        for (int64_t ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
+        for (int64_t ch = local; ch < n_chunks; ch += grp.n_ctas) {
             mbar_wait(tfull, acc_phase);
             tc_fence_after();
-            for (int g = part; g < n_groups; g += kGEpiWarps / 4) {
+            for (int g = part; g < n_colgroups; g += kGEpiWarps / 4) {
                 uint32_t r[16];
                 tmem_ld16(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(g * 16), r);
                 double *p = mine + int64_t(g * 16) * 128 + q * 32 + lane;
@@ -581,21 +601,71 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__
     if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
-// G[i][j] += sum over CTAs of their partial (fixed order: deterministic).  Entries below the
-// diagonal block are read from their mirror image.
-__global__ void gram_reduce_kernel(const double *__restrict__ scratch, int n_ctas, int n16, int n1, int n,
-                                   double *__restrict__ gram) {
+// G[i][j] += sum over the CTAs of the owning group of their partial (fixed order: deterministic).
+// Entries below the diagonal blocks are read from their mirror image.
+__global__ void gram_reduce_kernel(GramTcArgs a, int64_t n_chunks, int n, double *__restrict__ gram) {
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n * n) return;
     int i = idx / n, j = idx - i * n;
-    int64_t off;
-    if (i < 128) off = int64_t(j) * 128 + i;
-    else if (j >= 128) off = int64_t(n16 + (j - 128)) * 128 + (i - 128);
-    else off = int64_t(i) * 128 + j;  // mirror: entry (j, i) of m-tile 0
-    int64_t per_cta = int64_t(n16 + n1) * 128;
+    if (j < (i & ~127)) {  // below the diagonal block of row i: mirror
+        int t = i;
+        i = j;
+        j = t;
+    }
+    const int mt = i >> 7;
+    int gi = 0;
+    while (gi + 1 < a.n_groups && mt >= a.g[gi + 1].mt0) ++gi;
+    const GramGroup grp = a.g[gi];
+    int col = j - 128 * mt;  // column inside tile mt, then inside the group
+    for (int t = grp.mt0; t < mt; ++t) col += a.n16 - 128 * t;
+    const int64_t per_cta = int64_t(grp.width) * 128;
+    const double *base = a.scratch + grp.scratch_off + int64_t(col) * 128 + (i & 127);
+    const int live = int(n_chunks < grp.n_ctas ? n_chunks : grp.n_ctas);  // CTAs that got a chunk
     double acc = 0.0;
-    for (int b = 0; b < n_ctas; ++b) acc += scratch[b * per_cta + off];
+    for (int b = 0; b < live; ++b) acc += base[b * per_cta];
     gram[idx] += acc;
+}
+
+// Groups of consecutive m-tiles (greedy, <= 512 TMEM columns each) and their CTA shares.
+static int gram_plan(int n, int n_ctas, GramTcArgs &a) {
+    a.n16 = (n + 15) / 16 * 16;
+    const int n_mt = (a.n16 + 127) / 128, n_boxes = (a.n16 + 63) / 64;
+    a.n_groups = 0;
+    int mt = 0;
+    double total_work = 0.0, work[kGMaxGroups];
+    while (mt < n_mt) {
+        if (a.n_groups == kGMaxGroups) return -1;
+        GramGroup &g = a.g[a.n_groups];
+        g.mt0 = mt;
+        g.n_mt = 0;
+        g.width = 0;
+        while (mt < n_mt && g.width + (a.n16 - 128 * mt) <= 512) {
+            g.width += a.n16 - 128 * mt;
+            ++g.n_mt;
+            ++mt;
+        }
+        if (g.n_mt == 0) return -1;
+        g.box0 = 2 * g.mt0;
+        g.n_boxes = n_boxes - g.box0;
+        work[a.n_groups] = double(g.width);
+        total_work += work[a.n_groups];
+        ++a.n_groups;
+    }
+    if (n_ctas < a.n_groups) return -1;
+    int assigned = 0;
+    int64_t off = 0;
+    for (int k = 0; k < a.n_groups; ++k) {
+        GramGroup &g = a.g[k];
+        int share = (k + 1 == a.n_groups) ? n_ctas - assigned : int(n_ctas * work[k] / total_work + 0.5);
+        if (share < 1) share = 1;
+        if (share > n_ctas - assigned - (a.n_groups - 1 - k)) share = n_ctas - assigned - (a.n_groups - 1 - k);
+        g.cta0 = assigned;
+        g.n_ctas = share;
+        g.scratch_off = off;
+        assigned += share;
+        off += int64_t(share) * g.width * 128;
+    }
+    return 0;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -715,15 +785,16 @@ int cna_null_hist_tc(const void *xh, const void *xl, int64_t ld16, int64_t n_row
 }
 
 int64_t cna_gram_tc_workspace(int n) {
-    if (n <= 0 || n > 256) return -1;
-    int n16 = (n + 15) / 16 * 16;
-    int n1 = n16 > 128 ? n16 - 128 : 0;
-    return int64_t(num_sms()) * (n16 + n1) * 128 * int64_t(sizeof(double));
+    if (n <= 0 || n > 512) return -1;
+    GramTcArgs a{};
+    if (gram_plan(n, num_sms(), a) != 0) return -1;
+    const GramGroup &last = a.g[a.n_groups - 1];
+    return (last.scratch_off + int64_t(last.n_ctas) * last.width * 128) * int64_t(sizeof(double));
 }
 
 int cna_gram_tc(const void *xh, const void *xl, int64_t ld16, int64_t n_rows, int n, double *gram, void *workspace,
                 int64_t workspace_bytes, void *stream) {
-    CNA_REQUIRE(n > 0 && n <= 256, "cna_gram_tc: 1..256 samples supported (got %d)", n);
+    CNA_REQUIRE(n > 0 && n <= 512, "cna_gram_tc: 1..512 samples supported (got %d)", n);
     CNA_REQUIRE(n_rows >= 0 && n_rows < (int64_t(1) << 31) && ld16 % 8 == 0 && ld16 >= n, "cna_gram_tc: bad shape");
     CNA_REQUIRE(workspace && workspace_bytes >= cna_gram_tc_workspace(n), "cna_gram_tc: workspace too small");
     CNA_REQUIRE(((reinterpret_cast<uintptr_t>(xh) | reinterpret_cast<uintptr_t>(xl)) & 15) == 0,
@@ -731,10 +802,8 @@ int cna_gram_tc(const void *xh, const void *xl, int64_t ld16, int64_t n_rows, in
     if (n_rows == 0) return CNA_OK;
     cudaStream_t st = as_stream(stream);
     GramTcArgs a{};
+    CNA_REQUIRE(gram_plan(n, num_sms(), a) == 0, "cna_gram_tc: no tile plan for n=%d", n);
     a.n_rows = n_rows;
-    a.n16 = (n + 15) / 16 * 16;
-    a.n_boxes = (a.n16 + 63) / 64;
-    a.n1 = a.n16 > 128 ? a.n16 - 128 : 0;
     a.scratch = static_cast<double *>(workspace);
     CUtensorMap tm_h, tm_l;
     int rc;
@@ -742,13 +811,13 @@ int cna_gram_tc(const void *xh, const void *xl, int64_t ld16, int64_t n_rows, in
     if ((rc = make_map(&tm_l, xl, n, n_rows, ld16, 64, kGK, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
     int64_t stages = (n_rows + kGK - 1) / kGK;
     int64_t chunks = (stages + kGChunkStages - 1) / kGChunkStages;
-    unsigned grid = unsigned(chunks < num_sms() ? chunks : num_sms());
-    size_t smem = size_t(kGStages) * 2 * kGMaxBoxes * kGBoxBytes + 1024 + 256;
+    unsigned grid = unsigned(num_sms());  // every group keeps its CTA range; CTAs without a chunk idle
+    size_t smem = size_t(kGRingBytes) + 1024 + 256;
     CNA_CUDA(cudaFuncSetAttribute(gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     gram_tc_kernel<<<grid, kGThreads, smem, st>>>(tm_h, tm_l, a);
     CNA_LAUNCHED("gram_tc_kernel");
     int nn = n * n;
-    gram_reduce_kernel<<<(nn + 255) / 256, 256, 0, st>>>(a.scratch, int(grid), a.n16, a.n1, n, gram);
+    gram_reduce_kernel<<<(nn + 255) / 256, 256, 0, st>>>(a, chunks, n, gram);
     CNA_LAUNCHED("gram_reduce_kernel");
     return CNA_OK;
 }

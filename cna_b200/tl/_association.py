@@ -65,15 +65,16 @@ def check_inputs(data, y, sid_name, batches, covs, donorids, allow_low_sample_si
 _PINNED = {}
 
 
-def _to_host_pinned(t):
+def _to_host_pinned(t, slot="results"):
     """Device tensor -> numpy array through a cached page-locked staging buffer (a pageable D2H of
     the two per-cell float64 columns costs more than the kernels that produced them).  The returned
-    array is a view of the staging buffer: consume it before the next call."""
+    array is a view of the staging buffer of that ``slot``: consume it before the next call."""
     key = (t.dtype, tuple(t.shape))
-    buf = _PINNED.get(key)
+    held = _PINNED.get(slot)
+    buf = held[1] if held is not None and held[0] == key else None
     if buf is None:
-        _PINNED.clear()
-        buf = _PINNED[key] = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        buf = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        _PINNED[slot] = (key, buf)
     buf.copy_(t, non_blocking=True)
     torch.cuda.current_stream().synchronize()
     return buf.numpy()
@@ -132,7 +133,7 @@ def _pick(p, r2, ks):
     return np.asarray(ks)[pick], p[rows, pick], r2[rows, pick]
 
 
-def _association(res, perms, Nnull=1000, local_test=True, show_progress=False):
+def _association(res, perms, Nnull=1000, local_test=True, show_progress=False, idle_work=None):
     """``_nam.py:163`` (Gram + SVD of the residualised NAM) and ``_association.py:10-129`` after
     seeding / permutation drawing (done by the caller so that they overlap with the NAM kernels).
     ``res`` carries the device-resident residualised NAM (``res.planes`` / ``res.x``), M, r, the
@@ -221,6 +222,8 @@ def _association(res, perms, Nnull=1000, local_test=True, show_progress=False):
             comm.all_reduce(obs)
     mark("null kernels launched")
 
+    if idle_work is not None:
+        idle_work()  # host work that needs nothing from below, done while the SVD thread finishes
     U, svs, res.G = svd_future.result()
     res.U, res.svs = U, svs
 
@@ -350,15 +353,32 @@ def association(data, y, sid_name, batches=None, covs=None, donorids=None, ks=No
     # only the leading max(ks) components are read unless the full result surface is requested
     res.svd_top = None if return_full else int(max(ks_eff))
     print("performing association test", file=out)
-    core = _association(res, perms, Nnull=Nnull, local_test=local_test, show_progress=show_progress)
+    N = stn.N
+    dev = res.ncorr.device
+    coef_written = []
+
+    def write_coef_column():
+        """data.obs[key_added] (:228-231) is known as soon as the NAM is residualised: it is copied
+        back and written while the SVD thread is still busy."""
+        coef = torch.where(res.valid.bool(), res.ncorr, torch.full_like(res.ncorr, float("nan")))
+        if stn.graph is not None:
+            coef = stn.graph.unpermute(coef)
+        host = _to_host_pinned(coef, slot="coef")
+        if key_added in data.obs:
+            warnings.warn(f"Key '{key_added}' already exists in data.obs. Overwriting.")
+        data.obs[key_added] = host  # pandas copies on assignment
+        coef_written.append(True)
+        mark("coef column written")
+
+    early = comm is None and not return_full
+    core = _association(res, perms, Nnull=Nnull, local_test=local_test, show_progress=show_progress,
+                        idle_work=write_coef_column if early else None)
     svs = res.svs
 
     # ---- neighbourhood-level outputs (:228-237) ----
-    N = stn.N
-    dev = res.ncorr.device
     coef_d = torch.empty(N, dtype=torch.float64, device=dev)
     fdr_d = torch.empty(N, dtype=torch.float64, device=dev)
-    if key_added in data.obs:
+    if key_added in data.obs and not coef_written:
         warnings.warn(f"Key '{key_added}' already exists in data.obs. Overwriting.")
     if core.fdrs is None:
         # local_test=False: the reference writes the coefficients and then crashes looking up FDRs
@@ -368,6 +388,14 @@ def association(data, y, sid_name, batches=None, covs=None, donorids=None, ks=No
         thr = core.fdrs.threshold.to_numpy()
         pmin = np.fmin.accumulate(core.fdrs.fdr.to_numpy())  # Series.min() skips NaN
     _lib.cell_fdr(res.ncorr, res.valid, _to_dev(thr), _to_dev(pmin), coef_d, fdr_d)
+    if coef_written:  # only the FDR column is still missing
+        if core.fdrs is not None:
+            fdr_h = _to_host_pinned(fdr_d if stn.graph is None else stn.graph.unpermute(fdr_d), slot="fdr")
+            mark("results on host")
+            data.obs[f"{key_added}_fdr"] = fdr_h
+        mark("obs written")
+        report()
+        return core.p
     both = torch.stack([coef_d, fdr_d], dim=1)  # [cells x 2]
     if comm is not None:  # every rank ends with the full per-cell columns
         pad = torch.zeros((stn.rows_per, 2), dtype=torch.float64, device=dev)

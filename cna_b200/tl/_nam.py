@@ -278,7 +278,7 @@ def svd_nam(NAM):
             pd.DataFrame(V, index=cols, columns=pcs))
 
 
-TC_GRAM_MAX_N = 256  # TMEM holds the fp32 accumulators of at most 256 samples
+TC_GRAM_MAX_N = 512  # four 128-row output tiles in groups of <= 512 TMEM columns
 
 
 def planes_of(x, n):

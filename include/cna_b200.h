@@ -201,7 +201,7 @@ int cna_null_hist(const float *x, int64_t ld_x, int64_t n_rows, int n, const flo
 int cna_split_f16(const float *src, int64_t ld_src, int64_t src_rows, int src_cols, int transpose,
                   void *hi, void *lo, int64_t ld_dst, int64_t dst_rows, void *stream);
 
-/* Same contract as cna_gram (gram += X^T X), X given as fp16 planes [n_rows x ld16], n <= 256.
+/* Same contract as cna_gram (gram += X^T X), X given as fp16 planes [n_rows x ld16], n <= 512.
  * `workspace` holds per-SM fp64 partial Grams (cna_gram_tc_workspace(n) bytes, contents
  * irrelevant on entry).  replaces: _nam.py:105 `NAM.dot(NAM.T)`. */
 int64_t cna_gram_tc_workspace(int n);

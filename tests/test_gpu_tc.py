@@ -69,7 +69,8 @@ def test_right_multiply_tc(lib, N, n, n_out):
     assert (np.abs(ref.cpu().numpy()[:, :n_out] - want) / scale).max() < 2e-6
 
 
-@pytest.mark.parametrize("N,n", [(5000, 200), (700, 50), (100000, 200), (3000, 129), (513, 16), (40000, 256)])
+@pytest.mark.parametrize("N,n", [(5000, 200), (700, 50), (100000, 200), (3000, 129), (513, 16), (40000, 256),
+                                 (6000, 257), (20000, 330), (9000, 400), (50000, 500), (2000, 512), (100, 300)])
 def test_gram_tc(lib, N, n):
     import torch
     rng = np.random.default_rng(N + n)
