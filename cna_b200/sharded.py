@@ -5,9 +5,11 @@ CSR (column indices stay global), of the diffusion state and of the residualised
 sample-sized is replicated.  The data-path exchanges are
 
   * all-reduce of the graph's column sums (once per graph),
-  * an all-gather of the state before every diffusion step after the first (with the
-    sample-contiguous cell order of real data the kNN halo is ~every other shard's rows, so the
-    halo exchange degenerates to an all-gather),
+  * the kNN halo: the set of remote rows a shard's edges reference is computed once when the graph
+    is made resident (``DeviceGraph``: column ids are renamed to [own rows | halo rows], the
+    request lists are exchanged once); before every diffusion step after the first only those rows
+    travel (one all_to_all_single).  In the stored Cuthill-McKee cell order a shard's halo is about as
+    large as the shard itself instead of ~every other row,
   * all-gathers of one float64 per cell for the global medians (auto-stop, QC, ridge loop),
   * all-reduce of the n x n Gram, of max|ncorr| and of the (Kl x T) null / observed histograms,
   * a broadcast of the permutation indices from rank 0 (the legacy RNG stream is drawn once),
@@ -63,6 +65,26 @@ class Comm:
         else:
             dist.all_gather(list(out.chunk(self.world, dim=0)), local, group=self.group)
         return out
+
+    def all_gather_padded(self, t):
+        """1-D tensors of different lengths -> list of per-rank tensors (one padded all-gather)."""
+        n = torch.tensor([t.numel()], dtype=torch.int64, device=t.device)
+        sizes = self.all_gather_rows(n).tolist()
+        pad = torch.zeros(max(max(sizes), 1), dtype=t.dtype, device=t.device)
+        pad[: t.numel()] = t
+        allp = self.all_gather_rows(pad).reshape(self.world, -1)
+        return [allp[r, : sizes[r]] for r in range(self.world)]
+
+    def exchange_rows(self, send, send_splits, recv, recv_splits, fallback=None):
+        """Variable all-to-all of rows: ``send`` holds the rows for rank 0, 1, ... back to back
+        (``send_splits`` rows each); ``recv`` receives ``recv_splits`` rows from each rank in rank
+        order.  NCCL: one all_to_all_single over NVLink.  Other backends (the gloo tests) call
+        ``fallback()``, which must fill ``recv`` by other means."""
+        if self.backend == "nccl":
+            dist.all_to_all_single(recv, send, recv_splits, send_splits, group=self.group)
+        else:
+            fallback()
+        return recv
 
     def broadcast(self, t, src=0):
         dist.broadcast(t, src=src, group=self.group)

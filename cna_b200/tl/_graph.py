@@ -120,6 +120,18 @@ def cuthill_mckee_order(indptr, indices, n, max_levels=4096, max_roots=8):
     return order, inv
 
 
+_UPLOAD_STREAMS = {}
+
+
+def _upload_stream(dev):
+    """One side stream per device for the asynchronous part of graph uploads (a fresh stream per
+    call would make the caching allocator keep a separate 0.3 GB block for each of them)."""
+    key = (dev.type, dev.index)
+    if key not in _UPLOAD_STREAMS:
+        _UPLOAD_STREAMS[key] = torch.cuda.Stream(device=dev)
+    return _UPLOAD_STREAMS[key]
+
+
 class DeviceGraph:
     """CSR adjacency resident in HBM: int32 indptr / indices plus the raw edge data.  The
     normalised edge values ``A_ij / (colsum_j + w)`` and the diagonal ``w / (colsum_i + w)`` are
@@ -146,7 +158,7 @@ class DeviceGraph:
         data = A.data if A.data.dtype in (np.float32, np.float64) else A.data.astype(np.float64)
         # the edge weights (2/3 of the bytes) are not needed by the ordering: they travel on a side
         # stream while the breadth-first sweeps run (truly asynchronous when the host buffer is pinned)
-        main, side = torch.cuda.current_stream(), torch.cuda.Stream()
+        main, side = torch.cuda.current_stream(), _upload_stream(indptr.device)
         with torch.cuda.stream(side):
             data = _to_dev(data)
         data.record_stream(main)
@@ -163,17 +175,54 @@ class DeviceGraph:
                 _lib.permute_csr(indptr, indices, data, self.order, self.inv, new_indptr, new_indices, new_data)
                 indptr, indices, data = new_indptr, new_indices, new_data
         main.wait_stream(side)
+        self.halo_ids = None
         if shard is None:
             self.comm, self.row0, self.rows_per = None, 0, self.n_total
+            self.indices_global = indices
         else:
             self.comm, self.row0, row1, self.rows_per = shard
             e0, e1 = int(indptr[self.row0].item()), int(indptr[row1].item())
             indptr = (indptr[self.row0:row1 + 1] - e0).contiguous()
             indices, data = indices[e0:e1].clone(), data[e0:e1].clone()
+            self.indices_global = indices  # column sums / edge normalisation use global ids
+            indices = self._plan_halo(indices, row1)
         self.n = indptr.numel() - 1  # rows held by this device
         self.nnz = int(indices.numel())
         self.indptr, self.indices, self.data = indptr, indices, data
         self._scaled = {}
+
+    def _plan_halo(self, indices, row1):
+        """kNN halo of this shard, gathered once: the sorted remote row ids its edges reference
+        (``halo_ids``), the column ids renamed to positions in [own rows (rows_per slots) | halo rows],
+        and who sends what (``send_idx`` / ``send_splits`` / ``recv_splits``)."""
+        comm, r0, rows_per = self.comm, self.row0, self.rows_per
+        cols = indices.long()
+        local = (cols >= r0) & (cols < row1)
+        halo = torch.unique(cols[~local])  # sorted => grouped by owner rank, ascending
+        self.halo_ids = halo
+        renamed = torch.where(local, cols - r0, rows_per + torch.searchsorted(halo, cols))
+        owner = torch.div(halo, rows_per, rounding_mode="floor")
+        self.recv_splits = torch.bincount(owner, minlength=comm.world).tolist()
+        # every rank publishes its request list; a rank serves the ids that fall in its row block
+        send_idx, self.send_splits = [], []
+        for peer, wanted in enumerate(comm.all_gather_padded(halo)):
+            mine = wanted[(wanted >= r0) & (wanted < row1)] - r0 if peer != comm.rank else wanted[:0]
+            send_idx.append(mine)
+            self.send_splits.append(int(mine.numel()))
+        self.send_idx = torch.cat(send_idx)
+        return renamed.to(torch.int32)
+
+    def exchange_halo(self, ext):
+        """Fill the halo rows ``ext[rows_per:]`` of a [rows_per + n_halo, ld] state with the current
+        values of their owners' rows (``ext[:rows_per]`` on the owning ranks)."""
+        comm, rows_per = self.comm, self.rows_per
+        send = ext[:rows_per].index_select(0, self.send_idx)
+        recv = ext[rows_per:]
+
+        def via_all_gather():  # backends without all_to_all (gloo in the tests)
+            recv.copy_(comm.all_gather_rows(ext[:rows_per].contiguous()).index_select(0, self.halo_ids))
+
+        comm.exchange_rows(send, self.send_splits, recv, self.recv_splits, fallback=via_all_gather)
 
     def permute(self, t):
         """Rows of ``t`` (one per cell, caller's order) -> stored order."""
@@ -187,12 +236,12 @@ class DeviceGraph:
         key = (float(self_weight), dtype)
         if key not in self._scaled:
             colsum = torch.zeros(self.n_total, dtype=torch.float64, device=self.indptr.device)
-            _lib.graph_colsum(self.indptr, self.indices, self.data, colsum)
+            _lib.graph_colsum(self.indptr, self.indices_global, self.data, colsum)
             if self.comm is not None:  # column sums need every shard's rows (_nam.py:28)
                 self.comm.all_reduce(colsum)
             vals = torch.empty(self.nnz, dtype=dtype, device=colsum.device)
             diag = torch.empty(self.n, dtype=dtype, device=colsum.device)
-            _lib.graph_scale(self.indptr, self.indices, self.data, colsum, self_weight, vals, diag,
+            _lib.graph_scale(self.indptr, self.indices_global, self.data, colsum, self_weight, vals, diag,
                              row_offset=self.row0)
             self._scaled[key] = (vals, diag)
         return self._scaled[key]

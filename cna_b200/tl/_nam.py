@@ -59,6 +59,8 @@ def diffuse_stepwise(data, s, maxnsteps=15, show_progress=False, self_weight=1):
     (float32 or float64, CUDA tensors are yielded)."""
     out = select_output(show_progress)
     g = graph_of(data)
+    if g.comm is not None:
+        raise NotImplementedError("diffuse / diffuse_stepwise take the whole graph, not a cell-axis shard")
     on_device = torch.is_tensor(s)
     if on_device:
         cur = s if s.is_cuda else s.to(device())
@@ -140,11 +142,17 @@ def _nam_device(data, sid_name, nsteps=None, maxnsteps=15, self_weight=1, show_p
     if codes.numel() != g.n_total:
         raise ValueError("data.obs and the connectivities graph disagree on the number of cells")
     vals, diag = g.scaled(self_weight, torch.float32)
-    # a shard allocates rows_per rows (equal on every rank, so the state can be all-gathered) and
-    # touches only its first g.n
-    cur = torch.zeros((g.rows_per, ld), dtype=torch.float32, device=dev)
-    nxt = torch.zeros((g.rows_per, ld), dtype=torch.float32, device=dev)
+    # a shard allocates rows_per slots for its own rows (equal on every rank) followed by its kNN
+    # halo: the edges' column ids were renamed to positions in this buffer when the graph was made
+    # resident, so a step is a purely local SpMM once the halo rows have been refreshed
+    n_halo = 0 if comm is None else int(g.halo_ids.numel())
+    cur = torch.zeros((g.rows_per + n_halo, ld), dtype=torch.float32, device=dev)
+    nxt = torch.zeros((g.rows_per + n_halo, ld), dtype=torch.float32, device=dev)
     codes = g.permute(codes)  # device rows follow the graph's stored cell order
+    if comm is not None:
+        own = torch.zeros(g.rows_per, dtype=codes.dtype, device=dev)
+        own[: g.n] = codes[g.row0: g.row0 + g.n]
+        codes = torch.cat([own, codes.index_select(0, g.halo_ids)])
     st = NamState(cur[: g.n], S, labels, counts, data.obs.index)
     st.comm, st.row0, st.rows_per, st.graph = comm, g.row0, g.rows_per, g
     need_stats = nsteps is None or show_progress
@@ -155,13 +163,13 @@ def _nam_device(data, sid_name, nsteps=None, maxnsteps=15, self_weight=1, show_p
     for i in range(maxnsteps):
         print("\ttaking step", i + 1, file=out)
         if i == 0:
-            _lib.diffuse_onehot(g.indptr, g.indices, vals, diag, codes, S, cur, n_rows=g.n, row_offset=g.row0)
+            _lib.diffuse_onehot(g.indptr, g.indices, vals, diag, codes, S, cur, n_rows=g.n, row_offset=0)
         else:
             if show_progress:
                 old = cur.clone()
-            # the gathered rows live on other shards: exchange the state, then a local SpMM
-            src = comm.all_gather_rows(cur) if comm is not None else cur
-            _lib.diffuse_step(g.indptr, g.indices, vals, diag, src, nxt, S, n_rows=g.n, row_offset=g.row0)
+            if comm is not None:
+                g.exchange_halo(cur)  # only the rows other shards' edges reference travel
+            _lib.diffuse_step(g.indptr, g.indices, vals, diag, cur, nxt, S, n_rows=g.n, row_offset=0)
             cur, nxt = nxt, cur
         if need_stats:
             _lib.row_kurtosis(cur[: g.n], S, st.inv_count, kurt)

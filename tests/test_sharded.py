@@ -62,6 +62,9 @@ def _comm_checks(rank, world):
     assert comm.all_reduce(t.clone(), op="max").tolist() == [2.0] * 3
     g = comm.all_gather_rows(torch.full((2, 3), float(rank)))
     assert g.shape == (4, 3) and g[:2].eq(0).all() and g[2:].eq(1).all()
+    parts = comm.all_gather_padded(torch.arange(3 + 2 * rank, dtype=torch.int64) + 10 * rank)
+    assert [p.tolist() for p in parts] == [[0, 1, 2], [10, 11, 12, 13, 14]]
+    assert [p.numel() for p in comm.all_gather_padded(torch.zeros(0, dtype=torch.int64))] == [0, 0]
     b = torch.arange(5, dtype=torch.int32) if rank == 0 else torch.zeros(5, dtype=torch.int32)
     assert comm.broadcast(b).tolist() == list(range(5))
     # global median == numpy median of the concatenation, with masks, NaNs and a short tail shard
