@@ -86,10 +86,12 @@ def test_comm_helpers_gloo_world2():
     _spawn(_comm_checks, 2)
 
 
-def _sharded_vs_single(rank, world, spec):
+def _sharded_vs_single(rank, world, spec, reorder=False):
     import cna_b200 as cna
     from cna_b200.sharded import shard_to_device
     torch.cuda.set_device(0)
+    if reorder:  # shards of the Cuthill-McKee ordered graph: small halo, results in the caller's order
+        os.environ["CNA_B200_REORDER"] = "1"
     g = cases.load_demo_graph()
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
@@ -103,6 +105,11 @@ def _sharded_vs_single(rank, world, spec):
     # all-reduced Gram (summation order) only via U, which does not enter them at all
     np.testing.assert_array_equal(d1.obs[key].to_numpy(), d2.obs[key].to_numpy())
     np.testing.assert_allclose(d1.obs[key + "_fdr"].to_numpy(), d2.obs[key + "_fdr"].to_numpy(), rtol=1e-12)
+    sh = shard_to_device(d2)
+    if reorder:
+        assert sh.graph.order is not None
+        # the halo of a contiguous shard of the ordered graph is a fraction of the other shard
+        assert 0 < sh.graph.halo_ids.numel() < 0.8 * (len(d2.obs) - sh.graph.n)
 
 
 @pytest.mark.gpu
@@ -112,6 +119,14 @@ def test_sharded_association_matches_single_gpu(name):
     spec.pop("np_seed", None)
     spec.setdefault("seed", 0)
     _spawn(_sharded_vs_single, 2, spec)
+
+
+@pytest.mark.gpu
+def test_sharded_association_on_reordered_graph():
+    spec = dict(cases.DEMO_CASES["case_male_batch"])
+    spec.pop("np_seed", None)
+    spec.setdefault("seed", 0)
+    _spawn(_sharded_vs_single, 2, spec, True)
 
 
 def _sharded_auto_stop(rank, world):
