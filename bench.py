@@ -219,6 +219,7 @@ def rooflines(prof, steps, N, S, n, nnz, K, Kl, s_steps, peaks):
     b_spmm = 8 * nnz + 4 * (N + 1) + 4 * N + 2 * 4 * N * S
     spec = {
         "cna_diffuse_step_f32": ("hbm", b_spmm, "diffusion SpMM (one step)"),
+        "cna_diffuse_step_f32_qc": ("hbm", b_spmm, "diffusion SpMM, last step, with the QC batch-kurtosis fused in"),
         "cna_diffuse_onehot": ("hbm", b_spmm, "diffusion step 1 from the one-hot indicator"),
         "cna_resid_pass": ("hbm", 2 * 4 * N * S, "select/centre/residualise/standardise/ncorr pass"),
         "cna_gram": ("tensor", 2.0 * n * n * N, "Gram X^T X (CUDA cores)"),

@@ -67,6 +67,7 @@ _SIGNATURES = {
     "cna_graph_scale": [_VP, _VP, _VP, _INT, _I64, _VP, _DBL, _VP, _VP, _INT, _I64, _VP],
     "cna_diffuse_onehot": [_VP, _VP, _VP, _VP, _VP, _I64, _INT, _VP, _I64, _I64, _VP],
     "cna_diffuse_step_f32": [_VP, _VP, _VP, _VP, _VP, _VP, _I64, _INT, _I64, _I64, _VP],
+    "cna_diffuse_step_f32_qc": [_VP, _VP, _VP, _VP, _VP, _VP, _I64, _INT, _I64, _I64, _VP, _VP, _VP, _INT, _VP, _VP],
     "cna_diffuse_step_f64": [_VP, _VP, _VP, _VP, _VP, _VP, _I64, _INT, _I64, _I64, _VP],
     "cna_row_kurtosis": [_VP, _I64, _I64, _INT, _VP, _VP, _VP],
     "cna_batch_kurtosis": [_VP, _I64, _I64, _VP, _VP, _VP, _INT, _INT, _VP, _VP],
@@ -204,6 +205,17 @@ def diffuse_step(indptr, indices, vals, diag, src, dst, n_cols, n_rows=None, row
     _call(name, _ptr(indptr, torch.int32, "indptr"), _ptr(indices, torch.int32, "indices"),
           _ptr(vals, dt, "vals"), _ptr(diag, dt, "diag"), _ptr(src, dt, "src"), _ptr(dst, dt, "dst"),
           dst.shape[0] if n_rows is None else int(n_rows), int(n_cols), src.shape[1], int(row_offset), _stream())
+
+
+def diffuse_step_qc(indptr, indices, vals, diag, src, dst, n_cols, col_batch, inv_count_ld, batch_inv, kurt,
+                    n_rows=None, row_offset=0):
+    """fp32 diffusion step that also writes the batch-kurtosis QC statistic of every finished row."""
+    _call("cna_diffuse_step_f32_qc", _ptr(indptr, torch.int32, "indptr"), _ptr(indices, torch.int32, "indices"),
+          _ptr(vals, torch.float32, "vals"), _ptr(diag, torch.float32, "diag"), _ptr(src, torch.float32, "src"),
+          _ptr(dst, torch.float32, "dst"), dst.shape[0] if n_rows is None else int(n_rows), int(n_cols),
+          src.shape[1], int(row_offset), _ptr(col_batch, torch.int8, "col_batch"),
+          _ptr(inv_count_ld, torch.float64, "inv_count"), _ptr(batch_inv, torch.float64, "batch_inv"),
+          batch_inv.numel(), _ptr(kurt, torch.float64, "kurt"), _stream())
 
 
 def row_kurtosis(s, n_samples, inv_count, kurt):

@@ -95,12 +95,23 @@ onehot_step_kernel(const int32_t *__restrict__ indptr, const int32_t *__restrict
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ float4 ldg4(const float4 *p) { return __ldg(p); }
 
-template <int NV>
+// QC = true: the batch-kurtosis QC statistic of the finished row (_nam.py:78-82: Pearson kurtosis
+// across the per-batch means of s / C) is computed from the accumulators before the warp retires,
+// which saves the separate pass over the state after the last diffusion step (<= 8 batches).
+struct SpmmQc {
+    const int8_t *col_batch;   // [ld] batch of each sample column, -1 for padding
+    const double *inv_count;   // [ld] 1 / cells per sample (0 for padding)
+    const double *batch_inv;   // [n_batches] 1 / samples per batch
+    int n_batches;
+    double *kurt;              // [n_rows]
+};
+
+template <int NV, bool QC>
 __global__ void __launch_bounds__(256)
 spmm_f32_kernel(const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices,
                 const float *__restrict__ vals, const float *__restrict__ diag,
                 const float *__restrict__ in, float *__restrict__ out, int64_t n_rows, int nvec,
-                int64_t ld4, int64_t in_row_offset) {
+                int64_t ld4, int64_t in_row_offset, SpmmQc qc) {
     int64_t row = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
     if (row >= n_rows) return;
@@ -163,6 +174,46 @@ spmm_f32_kernel(const int32_t *__restrict__ indptr, const int32_t *__restrict__ 
             acc[q].z = fmaf(d, x.z, acc[q].z);
             acc[q].w = fmaf(d, x.w, acc[q].w);
             out4[row * ld4 + c] = acc[q];
+        }
+    }
+    if (QC) {
+        double bs[8];
+#pragma unroll
+        for (int b = 0; b < 8; ++b) bs[b] = 0.0;
+#pragma unroll
+        for (int q = 0; q < NV; ++q) {
+            int c = lane + 32 * q;
+            if (c < nvec) {
+                const float v[4] = {acc[q].x, acc[q].y, acc[q].z, acc[q].w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int col = 4 * c + k;
+                    const int bid = qc.col_batch[col];
+                    const double x = double(v[k]) * qc.inv_count[col];
+#pragma unroll
+                    for (int b = 0; b < 8; ++b) bs[b] += (bid == b) ? x : 0.0;
+                }
+            }
+        }
+        const int nb = qc.n_batches;
+        double mm = 0.0;
+#pragma unroll
+        for (int b = 0; b < 8; ++b)
+            if (b < nb) {
+                bs[b] = warp_sum(bs[b]) * qc.batch_inv[b];  // mean over the batch's samples
+                mm += bs[b];
+            }
+        if (lane == 0) {
+            mm /= nb;
+            double m2 = 0.0, m4 = 0.0;
+#pragma unroll
+            for (int b = 0; b < 8; ++b)
+                if (b < nb) {
+                    const double dlt = bs[b] - mm;
+                    m2 += dlt * dlt;
+                    m4 += dlt * dlt * dlt * dlt;
+                }
+            qc.kurt[row] = kurtosis_from_moments(mm, m2 / nb, m4 / nb, false);
         }
     }
 }
@@ -285,8 +336,9 @@ int cna_diffuse_step_f32(const int32_t *indptr, const int32_t *indices, const fl
     int nvec = (n_cols + 3) / 4;
     if (vec_ok && nvec <= 128) {
         int64_t ld4 = ld / 4;
+        SpmmQc none{};
 #define CNA_SPMM(NV) \
-    spmm_f32_kernel<NV><<<grid, 256, 0, st>>>(indptr, indices, vals, diag, in, out, n_rows, nvec, ld4, in_row_offset)
+    spmm_f32_kernel<NV, false><<<grid, 256, 0, st>>>(indptr, indices, vals, diag, in, out, n_rows, nvec, ld4, in_row_offset, none)
         if (nvec <= 32) CNA_SPMM(1);
         else if (nvec <= 64) CNA_SPMM(2);
         else if (nvec <= 96) CNA_SPMM(3);
@@ -298,6 +350,35 @@ int cna_diffuse_step_f32(const int32_t *indptr, const int32_t *indices, const fl
                                                          n_rows, n_cols, ld, in_row_offset);
         CNA_LAUNCHED("spmm_generic_kernel<float>");
     }
+    return CNA_OK;
+}
+
+int cna_diffuse_step_f32_qc(const int32_t *indptr, const int32_t *indices, const float *vals,
+                            const float *diag, const float *in, float *out, int64_t n_rows, int n_cols,
+                            int64_t ld, int64_t in_row_offset, const int8_t *col_batch,
+                            const double *inv_count, const double *batch_inv, int n_batches, double *kurt,
+                            void *stream) {
+    CNA_REQUIRE(n_rows >= 0 && n_cols > 0 && ld >= n_cols && ld % 4 == 0, "cna_diffuse_step_f32_qc: bad shape");
+    CNA_REQUIRE(in != out, "cna_diffuse_step_f32_qc: in-place step is not supported");
+    CNA_REQUIRE(n_batches >= 2 && n_batches <= 8 && col_batch && inv_count && batch_inv && kurt,
+                "cna_diffuse_step_f32_qc: 2..8 batches supported (got %d)", n_batches);
+    CNA_REQUIRE((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) % 16 == 0,
+                "cna_diffuse_step_f32_qc: state must be 16-byte aligned");
+    int nvec = (n_cols + 3) / 4;
+    CNA_REQUIRE(nvec <= 128, "cna_diffuse_step_f32_qc: at most 512 sample columns");
+    if (n_rows == 0) return CNA_OK;
+    unsigned grid = warp_rows_grid(n_rows, 256);
+    cudaStream_t st = as_stream(stream);
+    int64_t ld4 = ld / 4;
+    SpmmQc qc{col_batch, inv_count, batch_inv, n_batches, kurt};
+#define CNA_SPMM(NV) \
+    spmm_f32_kernel<NV, true><<<grid, 256, 0, st>>>(indptr, indices, vals, diag, in, out, n_rows, nvec, ld4, in_row_offset, qc)
+    if (nvec <= 32) CNA_SPMM(1);
+    else if (nvec <= 64) CNA_SPMM(2);
+    else if (nvec <= 96) CNA_SPMM(3);
+    else CNA_SPMM(4);
+#undef CNA_SPMM
+    CNA_LAUNCHED("spmm_f32_kernel<QC>");
     return CNA_OK;
 }
 

@@ -334,7 +334,8 @@ def association(data, y, sid_name, batches=None, covs=None, donorids=None, ks=No
     # ---- launch the diffusion (asynchronous unless nsteps is None) ----
     print("computing NAM", file=out)
     try:
-        stn = _nam._nam_device(data, sid_name, nsteps=nsteps, show_progress=show_progress, codes=codes)
+        stn = _nam._nam_device(data, sid_name, nsteps=nsteps, show_progress=show_progress, codes=codes,
+                               qc_batches=batches)
     except BaseException:
         if perms is not None:
             perms.cancel()

@@ -115,6 +115,8 @@ class NamState:
         self.row0 = 0
         self.rows_per = s.shape[0]
         self.graph = None  # DeviceGraph whose (possibly reordered) row order the state follows
+        self.qc_kurt = None  # per-cell batch kurtosis when the last diffusion step produced it
+        self.qc_batches = None
 
     @property
     def N(self):
@@ -129,9 +131,27 @@ def _r2_p20(s, old, S):
     return np.percentile(r2, 20)
 
 
-def _nam_device(data, sid_name, nsteps=None, maxnsteps=15, self_weight=1, show_progress=False, codes=None):
+def _qc_plan(batches, labels, ld, dev):
+    """Device tables for the QC statistic fused into the last diffusion step: batch of each sample
+    column (int8, -1 for padding) and 1 / samples per batch; None when the fused kernel does not
+    apply (one batch: no QC, _nam.py:89; more than 8 batches: separate kernel)."""
+    if batches is None or len(np.unique(batches)) == 1:
+        return None
+    ub, order, off = _batch_segments(batches.reindex(labels).to_numpy())  # _nam.py:79
+    if not 2 <= len(ub) <= 8:
+        return None
+    col_batch = np.full(ld, -1, dtype=np.int8)
+    for b in range(len(ub)):
+        col_batch[order[off[b]:off[b + 1]]] = b
+    return _to_dev(col_batch), _to_dev(1.0 / np.diff(off).astype(np.float64))
+
+
+def _nam_device(data, sid_name, nsteps=None, maxnsteps=15, self_weight=1, show_progress=False, codes=None,
+                qc_batches=None):
     """``_nam.py:44-76`` on the device.  The first step never materialises the one-hot matrix.
-    ``codes`` = an already computed ``sample_codes(data, sid_name)``."""
+    ``codes`` = an already computed ``sample_codes(data, sid_name)``; ``qc_batches`` = the per-sample
+    batch Series of the QC that will follow (``_qc_device``): with a fixed ``nsteps`` its per-cell
+    statistic is then produced by the last diffusion step itself."""
     out = select_output(show_progress)
     g = graph_of(data)
     labels, codes, counts = codes if codes is not None else sample_codes(data, sid_name)
@@ -157,6 +177,10 @@ def _nam_device(data, sid_name, nsteps=None, maxnsteps=15, self_weight=1, show_p
     st.comm, st.row0, st.rows_per, st.graph = comm, g.row0, g.rows_per, g
     need_stats = nsteps is None or show_progress
     kurt = torch.empty(g.n, dtype=torch.float64, device=dev) if need_stats else None
+    qc = _qc_plan(qc_batches, labels, ld, dev) if (nsteps is not None and nsteps >= 2) else None
+    if qc is not None:
+        inv_ld = torch.zeros(ld, dtype=torch.float64, device=dev)
+        inv_ld[:S] = st.inv_count
     old = None
     prevmedkurt = np.inf
     i = 0
@@ -169,7 +193,13 @@ def _nam_device(data, sid_name, nsteps=None, maxnsteps=15, self_weight=1, show_p
                 old = cur.clone()
             if comm is not None:
                 g.exchange_halo(cur)  # only the rows other shards' edges reference travel
-            _lib.diffuse_step(g.indptr, g.indices, vals, diag, cur, nxt, S, n_rows=g.n, row_offset=0)
+            if qc is not None and i + 1 == nsteps:  # last step: QC statistic straight from the accumulators
+                st.qc_kurt = torch.empty(g.n, dtype=torch.float64, device=dev)
+                st.qc_batches = qc_batches.reindex(labels)
+                _lib.diffuse_step_qc(g.indptr, g.indices, vals, diag, cur, nxt, S, qc[0], inv_ld, qc[1],
+                                     st.qc_kurt, n_rows=g.n, row_offset=0)
+            else:
+                _lib.diffuse_step(g.indptr, g.indices, vals, diag, cur, nxt, S, n_rows=g.n, row_offset=0)
             cur, nxt = nxt, cur
         if need_stats:
             _lib.row_kurtosis(cur[: g.n], S, st.inv_count, kurt)
@@ -209,10 +239,13 @@ def _qc_device(st, batches, show_progress=False):
         st.keep = None
         return
     b = batches.reindex(st.labels)  # _nam.py:79
-    ub, order, off = _batch_segments(b.to_numpy())
     dev = st.s.device
-    kurt = torch.empty(st.N, dtype=torch.float64, device=dev)
-    _lib.batch_kurtosis(st.s, st.inv_count, _to_dev(order), _to_dev(off), kurt)
+    if st.qc_kurt is not None and st.qc_batches is not None and b.equals(st.qc_batches):
+        kurt = st.qc_kurt  # already produced by the last diffusion step
+    else:
+        ub, order, off = _batch_segments(b.to_numpy())
+        kurt = torch.empty(st.N, dtype=torch.float64, device=dev)
+        _lib.batch_kurtosis(st.s, st.inv_count, _to_dev(order), _to_dev(off), kurt)
     med = device_median(kurt, comm=st.comm, rows_per=st.rows_per)
     threshold = max(6, 2 * med)  # _nam.py:94 (python max: a NaN median gives 6)
     print("throwing out neighborhoods with batch kurtosis >=", threshold, file=out)
@@ -233,7 +266,8 @@ def nam(data, sid_name, batches=None, nsteps=None, self_weight=1, max_frac_pcs=0
         u = data.obs[sid_name].unique()
         batches = pd.Series(np.ones(len(u)), index=u)
     print("computing NAM", file=out)
-    st = _nam_device(data, sid_name, nsteps=nsteps, self_weight=self_weight, show_progress=show_progress)
+    st = _nam_device(data, sid_name, nsteps=nsteps, self_weight=self_weight, show_progress=show_progress,
+                     qc_batches=batches)
     _qc_device(st, batches, show_progress=show_progress)
     return nam_frame(st, sid_name), keep_mask(st)
 

@@ -73,6 +73,16 @@ int cna_diffuse_step_f32(const int32_t *indptr, const int32_t *indices, const fl
                          int n_cols, int64_t ld, int64_t in_row_offset, void *stream);
 
 /* Same, fp64 state with any number of columns (cna.tl.diffuse / diffuse_stepwise on user input). */
+/* cna_diffuse_step_f32 that also emits the QC statistic of _nam.py:78-82 for every finished row:
+ * kurt[i] = Pearson kurtosis across batches of the per-batch means of out[i, :] * inv_count (what
+ * cna_batch_kurtosis computes in a separate pass).  col_batch [ld] int8 = batch of each sample column
+ * (-1 for padding), inv_count [ld] (0 for padding), batch_inv [n_batches] = 1 / samples per batch,
+ * 2 <= n_batches <= 8.  replaces: _nam.py:33 of the last step + :78-82. */
+int cna_diffuse_step_f32_qc(const int32_t *indptr, const int32_t *indices, const float *vals,
+                            const float *diag, const float *in, float *out, int64_t n_rows, int n_cols,
+                            int64_t ld, int64_t in_row_offset, const int8_t *col_batch,
+                            const double *inv_count, const double *batch_inv, int n_batches, double *kurt,
+                            void *stream);
 int cna_diffuse_step_f64(const int32_t *indptr, const int32_t *indices, const double *vals,
                          const double *diag, const double *in, double *out, int64_t n_rows,
                          int n_cols, int64_t ld, int64_t in_row_offset, void *stream);
