@@ -4,7 +4,7 @@
 #   <name>.ncu-rep        one --set full capture per heavy kernel
 CFG=${1:-C}
 shift
-KERNELS=${@:-"spmm_f32 resid_kernel xb_tc gram_tc onehot_step batch_kurtosis"}
+KERNELS=${@:-"spmm_f32 resid_kernel xb_tc gram_tc onehot_step"}
 K='regex:spmm_f32|onehot_step|row_kurtosis|batch_kurtosis|resid_kernel|gram_|xb_|split_f16|perm_stats|absmax|obs_hist|cell_fdr|colsum|scale_kernel|bfs_|permute_'
 BENCH="python bench.py --config $CFG --steps 1 --warmup 1 --no-cpu-baseline --no-e2e"
 ncu --metrics gpu__time_duration.sum --clock-control none -k "$K" -c 400 --csv --log-file gpurun_out/launches.csv $BENCH > gpurun_out/ncu_launches.log 2>&1
