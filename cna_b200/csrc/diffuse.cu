@@ -9,7 +9,9 @@
 // a whole number of 32-byte sectors.  A warp owns one output row; lanes own float4 column groups,
 // the (index, value) pairs of the row are read coalesced 32 at a time and broadcast with shuffles,
 // and four gathered source rows are kept in flight per lane.  Accumulation is in CSR order, the
-// order scipy's csr_matvecs uses.
+// order scipy's csr_matvecs uses.  The graph is stored in a Cuthill-McKee cell order (reorder.cu), so
+// the gathered rows come from L2/L1 rather than HBM; the kernel is then bound by the L1/TEX data pipe
+// (profiles/): all 4.nnz.S gathered bytes pass through it whatever the hit rate.
 #include "common.cuh"
 
 namespace cna {

@@ -1,7 +1,8 @@
 """Cell-axis sharding of the hot path across the GPUs of one box.
 
-One process per GPU (``torchrun``); rank g owns a contiguous block of cells: its rows of the kNN
-CSR (column indices stay global), of the diffusion state and of the residualised NAM.  Everything
+One process per GPU (``torchrun``); rank g owns a contiguous block of cells (of the stored,
+Cuthill-McKee ordered graph): its rows of the kNN CSR, of the diffusion state and of the
+residualised NAM.  Everything
 sample-sized is replicated.  The data-path exchanges are
 
   * all-reduce of the graph's column sums (once per graph),
@@ -11,7 +12,7 @@ sample-sized is replicated.  The data-path exchanges are
     travel (one all_to_all_single).  In the stored Cuthill-McKee cell order a shard's halo is about as
     large as the shard itself instead of ~every other row,
   * all-gathers of one float64 per cell for the global medians (auto-stop, QC, ridge loop),
-  * all-reduce of the n x n Gram, of max|ncorr| and of the (Kl x T) null / observed histograms,
+  * all-reduce of the n x n Gram, of max|ncorr| and of the T-bin null / observed histograms,
   * a broadcast of the permutation indices from rank 0 (the legacy RNG stream is drawn once),
   * an all-gather of the per-cell outputs, so every rank ends with the full ``data.obs`` columns.
 
