@@ -84,6 +84,8 @@ _SIGNATURES = {
     "cna_cell_fdr": [_VP, _VP, _I64, _VP, _VP, _INT, _VP, _VP, _VP],
     "cna_knn_bruteforce": [_VP, _I64, _INT, _INT, _VP, _VP, _VP],
     "cna_bfs_expand": [_VP, _VP, _VP, _INT, _INT, _INT, _VP, _VP, _VP, _VP, _VP],
+    "cna_bfs_keys": [_VP, _INT, _VP, _VP, _VP],
+    "cna_bfs_place": [_VP, _INT, _VP, _VP, _VP],
     "cna_permute_csr": [_VP, _VP, _VP, _INT, _VP, _VP, _VP, _I64, _VP, _VP, _VP],
     "cna_host_randn": [_VP, _VP, _VP, _VP, _I64, _VP, _INT],
     "cna_host_perm_blocks": [_VP, _VP, _VP, _VP, _INT, _VP, _VP, _I64, _VP, _I64, _INT],
@@ -335,6 +337,16 @@ def bfs_expand(indptr, indices, frontier, pos_base, next_level, level, first_par
           _ptr(frontier, torch.int32, "frontier"), frontier.numel(), int(pos_base), int(next_level),
           _ptr(level, torch.int32, "level"), _ptr(first_parent, torch.int32, "first_parent"),
           _ptr(nxt, torch.int32, "next"), _ptr(next_count, torch.int32, "next_count"), _stream())
+
+
+def bfs_keys(nxt, n, first_parent, keys):
+    _call("cna_bfs_keys", _ptr(nxt, torch.int32, "next"), int(n), _ptr(first_parent, torch.int32, "first_parent"),
+          _ptr(keys, torch.int64, "keys"), _stream())
+
+
+def bfs_place(sorted_keys, n, order, offset, frontier):
+    _call("cna_bfs_place", _ptr(sorted_keys, torch.int64, "sorted_keys"), int(n),
+          _ptr(order, torch.int64, "order") + 8 * int(offset), _ptr(frontier, torch.int32, "frontier"), _stream())
 
 
 def permute_csr(indptr, indices, data, order, inv, new_indptr, new_indices, new_data):

@@ -108,7 +108,7 @@ struct SpmmQc {
     double *kurt;              // [n_rows]
 };
 
-template <int NV, bool QC>
+template <int NV, int QC>  // QC = 0: plain step; QC = 2 / 4 / 8: batch-kurtosis epilogue for <= QC batches
 __global__ void __launch_bounds__(256)
 spmm_f32_kernel(const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices,
                 const float *__restrict__ vals, const float *__restrict__ diag,
@@ -178,10 +178,11 @@ spmm_f32_kernel(const int32_t *__restrict__ indptr, const int32_t *__restrict__ 
             out4[row * ld4 + c] = acc[q];
         }
     }
-    if (QC) {
-        double bs[8];
+    if (QC > 0) {
+        constexpr int NB = QC > 0 ? QC : 1;
+        double bs[NB];
 #pragma unroll
-        for (int b = 0; b < 8; ++b) bs[b] = 0.0;
+        for (int b = 0; b < NB; ++b) bs[b] = 0.0;
 #pragma unroll
         for (int q = 0; q < NV; ++q) {
             int c = lane + 32 * q;
@@ -193,14 +194,14 @@ spmm_f32_kernel(const int32_t *__restrict__ indptr, const int32_t *__restrict__ 
                     const int bid = qc.col_batch[col];
                     const double x = double(v[k]) * qc.inv_count[col];
 #pragma unroll
-                    for (int b = 0; b < 8; ++b) bs[b] += (bid == b) ? x : 0.0;
+                    for (int b = 0; b < NB; ++b) bs[b] += (bid == b) ? x : 0.0;
                 }
             }
         }
         const int nb = qc.n_batches;
         double mm = 0.0;
 #pragma unroll
-        for (int b = 0; b < 8; ++b)
+        for (int b = 0; b < NB; ++b)
             if (b < nb) {
                 bs[b] = warp_sum(bs[b]) * qc.batch_inv[b];  // mean over the batch's samples
                 mm += bs[b];
@@ -209,7 +210,7 @@ spmm_f32_kernel(const int32_t *__restrict__ indptr, const int32_t *__restrict__ 
             mm /= nb;
             double m2 = 0.0, m4 = 0.0;
 #pragma unroll
-            for (int b = 0; b < 8; ++b)
+            for (int b = 0; b < NB; ++b)
                 if (b < nb) {
                     const double dlt = bs[b] - mm;
                     m2 += dlt * dlt;
@@ -340,7 +341,7 @@ int cna_diffuse_step_f32(const int32_t *indptr, const int32_t *indices, const fl
         int64_t ld4 = ld / 4;
         SpmmQc none{};
 #define CNA_SPMM(NV) \
-    spmm_f32_kernel<NV, false><<<grid, 256, 0, st>>>(indptr, indices, vals, diag, in, out, n_rows, nvec, ld4, in_row_offset, none)
+    spmm_f32_kernel<NV, 0><<<grid, 256, 0, st>>>(indptr, indices, vals, diag, in, out, n_rows, nvec, ld4, in_row_offset, none)
         if (nvec <= 32) CNA_SPMM(1);
         else if (nvec <= 64) CNA_SPMM(2);
         else if (nvec <= 96) CNA_SPMM(3);
@@ -373,13 +374,20 @@ int cna_diffuse_step_f32_qc(const int32_t *indptr, const int32_t *indices, const
     cudaStream_t st = as_stream(stream);
     int64_t ld4 = ld / 4;
     SpmmQc qc{col_batch, inv_count, batch_inv, n_batches, kurt};
-#define CNA_SPMM(NV) \
-    spmm_f32_kernel<NV, true><<<grid, 256, 0, st>>>(indptr, indices, vals, diag, in, out, n_rows, nvec, ld4, in_row_offset, qc)
+#define CNA_SPMM_NB(NV, NB) \
+    spmm_f32_kernel<NV, NB><<<grid, 256, 0, st>>>(indptr, indices, vals, diag, in, out, n_rows, nvec, ld4, in_row_offset, qc)
+#define CNA_SPMM(NV)                               \
+    do {                                           \
+        if (n_batches <= 2) CNA_SPMM_NB(NV, 2);    \
+        else if (n_batches <= 4) CNA_SPMM_NB(NV, 4); \
+        else CNA_SPMM_NB(NV, 8);                   \
+    } while (0)
     if (nvec <= 32) CNA_SPMM(1);
     else if (nvec <= 64) CNA_SPMM(2);
     else if (nvec <= 96) CNA_SPMM(3);
     else CNA_SPMM(4);
 #undef CNA_SPMM
+#undef CNA_SPMM_NB
     CNA_LAUNCHED("spmm_f32_kernel<QC>");
     return CNA_OK;
 }

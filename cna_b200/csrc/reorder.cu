@@ -40,6 +40,27 @@ __global__ void bfs_expand_kernel(const int32_t *__restrict__ indptr, const int3
     }
 }
 
+// Sort keys of the nodes discovered for the next level: (position of the first parent, node id).
+__global__ void bfs_keys_kernel(const int32_t *__restrict__ next, int n, const int32_t *__restrict__ first_parent,
+                                int64_t *__restrict__ keys) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        int v = next[i];
+        keys[i] = (int64_t(first_parent[v]) << 32) | int64_t(uint32_t(v));
+    }
+}
+
+// The sorted level becomes the next stretch of the order and the next frontier.
+__global__ void bfs_place_kernel(const int64_t *__restrict__ sorted_keys, int n, int64_t *__restrict__ order_out,
+                                 int32_t *__restrict__ frontier) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        int v = int(sorted_keys[i] & 0xFFFFFFFFll);
+        order_out[i] = v;
+        frontier[i] = v;
+    }
+}
+
 // Row i of the new graph is row order[i] of the old one, column ids renamed through inv.
 template <typename T>
 __global__ void permute_csr_kernel(const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices,
@@ -73,6 +94,22 @@ int cna_bfs_expand(const int32_t *indptr, const int32_t *indices, const int32_t 
     bfs_expand_kernel<<<grid, 256, 0, as_stream(stream)>>>(indptr, indices, frontier, n_front, pos_base,
                                                           next_level, level, first_parent, next, next_count);
     CNA_LAUNCHED("bfs_expand_kernel");
+    return CNA_OK;
+}
+
+int cna_bfs_keys(const int32_t *next, int n, const int32_t *first_parent, int64_t *keys, void *stream) {
+    CNA_REQUIRE(next && first_parent && keys && n >= 0, "cna_bfs_keys: bad arguments");
+    if (n == 0) return CNA_OK;
+    bfs_keys_kernel<<<(n + 255) / 256, 256, 0, as_stream(stream)>>>(next, n, first_parent, keys);
+    CNA_LAUNCHED("bfs_keys_kernel");
+    return CNA_OK;
+}
+
+int cna_bfs_place(const int64_t *sorted_keys, int n, int64_t *order_out, int32_t *frontier, void *stream) {
+    CNA_REQUIRE(sorted_keys && order_out && frontier && n >= 0, "cna_bfs_place: bad arguments");
+    if (n == 0) return CNA_OK;
+    bfs_place_kernel<<<(n + 255) / 256, 256, 0, as_stream(stream)>>>(sorted_keys, n, order_out, frontier);
+    CNA_LAUNCHED("bfs_place_kernel");
     return CNA_OK;
 }
 

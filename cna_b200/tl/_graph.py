@@ -12,6 +12,7 @@ import scipy.sparse as sp
 import torch
 
 from .. import _lib
+from ._timing import mark
 
 
 def get_connectivity(data):
@@ -74,9 +75,11 @@ def _bfs_far_node(indptr, indices, n, root, max_levels):
     return int(frontier.min().item())  # min: independent of the order of discovery
 
 
-def cuthill_mckee_order(indptr, indices, n, max_levels=4096, max_roots=8):
+def cuthill_mckee_order(indptr, indices, n, max_levels=4096, max_roots=8, far_root=True):
     """Cuthill-McKee ordering of a symmetric CSR on the device (csrc/reorder.cu): breadth-first levels
     from a pseudo-peripheral root, each level sorted by (position of its first parent, node id).
+    ``far_root=False`` skips the extra sweep that looks for the pseudo-peripheral root (one-shot calls
+    on a host graph, where the ordering is on the critical path: a slightly wider band, ~30 % cheaper).
     Returns (order int64 [n] new -> old, inv int32 [n] old -> new), or None when the graph is too
     path-like to be worth it (more than ``max_levels`` levels).  Components beyond ``max_roots`` are
     appended in their original order.  Deterministic: sets and sort keys do not depend on timing."""
@@ -85,6 +88,8 @@ def cuthill_mckee_order(indptr, indices, n, max_levels=4096, max_roots=8):
     first_parent = torch.full((n,), 2 ** 31 - 1, dtype=torch.int32, device=dev)
     order = torch.empty(n, dtype=torch.int64, device=dev)
     nxt = torch.empty(n, dtype=torch.int32, device=dev)
+    keys = torch.empty(n, dtype=torch.int64, device=dev)
+    front_buf = torch.empty(n, dtype=torch.int32, device=dev)
     count = torch.zeros(1, dtype=torch.int32, device=dev)
     deg = (indptr[1:] - indptr[:-1]).long()
     placed, lvl = 0, 0
@@ -93,8 +98,9 @@ def cuthill_mckee_order(indptr, indices, n, max_levels=4096, max_roots=8):
             break
         big = torch.iinfo(torch.int64).max
         root = int(torch.where(level < 0, deg, torch.full_like(deg, big)).argmin().item())
-        if attempt == 0:  # the giant component: start from the far end of a long shortest path
+        if attempt == 0 and far_root:  # the giant component: start from the far end of a long shortest path
             root = _bfs_far_node(indptr, indices, n, root, max_levels)
+            mark("graph: pseudo-peripheral root found")
         level[root] = lvl
         frontier = torch.tensor([root], dtype=torch.int32, device=dev)
         order[placed] = root
@@ -105,10 +111,10 @@ def cuthill_mckee_order(indptr, indices, n, max_levels=4096, max_roots=8):
             c = int(count.item())
             if c == 0:
                 break
-            cand = nxt[:c].long()
-            nodes = torch.sort((first_parent[cand].long() << 32) | cand).values & 0xFFFFFFFF
-            order[placed:placed + c] = nodes
-            frontier = nodes.to(torch.int32)
+            _lib.bfs_keys(nxt, c, first_parent, keys)
+            srt = torch.sort(keys[:c]).values
+            _lib.bfs_place(srt, c, order, placed, front_buf)
+            frontier = front_buf[:c]
             pos_base, placed, lvl = placed, placed + c, lvl + 1
             if lvl > max_levels:
                 return None
@@ -141,7 +147,7 @@ class DeviceGraph:
     new; both None when the original order is kept).  Everything row-indexed on the device is in the
     new order; the host boundary (``unpermute``) restores the caller's order."""
 
-    def __init__(self, A, shard=None, reorder=None):
+    def __init__(self, A, shard=None, reorder=None, resident=True):
         """``shard`` = (comm, row0, row1, rows_per) keeps only rows [row0, row1) (of the stored
         order) on this device (cell-axis sharding, ``cna_b200.sharded``); column indices stay
         global."""
@@ -163,8 +169,10 @@ class DeviceGraph:
             data = _to_dev(data)
         data.record_stream(main)
         self.order = self.inv = None
+        mark("graph: indices queued for upload")
         if (want_reorder(self.n_total) if reorder is None else reorder) and self.n_total > 1:
-            res = cuthill_mckee_order(indptr, indices, self.n_total)
+            res = cuthill_mckee_order(indptr, indices, self.n_total, far_root=resident)
+            mark("graph: cell order computed")
             if res is not None:
                 self.order, self.inv = res
                 deg = (indptr[1:] - indptr[:-1])[self.order]
@@ -276,7 +284,7 @@ def graph_of(data):
     g = getattr(data, "graph", None)
     if isinstance(g, DeviceGraph):  # ResidentData / ShardedData
         return g
-    return DeviceGraph(get_connectivity(data))
+    return DeviceGraph(get_connectivity(data), resident=False)  # one-shot: built for this call only
 
 
 def sample_codes(data, sid_name):

@@ -265,6 +265,11 @@ int cna_bfs_expand(const int32_t *indptr, const int32_t *indices, const int32_t 
                    int pos_base, int next_level, int32_t *level, int32_t *first_parent, int32_t *next,
                    int32_t *next_count, void *stream);
 
+/* Helpers of the per-level sort: keys[i] = (first_parent[next[i]] << 32) | next[i]; after sorting the
+ * keys, the node ids (low words) are written to order_out[0..n) and to the next frontier. */
+int cna_bfs_keys(const int32_t *next, int n, const int32_t *first_parent, int64_t *keys, void *stream);
+int cna_bfs_place(const int64_t *sorted_keys, int n, int64_t *order_out, int32_t *frontier, void *stream);
+
 /* Symmetric permutation of a CSR: row i of the result is row order[i] of the input with its column
  * ids renamed through inv (inv[order[i]] = i); edges keep their order inside a row, so downstream
  * sums are performed in the original order.  new_indptr = prefix sums of the permuted row lengths. */
