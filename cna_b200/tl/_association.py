@@ -139,10 +139,13 @@ def _association(res, perms, Nnull=1000, local_test=True, show_progress=False, i
     ``res`` carries the device-resident residualised NAM (``res.planes`` / ``res.x``), M, r, the
     standardised phenotype and ks; U, svs and the Gram are added to it.
 
-    Order of work: the Gram and max|ncorr| are launched and read back with one sync; the conditioned
-    null phenotypes (which need M but not U) and the null GEMM + histograms are launched next, so the
-    GPU works on them while the host does the n x n SVD; the PC regressions of all permutations
-    follow once U is known."""
+    Order of work: the Gram and max|ncorr| are launched and read back with one sync; the n x n SVD then
+    runs on a helper thread.  Meanwhile this thread launches the conditioned null phenotypes (which need
+    M but not U) and the null GEMM + histograms, turns the histograms into the FDR table and starts on
+    ``idle_work(fdrs, svd_done)`` (the per-cell output columns; a sequence of steps that stops early once
+    ``svd_done()`` is true).  With U: observed statistics, the PC regressions of all permutations are
+    launched, ``idle_work(fdrs, None)`` finishes its remaining steps while they run, then the global
+    p-value."""
     out = select_output(show_progress)
     M, r, n = res.M, res.r, res.n
     dev = res.ncorr.device
@@ -160,23 +163,6 @@ def _association(res, perms, Nnull=1000, local_test=True, show_progress=False, i
             comm.all_reduce(mx, op="max")
     Gh = G_d.cpu().numpy()
     mark("gram on host")
-    # The n x n SVD needs only the Gram and the null kernels only the permutations: the SVD runs on a
-    # helper thread (LAPACK releases the GIL) while this thread waits for the draws and launches the
-    # null kernels, whichever of the two inputs is ready first.
-    svd_future = _helper_pool().submit(_nam.svd_of_gram, Gh, res.svd_top)  # _nam.py:105
-
-    # ---- permutations: indices from the host RNG (bit-exact), everything else on the device ----
-    if perms is not None:
-        perm_d = perms.result_device(dev)
-    else:  # a shard other than rank 0: the indices are drawn once, by rank 0
-        perm_d = torch.empty((Nnull, n), dtype=torch.int32, device=dev)
-    if comm is not None:
-        comm.broadcast(perm_d, src=0)
-    mark("permutations uploaded")
-    y_d = _to_dev(y)
-    C_d = _to_dev(res.C) if r else None
-    W_d = _to_dev(np.ascontiguousarray(res.W_last)) if r else None
-
     want_null_table = res.svd_top is None  # full result surface: every null p-value from scipy
 
     def launch_pc_regressions(U):
@@ -200,83 +186,111 @@ def _association(res, perms, Nnull=1000, local_test=True, show_progress=False, i
             return (sse_d[0].cpu().numpy(), sse_d[1].cpu().numpy(), None)
         return (sse_d[0], sse_d[1], (sse_d[2][0].cpu().numpy(), sse_d[2][1].cpu().numpy()))
 
-    # ---- neighbourhood-level null (:92-103) ----
-    fdrs, fdr_5p_t, fdr_10p_t = None, None, None
-    if local_test:
-        print("computing neighborhood-level FDRs", file=out)
-        maxcorr = max(float(mx.item()), 0.001)  # :101
-        thresholds = np.arange(maxcorr / 4, maxcorr, maxcorr / 400)  # :102
-        edges = _stats.threshold_edges(thresholds)
-        T = len(thresholds)
-        edges_d, thr_d = _to_dev(edges), _to_dev(thresholds)
-        hist = torch.zeros(T, dtype=torch.int64, device=dev)  # summed over the Kl nulls
-        obs = torch.zeros((2, T), dtype=torch.int32, device=dev)
-        # ycond_ = M.y_[:, :Kl] / std (ddof=1) (:94-97) as transposed fp16 hi/lo planes, then
-        # (cells x n) . (n x Kl) on the tensor cores with the histogram epilogue straight out of TMEM
-        ytp = _lib.Planes(Kl, n, dev, zero=True)
-        _lib.perm_stats(y_d, perm_d[:Kl], C_d, W_d, None, None, None, None, None, Kl, planes=ytp)
-        _lib.null_hist_tc(res.planes, n, ytp, Kl, edges_d, float(edges[0]), hist)
-        _lib.obs_hist(res.ncorr, res.valid, edges_d, thr_d, obs[0], obs[1])
-        if comm is not None:  # counts over all shards
-            comm.all_reduce(hist)
-            comm.all_reduce(obs)
-    mark("null kernels launched")
+    def observed_test(U):
+        """Observed phenotype (:64-74): n-sized host arithmetic in float64."""
+        ycond = M.dot(y)
+        ycond = ycond / ycond.std(ddof=1)  # a pandas Series in the reference -> ddof=1
+        ssered = np.array([ycond.dot(ycond)])
+        ssefull = np.array([[np.sum((U[:, :k].dot(U[:, :k].T.dot(ycond)) - ycond) ** 2) for k in ks]])
+        p_all, r2_all = _f_pvalues(ssered, ssefull, ks, n, r)
+        k, p, r2 = (a[0] for a in _pick(p_all, r2_all, ks))
+        if k == max(ks):  # :65-67
+            warnings.warn(("data supported use of {} NAM PCs, which is the maximum considered. "
+                           'Consider allowing more PCs by using the "ks" argument.').format(k))
+        beta = U[:, :k].T.dot(ycond)  # :72
+        yhat = U[:, :k].dot(beta)
+        r2_perpc = (beta / np.sqrt(ycond.dot(ycond))) ** 2  # :74
+        return Namespace(k=k, p=p, r2=r2, beta=beta, yresid_hat=yhat, yresid=ycond, r2_perpc=r2_perpc)
 
-    if idle_work is not None:
-        idle_work()  # host work that needs nothing from below, done while the SVD thread finishes
+    def global_pvalue(p, sse_d):
+        """:84-88 from the regressions of the permuted phenotypes."""
+        sse_host = fetch(sse_d)
+        if sse_host[2] is None:
+            nullp, nullr2 = _f_pvalues(sse_host[0], sse_host[1], ks, n, r)
+            _, nullminps, nullr2s = _pick(nullp, nullr2, ks)
+        else:
+            # min-p per permutation from the device (fp64 incomplete beta, ~1e-13 of scipy); the few that
+            # fall within 1e-9 relative of the decision threshold are re-evaluated with scipy so that the
+            # count below is exactly the reference's
+            nullminps, nullr2s = sse_host[2]
+            thr = p + 1e-8
+            near = np.abs(nullminps - thr) <= 1e-9 * thr
+            if near.any():
+                ix = torch.as_tensor(np.nonzero(near)[0], device=dev)
+                pp, rr2 = _f_pvalues(sse_host[0][ix].cpu().numpy(), sse_host[1][ix].cpu().numpy(), ks, n, r)
+                _, nullminps[near], nullr2s[near] = _pick(pp, rr2, ks)
+        nhit = int((nullminps <= p + 1e-8).sum())
+        if nhit == 0:
+            warnings.warn("global association p-value attained minimal possible value. "
+                          "Consider increasing Nnull")
+        mark("global p done")
+        return (nhit + 1) / (Nnull + 1), nullminps, nullr2s
+
+    # The n x n SVD (_nam.py:105) needs only the Gram: it runs on a helper thread (LAPACK releases the
+    # GIL) while this thread launches the null kernels and writes the per-cell outputs.
+    svd_future = _helper_pool().submit(_nam.svd_of_gram, Gh, res.svd_top)
+
+    fdrs, fdr_5p_t, fdr_10p_t = None, None, None
+    try:
+        # ---- permutations: indices from the host RNG (bit-exact), everything else on the device ----
+        if perms is not None:
+            perm_d = perms.result_device(dev)
+        else:  # a shard other than rank 0: the indices are drawn once, by rank 0
+            perm_d = torch.empty((Nnull, n), dtype=torch.int32, device=dev)
+        if comm is not None:
+            comm.broadcast(perm_d, src=0)
+        mark("permutations uploaded")
+        y_d = _to_dev(y)
+        C_d = _to_dev(res.C) if r else None
+        W_d = _to_dev(np.ascontiguousarray(res.W_last)) if r else None
+
+        # ---- neighbourhood-level null (:92-103) ----
+        if local_test:
+            print("computing neighborhood-level FDRs", file=out)
+            maxcorr = max(float(mx.item()), 0.001)  # :101
+            thresholds = np.arange(maxcorr / 4, maxcorr, maxcorr / 400)  # :102
+            edges = _stats.threshold_edges(thresholds)
+            T = len(thresholds)
+            edges_d, thr_d = _to_dev(edges), _to_dev(thresholds)
+            hist = torch.zeros(T, dtype=torch.int64, device=dev)  # summed over the Kl nulls
+            obs = torch.zeros((2, T), dtype=torch.int32, device=dev)
+            # ycond_ = M.y_[:, :Kl] / std (ddof=1) (:94-97) as transposed fp16 hi/lo planes, then
+            # (cells x n) . (n x Kl) on the tensor cores with the histogram epilogue straight out of TMEM
+            ytp = _lib.Planes(Kl, n, dev, zero=True)
+            _lib.perm_stats(y_d, perm_d[:Kl], C_d, W_d, None, None, None, None, None, Kl, planes=ytp)
+            _lib.null_hist_tc(res.planes, n, ytp, Kl, edges_d, float(edges[0]), hist)
+            _lib.obs_hist(res.ncorr, res.valid, edges_d, thr_d, obs[0], obs[1])
+            if comm is not None:  # counts over all shards
+                comm.all_reduce(hist)
+                comm.all_reduce(obs)
+        mark("null kernels launched")
+
+        if local_test:  # :105-118; needs the histograms only
+            obs_h = obs.cpu().numpy()
+            fdr_vals = _stats.fdr_from_counts(hist.cpu().numpy(), obs_h[0], n_null=Kl)  # _stats.py:64-83
+            num_detected = _stats.tails_from_hist(obs_h[1].astype(np.int64))  # :105-108
+            fdrs = pd.DataFrame({"threshold": thresholds, "fdr": fdr_vals, "num_detected": num_detected})
+            if not np.nanmin(fdr_vals) > 0.05:  # :111-114 (Series.min skips NaN; first row with fdr <= 0.05)
+                fdr_5p_t = thresholds[np.nonzero(fdr_vals <= 0.05)[0][0]]
+            if not np.nanmin(fdr_vals) > 0.1:  # :115-118
+                fdr_10p_t = thresholds[np.nonzero(fdr_vals <= 0.1)[0][0]]
+            mark("fdr table done")
+        if idle_work is not None:
+            idle_work(fdrs, svd_future.done)  # per-cell outputs, for as long as the SVD thread is busy
+    except BaseException:
+        svd_future.result()
+        raise
     U, svs, res.G = svd_future.result()
     res.U, res.svs = U, svs
+    o = observed_test(U)
+    sse_d = launch_pc_regressions(U)
+    if idle_work is not None:
+        idle_work(fdrs, None)  # whatever is left of them, while the GPU runs the regressions
+    pfinal, nullminps, nullr2s = global_pvalue(o.p, sse_d)
 
-    # ---- observed phenotype (:64-74): n-sized host arithmetic in float64 -----------------
-    ycond = M.dot(y)
-    ycond = ycond / ycond.std(ddof=1)  # a pandas Series in the reference -> ddof=1
-    ssered = np.array([ycond.dot(ycond)])
-    ssefull = np.array([[np.sum((U[:, :k].dot(U[:, :k].T.dot(ycond)) - ycond) ** 2) for k in ks]])
-    p_all, r2_all = _f_pvalues(ssered, ssefull, ks, n, r)
-    k, p, r2 = (a[0] for a in _pick(p_all, r2_all, ks))
-    if k == max(ks):  # :65-67
-        warnings.warn(("data supported use of {} NAM PCs, which is the maximum considered. "
-                       'Consider allowing more PCs by using the "ks" argument.').format(k))
-    beta = U[:, :k].T.dot(ycond)  # :72
-    yhat = U[:, :k].dot(beta)
-    r2_perpc = (beta / np.sqrt(ycond.dot(ycond))) ** 2  # :74
-
-    # ---- the global p-value (:84-88) ----
-    sse_host = fetch(launch_pc_regressions(U))
-    if sse_host[2] is None:
-        nullp, nullr2 = _f_pvalues(sse_host[0], sse_host[1], ks, n, r)
-        _, nullminps, nullr2s = _pick(nullp, nullr2, ks)
-    else:
-        # min-p per permutation from the device (fp64 incomplete beta, ~1e-13 of scipy); the few that
-        # fall within 1e-9 relative of the decision threshold are re-evaluated with scipy so that the
-        # count below is exactly the reference's
-        nullminps, nullr2s = sse_host[2]
-        thr = p + 1e-8
-        near = np.abs(nullminps - thr) <= 1e-9 * thr
-        if near.any():
-            ix = torch.as_tensor(np.nonzero(near)[0], device=dev)
-            pp, rr2 = _f_pvalues(sse_host[0][ix].cpu().numpy(), sse_host[1][ix].cpu().numpy(), ks, n, r)
-            _, nullminps[near], nullr2s[near] = _pick(pp, rr2, ks)
-    nhit = int((nullminps <= p + 1e-8).sum())
-    pfinal = (nhit + 1) / (Nnull + 1)
-    if nhit == 0:
-        warnings.warn("global association p-value attained minimal possible value. "
-                      "Consider increasing Nnull")
-
-    mark("global p done")
-    if local_test:
-        obs_h = obs.cpu().numpy()
-        fdr_vals = _stats.fdr_from_counts(hist.cpu().numpy(), obs_h[0], n_null=Kl)  # _stats.py:64-83
-        num_detected = _stats.tails_from_hist(obs_h[1].astype(np.int64))  # :105-108
-        fdrs = pd.DataFrame({"threshold": thresholds, "fdr": fdr_vals, "num_detected": num_detected})
-        if not np.nanmin(fdr_vals) > 0.05:  # :111-114 (Series.min skips NaN; first row with fdr <= 0.05)
-            fdr_5p_t = thresholds[np.nonzero(fdr_vals <= 0.05)[0][0]]
-        if not np.nanmin(fdr_vals) > 0.1:  # :115-118
-            fdr_10p_t = thresholds[np.nonzero(fdr_vals <= 0.1)[0][0]]
-
-    return Namespace(p=pfinal, nullminps=nullminps, k=k, ncorrs=None, fdrs=fdrs,
-                     fdr_5p_t=fdr_5p_t, fdr_10p_t=fdr_10p_t, yresid_hat=yhat, yresid=ycond,
-                     ks=ks, beta=beta, r2=r2, r2_perpc=r2_perpc,
+    return Namespace(p=pfinal, nullminps=nullminps, k=o.k, ncorrs=None, fdrs=fdrs,
+                     fdr_5p_t=fdr_5p_t, fdr_10p_t=fdr_10p_t, yresid_hat=o.yresid_hat, yresid=o.yresid,
+                     ks=ks, beta=o.beta, r2=o.r2, r2_perpc=o.r2_perpc,
                      nullr2_mean=nullr2s.mean(), nullr2_std=nullr2s.std())
 
 
@@ -356,47 +370,64 @@ def association(data, y, sid_name, batches=None, covs=None, donorids=None, ks=No
     print("performing association test", file=out)
     N = stn.N
     dev = res.ncorr.device
-    coef_written = []
+    columns_written = []
 
-    def write_coef_column():
-        """data.obs[key_added] (:228-231) is known as soon as the NAM is residualised: it is copied
-        back and written while the SVD thread is still busy."""
+    def fdr_lookup_tables(fdrs):
+        if fdrs is None:
+            # local_test=False: the reference writes the coefficients and then crashes looking up FDRs
+            # (res.fdrs is None at :235); here the FDR column is simply not written.
+            return np.array([np.inf]), np.array([1.0])
+        return fdrs.threshold.to_numpy(), np.fmin.accumulate(fdrs.fdr.to_numpy())  # Series.min() skips NaN
+
+    def column_steps(fdrs):
+        """data.obs[key_added] (:228-231) is known as soon as the NAM is residualised and the per-cell
+        FDR (:234-237) as soon as the null histograms are: both are copied back and written in the
+        shadow of the SVD thread and of the permutation regressions.  One yield per step."""
         coef = torch.where(res.valid.bool(), res.ncorr, torch.full_like(res.ncorr, float("nan")))
         if stn.graph is not None:
             coef = stn.graph.unpermute(coef)
         host = _to_host_pinned(coef, slot="coef")
+        yield
         if key_added in data.obs:
             warnings.warn(f"Key '{key_added}' already exists in data.obs. Overwriting.")
         data.obs[key_added] = host  # pandas copies on assignment
-        coef_written.append(True)
         mark("coef column written")
+        yield
+        if fdrs is not None:
+            thr, pmin = fdr_lookup_tables(fdrs)
+            coef_d = torch.empty(N, dtype=torch.float64, device=dev)
+            fdr_d = torch.empty(N, dtype=torch.float64, device=dev)
+            _lib.cell_fdr(res.ncorr, res.valid, _to_dev(thr), _to_dev(pmin), coef_d, fdr_d)
+            fdr_h = _to_host_pinned(fdr_d if stn.graph is None else stn.graph.unpermute(fdr_d), slot="fdr")
+            yield
+            data.obs[f"{key_added}_fdr"] = fdr_h
+        columns_written.append(True)
+        mark("obs written")
 
+    def write_columns(fdrs, stop):
+        """Runs the remaining steps, returning early (to be resumed) once ``stop()`` is true."""
+        if not steps:
+            steps.append(column_steps(fdrs))
+        for _ in steps[0]:
+            if stop is not None and stop():
+                return
+
+    steps = []
     early = comm is None and not return_full
     core = _association(res, perms, Nnull=Nnull, local_test=local_test, show_progress=show_progress,
-                        idle_work=write_coef_column if early else None)
+                        idle_work=write_columns if early else None)
     svs = res.svs
+    if columns_written:
+        report()
+        return core.p
 
     # ---- neighbourhood-level outputs (:228-237) ----
     coef_d = torch.empty(N, dtype=torch.float64, device=dev)
     fdr_d = torch.empty(N, dtype=torch.float64, device=dev)
-    if key_added in data.obs and not coef_written:
+    if key_added in data.obs:
         warnings.warn(f"Key '{key_added}' already exists in data.obs. Overwriting.")
-    if core.fdrs is None:
-        # local_test=False: the reference writes the coefficients and then crashes looking up FDRs
-        # (res.fdrs is None at :235); here the FDR column is simply not written.
-        thr, pmin = np.array([np.inf]), np.array([1.0])
-    else:
-        thr = core.fdrs.threshold.to_numpy()
-        pmin = np.fmin.accumulate(core.fdrs.fdr.to_numpy())  # Series.min() skips NaN
+    thr, pmin = fdr_lookup_tables(core.fdrs)
     _lib.cell_fdr(res.ncorr, res.valid, _to_dev(thr), _to_dev(pmin), coef_d, fdr_d)
-    if coef_written:  # only the FDR column is still missing
-        if core.fdrs is not None:
-            fdr_h = _to_host_pinned(fdr_d if stn.graph is None else stn.graph.unpermute(fdr_d), slot="fdr")
-            mark("results on host")
-            data.obs[f"{key_added}_fdr"] = fdr_h
-        mark("obs written")
-        report()
-        return core.p
     both = torch.stack([coef_d, fdr_d], dim=1)  # [cells x 2]
     if comm is not None:  # every rank ends with the full per-cell columns
         pad = torch.zeros((stn.rows_per, 2), dtype=torch.float64, device=dev)
