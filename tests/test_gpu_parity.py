@@ -206,6 +206,42 @@ def test_diffusion_kernels_vs_oracle(cna, n, S, deg):
     np.testing.assert_allclose(b.cpu().numpy(), orc.diffuse(A, s0, 1, self_weight=0.5), rtol=1e-12, atol=1e-14)
 
 
+@pytest.mark.parametrize("n,S,nb", [(3000, 50, 5), (2048, 200, 4), (900, 100, 2), (700, 333, 8)])
+def test_fused_qc_step_matches_separate_kernels(cna, n, S, nb):
+    """The last diffusion step with the batch-kurtosis epilogue = plain step + cna_batch_kurtosis."""
+    import pandas as pd
+    import torch
+    from cna_b200 import _lib
+    from cna_b200.tl import _nam
+    from cna_b200.tl._graph import DeviceGraph, _to_dev
+    A = _random_graph(n, 9, seed=n + S + nb, hub=5)
+    rng = np.random.default_rng(nb)
+    codes = rng.integers(0, S, n)
+    codes[:S] = np.arange(S)
+    g = DeviceGraph(A)
+    vals, diag = g.scaled(1, torch.float32)
+    ld = (S + 7) // 8 * 8
+    cur = torch.zeros((n, ld), dtype=torch.float32, device="cuda")
+    _lib.diffuse_onehot(g.indptr, g.indices, vals, diag, torch.as_tensor(codes, dtype=torch.int32, device="cuda"), S, cur)
+    labels = pd.Index(np.arange(S))
+    batches = pd.Series(rng.permutation(np.arange(S) % nb), index=labels)
+    col_batch, batch_inv = _nam._qc_plan(batches, labels, ld, cur.device)
+    counts = np.bincount(codes, minlength=S).astype(np.float64)
+    inv = torch.as_tensor(1 / counts, device="cuda")
+    inv_ld = torch.zeros(ld, dtype=torch.float64, device="cuda")
+    inv_ld[:S] = inv
+    plain = torch.zeros_like(cur)
+    _lib.diffuse_step(g.indptr, g.indices, vals, diag, cur, plain, S)
+    ub, order, off = _nam._batch_segments(batches.to_numpy())
+    want = torch.empty(n, dtype=torch.float64, device="cuda")
+    _lib.batch_kurtosis(plain, inv, _to_dev(order), _to_dev(off), want)
+    out = torch.zeros_like(cur)
+    kurt = torch.full((n,), -7.0, dtype=torch.float64, device="cuda")
+    _lib.diffuse_step_qc(g.indptr, g.indices, vals, diag, cur, out, S, col_batch, inv_ld, batch_inv, kurt)
+    assert torch.equal(out[:, :S], plain[:, :S])
+    np.testing.assert_allclose(kurt.cpu().numpy(), want.cpu().numpy(), rtol=1e-9, atol=1e-9, equal_nan=True)
+
+
 @pytest.mark.parametrize("N,n,S,r,nb", [(5000, 50, 50, 6, 5), (3000, 37, 45, 0, 1), (4100, 200, 200, 5, 4),
                                        (1000, 100, 120, 12, 10), (2000, 330, 400, 3, 2)])
 def test_resid_pass_gram_null_vs_oracle(cna, N, n, S, r, nb):
