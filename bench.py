@@ -47,7 +47,7 @@ METRIC = "cells/sec through nam()+association(), 1M cells/200 samples/10k perms"
 # CPU sample: same samples / k / steps, cells and permutations scaled down by the same factor
 CPU_SAMPLE_SCALE = 20
 # DRAM traffic of one SpMM launch at config C from the committed `ncu --set full` capture
-# (profiles/r01b_ncu_full_summary.txt: 2.600 GB read + 0.780 GB written; 31.6 GB before the reordering)
+# (profiles/r01c_ncu_spmm_summary.txt: 2.600 GB read + 0.780 GB written; 31.6 GB before the reordering)
 SPMM_DRAM_TRAFFIC_GB = 3.380
 
 
@@ -342,7 +342,7 @@ def run_ours(args):
                    "achieved": spmm["achieved"], "peak": spmm["peak"], "unit": "GB/s", "frac": spmm["frac"],
                    "traffic": SPMM_DRAM_TRAFFIC_GB if (args.config == "C" and world == 1) else None,
                    "traffic_unit": "GB per launch (dram__bytes_read.sum + dram__bytes_write.sum, "
-                                   "profiles/r01b_ncu_full_summary.txt)",
+                                   "profiles/r01c_ncu_spmm_summary.txt)",
                    "algorithmic_gb": spmm["algorithmic_bytes"] / 1e9,
                    "peak_source": peaks["source"] + " (MEASURED_PEAKS.json hbm_gbs)"}
     line = {

@@ -10,6 +10,11 @@ KEYS = [
     ("dram__bytes_write.sum", "DRAM write"),
     ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "DRAM throughput % of peak"),
     ("lts__t_bytes.sum", "L2 bytes"),
+    ("lts__t_sectors.sum", "L2 sectors (x 32 B)"),
+    ("lts__cycles_elapsed.avg", "L2 cycles"),
+    ("l1tex__m_xbar2l1tex_read_bytes.sum", "L2 -> L1 read bytes"),
+    ("l1tex__t_sectors.sum", "L1 sectors looked up (x 32 B)"),
+    ("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "L1 data-pipe wavefronts % of peak"),
     ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "L2 throughput % of peak"),
     ("lts__t_sector_hit_rate.pct", "L2 hit rate %"),
     ("l1tex__t_sector_hit_rate.pct", "L1 hit rate %"),
