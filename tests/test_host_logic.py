@@ -27,6 +27,11 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_lib.EXPORTS)
     assert lib.cna_abi_version() == 2
     assert isinstance(lib.cna_last_error(), bytes)
+    # every entry point is documented: a "replaces:" citation in the header, a row in INTEGRATION.md
+    integration = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    for name in declared:
+        assert name in integration, f"{name} is missing from INTEGRATION.md"
+    assert header.count("replaces:") >= 20
 
 
 def test_no_cpu_fallback():
