@@ -166,8 +166,13 @@ def _nam_device(data, sid_name, nsteps=None, maxnsteps=15, self_weight=1, show_p
     # halo: the edges' column ids were renamed to positions in this buffer when the graph was made
     # resident, so a step is a purely local SpMM once the halo rows have been refreshed
     n_halo = 0 if comm is None else int(g.halo_ids.numel())
-    cur = torch.zeros((g.rows_per + n_halo, ld), dtype=torch.float32, device=dev)
-    nxt = torch.zeros((g.rows_per + n_halo, ld), dtype=torch.float32, device=dev)
+    # On one device every row of both buffers is written before it is read (the one-hot step writes all
+    # ld columns, the later steps whole float4 groups computed from them; columns past the last group
+    # are never touched by any consumer), so the 2 x 4*N*ld bytes are not zero-filled.  A shard also
+    # holds padding rows up to rows_per that only the collectives see: those buffers start as zeros.
+    alloc = torch.empty if comm is None else torch.zeros
+    cur = alloc((g.rows_per + n_halo, ld), dtype=torch.float32, device=dev)
+    nxt = alloc((g.rows_per + n_halo, ld), dtype=torch.float32, device=dev)
     codes = g.permute(codes)  # device rows follow the graph's stored cell order
     if comm is not None:
         own = torch.zeros(g.rows_per, dtype=codes.dtype, device=dev)
