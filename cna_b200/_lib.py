@@ -94,10 +94,12 @@ _SIGNATURES = {
     "cna_split_f16": [_VP, _I64, _I64, _INT, _INT, _VP, _VP, _I64, _I64, _VP],
     "cna_gram_tc": [_VP, _VP, _I64, _I64, _INT, _VP, _VP, _I64, _VP],
     "cna_right_multiply_tc": [_VP, _VP, _I64, _I64, _INT, _VP, _VP, _I64, _INT, _VP, _I64, _VP],
+    "cna_host_refine_order": [_VP, _VP, _I64, _VP, _VP, _I64, _INT, _VP, _INT],
     "cna_null_hist_tc": [_VP, _VP, _I64, _I64, _INT, _VP, _VP, _I64, _INT, _VP, _INT, _DBL, _VP, _VP],
 }
 EXPORTS = sorted(list(_SIGNATURES) + ["cna_abi_version", "cna_last_error", "cna_launch_count",
                                       "cna_gram_tc_workspace", "cna_host_perm_blocks_async"])
+
 
 
 def _declare(lib):
@@ -473,6 +475,24 @@ def host_perm_blocks(block_off, src_pos, num, n_threads=0):
     with _LegacyState() as st:
         _host_call("cna_host_perm_blocks", *st.args(), len(block_off) - 1, block_off.ctypes.data,
                    None if sp is None else sp.ctypes.data, int(num), out.ctypes.data, total, int(n_threads))
+    return out
+
+
+def host_refine_order(indptr, indices, order, inv, block, window=8, n_threads=0):
+    """Greedy re-ordering of the rows inside every ``block`` of a cell order (host arrays in, host
+    array out; see cna_host_refine_order in the header).  ``indptr`` / ``indices``: the caller-order
+    CSR; ``order``: stored position -> caller row; ``inv``: its inverse."""
+    import numpy as np
+    indptr = np.ascontiguousarray(indptr, dtype=np.int32)
+    indices = np.ascontiguousarray(indices, dtype=np.int32)
+    order = np.ascontiguousarray(order, dtype=np.int64)
+    inv = np.ascontiguousarray(inv, dtype=np.int32)
+    n = len(indptr) - 1
+    if len(order) != n or len(inv) != n:
+        raise ValueError("order / inv must have one entry per row")
+    out = np.empty(n, dtype=np.int64)
+    _host_call("cna_host_refine_order", indptr.ctypes.data, indices.ctypes.data, n, order.ctypes.data,
+               inv.ctypes.data, int(block), int(window), out.ctypes.data, int(n_threads))
     return out
 
 

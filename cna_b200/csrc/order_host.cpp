@@ -1,0 +1,101 @@
+// Local refinement of the cell order (host side; no reference counterpart, like csrc/reorder.cu it
+// only decides where a cell's row lives in HBM).
+//
+// The diffusion SpMM is bound by the bytes its row gathers pull from L2 into the SMs' L1 caches
+// (DESIGN.md section 4), and the L1 hit rate is the share of a row's neighbours that the other rows of
+// its CTA -- the 7 rows next to it in the stored order -- gather at about the same time.  The
+// Cuthill-McKee order gives the band structure L2 needs, but inside a breadth-first level consecutive
+// rows are siblings, not neighbours: they share 38 % of their neighbour lists with the 7 rows before
+// them.  This pass keeps every block of `block` consecutive rows where it is (so the band, and with it
+// the L2 hit rate, is untouched) and re-orders the rows inside the block greedily: the next row is the
+// unplaced row of the block with the most edges into the last `window` placed rows.  On the benchmark
+// graph (1M cells, k = 30) that raises the 7-row overlap to 60 % and, in the trace-driven cache model
+// of scripts/spmm_cache_model, the L1 hit rate of the gathers from 23.5 % (= measured) to 44 %.
+//
+// Like the Cuthill-McKee pass this only renames cells: rows keep their edges in their original order,
+// so every floating-point sum is performed exactly as before.  Deterministic (ties go to the smaller
+// position; blocks are independent and may run on any number of threads).
+#include <algorithm>
+#include <atomic>
+#include <cstdint>
+#include <cstdio>
+#include <thread>
+#include <vector>
+
+#include "../../include/cna_b200.h"
+
+namespace cna {
+int set_error(int code, const char *fmt, ...);  // api.cu
+}
+
+namespace {
+
+struct View {
+    const int32_t *indptr;   // caller-order CSR
+    const int32_t *indices;
+    const int64_t *order;    // stored position -> caller row
+    const int32_t *inv;      // caller row -> stored position
+};
+
+// Greedy order of the stored positions [b0, b1); writes the caller rows to out[b0 .. b1).
+void refine_block(const View &g, int64_t b0, int64_t b1, int window, int64_t *out) {
+    const int64_t len = b1 - b0;
+    std::vector<int32_t> score(len, 0), placed_at(len, -1);
+    std::vector<int64_t> seq;  // stored positions in their new order
+    seq.reserve(len);
+    int64_t next_free = 0;
+    auto for_each_neighbour = [&](int64_t u, auto &&fn) {  // u: stored position
+        const int64_t row = g.order[u];
+        for (int32_t e = g.indptr[row]; e < g.indptr[row + 1]; ++e) {
+            const int64_t v = g.inv[g.indices[e]];
+            if (v >= b0 && v < b1) fn(v - b0);
+        }
+    };
+    while (int64_t(seq.size()) < len) {
+        int64_t best = -1;
+        int32_t best_score = 0;
+        const int64_t done = int64_t(seq.size());
+        for (int64_t p = std::max<int64_t>(0, done - window); p < done; ++p)
+            for_each_neighbour(seq[p], [&](int64_t v) {
+                if (placed_at[v] >= 0) return;
+                if (score[v] > best_score || (score[v] == best_score && best >= 0 && v < best)) {
+                    best = v;
+                    best_score = score[v];
+                }
+            });
+        if (best < 0) {  // nothing adjacent to the window: continue with the first unplaced row
+            while (placed_at[next_free] >= 0) ++next_free;
+            best = next_free;
+        }
+        placed_at[best] = int32_t(done);
+        seq.push_back(b0 + best);
+        for_each_neighbour(b0 + best, [&](int64_t v) { ++score[v]; });
+        if (done >= window) for_each_neighbour(seq[done - window], [&](int64_t v) { --score[v]; });
+    }
+    for (int64_t i = 0; i < len; ++i) out[b0 + i] = g.order[seq[i]];
+}
+
+}  // namespace
+
+extern "C" int cna_host_refine_order(const int32_t *indptr, const int32_t *indices, int64_t n,
+                                     const int64_t *order, const int32_t *inv, int64_t block, int window,
+                                     int64_t *order_out, int n_threads) {
+    if (!indptr || !indices || !order || !inv || !order_out || n < 0 || block < 1 || window < 1) {
+        return cna::set_error(CNA_ERR_INVALID, "cna_host_refine_order: bad arguments");
+    }
+    const View g{indptr, indices, order, inv};
+    const int64_t n_blocks = (n + block - 1) / block;
+    unsigned hw = std::thread::hardware_concurrency();
+    int64_t threads = n_threads > 0 ? n_threads : (hw > 1 ? std::min<unsigned>(hw - 1, 64) : 1);
+    threads = std::max<int64_t>(1, std::min<int64_t>(threads, n_blocks));
+    std::atomic<int64_t> next{0};
+    auto work = [&]() {
+        for (int64_t b = next.fetch_add(1); b < n_blocks; b = next.fetch_add(1))
+            refine_block(g, b * block, std::min(n, (b + 1) * block), window, order_out);
+    };
+    std::vector<std::thread> pool;
+    for (int64_t t = 1; t < threads; ++t) pool.emplace_back(work);
+    work();
+    for (auto &t : pool) t.join();
+    return CNA_OK;
+}

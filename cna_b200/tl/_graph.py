@@ -75,6 +75,14 @@ def _bfs_far_node(indptr, indices, n, root, max_levels):
     return int(frontier.min().item())  # min: independent of the order of discovery
 
 
+def local_order_block():
+    """Block size of the host-side local refinement of the cell order of resident graphs
+    (``CNA_B200_LOCAL_ORDER``; 0 = off).  Off by default: the pass costs ~1.5 s per million cells on
+    the host and its effect on the SpMM has so far been established with the cache model only
+    (DESIGN.md section 7)."""
+    return int(os.environ.get("CNA_B200_LOCAL_ORDER", "0"))
+
+
 def cuthill_mckee_order(indptr, indices, n, max_levels=4096, max_roots=8, far_root=True):
     """Cuthill-McKee ordering of a symmetric CSR on the device (csrc/reorder.cu): breadth-first levels
     from a pseudo-peripheral root, each level sorted by (position of its first parent, node id).
@@ -175,6 +183,9 @@ class DeviceGraph:
             mark("graph: cell order computed")
             if res is not None:
                 self.order, self.inv = res
+                if resident and local_order_block() > 0:
+                    self._refine_order(A, local_order_block())
+                    mark("graph: cell order refined")
                 deg = (indptr[1:] - indptr[:-1])[self.order]
                 new_indptr = torch.zeros(self.n_total + 1, dtype=torch.int32, device=indptr.device)
                 new_indptr[1:] = torch.cumsum(deg, 0)
@@ -198,6 +209,15 @@ class DeviceGraph:
         self.nnz = int(indices.numel())
         self.indptr, self.indices, self.data = indptr, indices, data
         self._scaled = {}
+
+    def _refine_order(self, A, block):
+        """Greedy re-ordering of the rows inside every block of the Cuthill-McKee order, on the host
+        (csrc/order_host.cpp): more shared neighbours between the rows of a CTA of the diffusion SpMM."""
+        refined = _lib.host_refine_order(A.indptr, A.indices, self.order.cpu().numpy(), self.inv.cpu().numpy(),
+                                         block)
+        self.order = _to_dev(refined, torch.int64)
+        self.inv = torch.empty(self.n_total, dtype=torch.int32, device=self.order.device)
+        self.inv[self.order] = torch.arange(self.n_total, dtype=torch.int32, device=self.order.device)
 
     def _plan_halo(self, indices, row1):
         """kNN halo of this shard, gathered once: the sorted remote row ids its edges reference

@@ -308,6 +308,16 @@ void *cna_host_perm_blocks_async(uint32_t *key, int *pos, int *has_gauss, double
 int cna_host_perm_done(void *handle);
 int cna_host_perm_wait(void *handle);
 
+/* Host-side local refinement of a cell order (csrc/order_host.cpp): every block of `block`
+ * consecutive stored positions keeps its place, the rows inside it are re-ordered greedily so that the
+ * next row is the unplaced row with the most edges into the last `window` placed rows (more shared
+ * neighbours between the rows of a CTA = more L1 hits in the diffusion SpMM).  indptr / indices: the
+ * caller-order CSR in host memory; order[n]: stored position -> caller row; inv[n]: its inverse;
+ * order_out[n]: the refined stored position -> caller row.  Deterministic; n_threads = 0 picks the
+ * host's core count.  No reference counterpart (a property of the layout in HBM, like cna_bfs_expand). */
+int cna_host_refine_order(const int32_t *indptr, const int32_t *indices, int64_t n, const int64_t *order,
+                          const int32_t *inv, int64_t block, int window, int64_t *order_out, int n_threads);
+
 /* ------------------------------------------------------------------------------------------
  * utilities used by the data generator (not on the timed path)
  * ------------------------------------------------------------------------------------------ */

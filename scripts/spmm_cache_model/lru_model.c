@@ -1,5 +1,6 @@
 // Trace-driven L1 / L2 hit-rate model of the warp-per-row SpMM: 148 SMs, each an LRU
 // cache of `cap` state rows, over one shared LRU L2; warps of an SM advance round-robin, `quad` edges per turn.
+// An odd N reads the files written by local_greedy.c (the refined order of the graph of N - 1 rows).
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -26,11 +27,11 @@ static int lru_access(lru_t *c, int k) {  // 1 = hit
     c->key[n] = k; h_insert(c, n); push_front(c, n); return 0;
 }
 int main(int argc, char **argv) {
-    int N = atoi(argv[1]); int rows_per_cta = atoi(argv[2]); int ctas_per_sm = atoi(argv[3]); int cap = atoi(argv[4]);
+    int N = atoi(argv[1]); int NF = N; if (N % 2 == 1) N -= 1; int rows_per_cta = atoi(argv[2]); int ctas_per_sm = atoi(argv[3]); int cap = atoi(argv[4]);
     int contiguous = atoi(argv[5]);  // 0: global round-robin CTA queue; 1: each SM owns a contiguous range of rows
     int quad = argc > 6 ? atoi(argv[6]) : 4; int K = argc > 7 ? atoi(argv[7]) : 256; int l2cap = argc > 8 ? atoi(argv[8]) : 157000; lru_t l2; lru_init(&l2, l2cap); long l2hits = 0, l2acc = 0;
-    char fn[256]; sprintf(fn, "/tmp/sim/ptr_%d.bin", N); FILE *f = fopen(fn, "rb"); int *ptr = malloc(sizeof(int) * (N + 1)); fread(ptr, 4, N + 1, f); fclose(f);
-    int nnz = ptr[N]; sprintf(fn, "/tmp/sim/idx_%d.bin", N); f = fopen(fn, "rb"); int *idx = malloc(sizeof(int) * (size_t)nnz); fread(idx, 4, nnz, f); fclose(f);
+    char fn[256]; sprintf(fn, "/tmp/sim/ptr_%d.bin", NF); FILE *f = fopen(fn, "rb"); int *ptr = malloc(sizeof(int) * (N + 1)); fread(ptr, 4, N + 1, f); fclose(f);
+    int nnz = ptr[N]; sprintf(fn, "/tmp/sim/idx_%d.bin", NF); f = fopen(fn, "rb"); int *idx = malloc(sizeof(int) * (size_t)nnz); fread(idx, 4, nnz, f); fclose(f);
     int n_cta = (N + rows_per_cta - 1) / rows_per_cta;
     lru_t *cache = malloc(sizeof(lru_t) * NSM); for (int s = 0; s < NSM; ++s) lru_init(&cache[s], cap);
     int nslot = NSM * ctas_per_sm; int *slot_cta = malloc(sizeof(int) * nslot); int *cur = malloc(sizeof(int) * nslot * rows_per_cta);

@@ -274,3 +274,46 @@ def test_obs_to_sample_matches_reference_semantics():
         ref = importlib.util.module_from_spec(spec)
         spec.loader.exec_module(ref)
         pd.testing.assert_frame_equal(got, ref.obs_to_sample(d, ["case", "male", "batch"], "id"))
+
+
+def test_host_refine_order_is_a_blockwise_permutation_and_raises_neighbour_overlap():
+    """csrc/order_host.cpp: rows are only moved inside their block, the result does not depend on the
+    thread count or on how the caller labels the rows, and consecutive rows share more neighbours."""
+    from sklearn.neighbors import NearestNeighbors
+    import scipy.sparse as sp
+    from cna_b200 import _lib
+    rng = np.random.default_rng(5)
+    n, k, block = 6000, 12, 1024
+    pts = rng.normal(size=(n, 3))
+    nbr = NearestNeighbors(n_neighbors=k + 1).fit(pts).kneighbors(pts, return_distance=False)[:, 1:]
+    A = sp.csr_matrix((np.ones(n * k), (np.repeat(np.arange(n), k), nbr.ravel())), shape=(n, n))
+    A = ((A + A.T) > 0).astype(np.float64).tocsr()
+    A.sort_indices()
+    order = np.arange(n, dtype=np.int64)
+    inv = np.arange(n, dtype=np.int32)
+    out = _lib.host_refine_order(A.indptr, A.indices, order, inv, block, window=8, n_threads=1)
+    assert np.array_equal(np.sort(out), np.arange(n))
+    for b in range(0, n, block):
+        assert set(out[b:b + block]) == set(range(b, min(n, b + block)))
+    for threads in (0, 3):
+        assert np.array_equal(out, _lib.host_refine_order(A.indptr, A.indices, order, inv, block, 8, threads))
+
+    def overlap7(seq):  # share of a row's neighbours also gathered by the 7 rows before it
+        nb = [set(A.indices[A.indptr[r]:A.indptr[r + 1]]) for r in seq]
+        vals = [len(nb[i] & set().union(*nb[i - 7:i])) / max(len(nb[i]), 1) for i in range(7, n, 5)]
+        return float(np.mean(vals))
+
+    assert overlap7(out) > overlap7(order) + 0.15
+
+    # the caller's labelling does not matter: relabel the rows, pass the matching order / inv
+    relabel = rng.permutation(n)  # caller row of stored position i
+    back = np.argsort(relabel)
+    P = sp.csr_matrix((np.ones(n), (relabel, np.arange(n))), shape=(n, n))
+    B = (P @ A @ P.T).tocsr()
+    B.sort_indices()
+    out2 = _lib.host_refine_order(B.indptr, B.indices, relabel.astype(np.int64), back.astype(np.int32), block, 8, 2)
+    for b in range(0, n, block):
+        assert set(back[out2[b:b + block]]) == set(range(b, min(n, b + block)))
+    assert abs(overlap7(back[out2]) - overlap7(out)) < 0.05
+    with pytest.raises(_lib.CnaError):
+        _lib.host_refine_order(A.indptr, A.indices, order, inv, 0)
