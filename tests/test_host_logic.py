@@ -317,3 +317,29 @@ def test_host_refine_order_is_a_blockwise_permutation_and_raises_neighbour_overl
     assert abs(overlap7(back[out2]) - overlap7(out)) < 0.05
     with pytest.raises(_lib.CnaError):
         _lib.host_refine_order(A.indptr, A.indices, order, inv, 0)
+
+
+def test_obs_column_adoption_semantics():
+    """association() hands its per-cell result buffers to ``data.obs`` without a second copy: the column
+    must hold the values, keep the buffer alive, survive the next call's overwrite of the same key, and
+    work for any obs index (non-unique labels included)."""
+    from cna_b200.tl._association import _adopt_column
+    N = 5000
+    for index in (pd.RangeIndex(N), pd.Index(np.arange(N) % 7), pd.Index([f"c{i}" for i in range(N)])):
+        obs = pd.DataFrame({"id": np.arange(N) % 50}, index=index)
+
+        def fresh(value):
+            return (torch.arange(N, dtype=torch.float64) + value).numpy()  # the tensor itself goes out of scope
+
+        _adopt_column(obs, "coef", fresh(0.0))
+        assert obs["coef"].dtype == np.float64
+        np.testing.assert_array_equal(obs["coef"].to_numpy(), np.arange(N))
+        snapshot = obs["coef"]
+        _adopt_column(obs, "coef", fresh(7.0))  # the next call overwrites the key with a new buffer
+        np.testing.assert_array_equal(obs["coef"].to_numpy(), np.arange(N) + 7.0)
+        np.testing.assert_array_equal(snapshot.to_numpy(), np.arange(N))
+        nan_col = np.full(N, np.nan)
+        _adopt_column(obs, "coef_fdr", nan_col)
+        assert obs["coef_fdr"].isna().all() and list(obs.columns) == ["id", "coef", "coef_fdr"]
+        obs.iloc[0, obs.columns.get_loc("coef")] = -1.0  # user-side writes keep working
+        assert obs["coef"].iloc[0] == -1.0 and obs["coef"].iloc[1] == 8.0
