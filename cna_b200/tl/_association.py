@@ -43,7 +43,11 @@ def check_inputs(data, y, sid_name, batches, covs, donorids, allow_low_sample_si
     if batches is None:
         batches = pd.Series(np.ones(len(y)), index=y.index)
     if covs is not None:
-        filter_samples = ~(y.isna() | covs.isna().any(axis=1)) & y.index.isin(present)
+        if covs.index.equals(y.index):  # same rows in the same order: the row-wise any() in numpy
+            missing = y.isna().to_numpy() | covs.isna().to_numpy().any(axis=1)
+            filter_samples = pd.Series(~missing & y.index.isin(present), index=y.index)
+        else:  # pandas aligns the two indexes
+            filter_samples = ~(y.isna() | covs.isna().any(axis=1)) & y.index.isin(present)
         if donorids is not None:
             print("WARNING: We currently do not account for multiple samples per donor "
                   "when conditioning on covariates. This conditioning may therefore account "
