@@ -40,39 +40,45 @@ struct View {
 // Greedy order of the stored positions [b0, b1); writes the caller rows to out[b0 .. b1).
 void refine_block(const View &g, int64_t b0, int64_t b1, int window, int64_t *out) {
     const int64_t len = b1 - b0;
-    std::vector<int32_t> score(len, 0), placed_at(len, -1);
-    std::vector<int64_t> seq;  // stored positions in their new order
-    seq.reserve(len);
-    int64_t next_free = 0;
-    auto for_each_neighbour = [&](int64_t u, auto &&fn) {  // u: stored position
-        const int64_t row = g.order[u];
+    // edges that stay inside the block, as block-local positions (one pass over the block's rows)
+    std::vector<int32_t> adj_ptr(len + 1, 0), adj;
+    for (int64_t u = 0; u < len; ++u) {
+        const int64_t row = g.order[b0 + u];
         for (int32_t e = g.indptr[row]; e < g.indptr[row + 1]; ++e) {
             const int64_t v = g.inv[g.indices[e]];
-            if (v >= b0 && v < b1) fn(v - b0);
+            if (v >= b0 && v < b1) adj.push_back(int32_t(v - b0));
         }
-    };
+        adj_ptr[u + 1] = int32_t(adj.size());
+    }
+    std::vector<int32_t> score(len, 0), seq;  // seq: block-local positions in their new order
+    std::vector<char> placed(len, 0);
+    seq.reserve(len);
+    int64_t next_free = 0;
     while (int64_t(seq.size()) < len) {
-        int64_t best = -1;
-        int32_t best_score = 0;
+        int32_t best = -1, best_score = 0;
         const int64_t done = int64_t(seq.size());
         for (int64_t p = std::max<int64_t>(0, done - window); p < done; ++p)
-            for_each_neighbour(seq[p], [&](int64_t v) {
-                if (placed_at[v] >= 0) return;
+            for (int32_t e = adj_ptr[seq[p]]; e < adj_ptr[seq[p] + 1]; ++e) {
+                const int32_t v = adj[e];
+                if (placed[v]) continue;
                 if (score[v] > best_score || (score[v] == best_score && best >= 0 && v < best)) {
                     best = v;
                     best_score = score[v];
                 }
-            });
+            }
         if (best < 0) {  // nothing adjacent to the window: continue with the first unplaced row
-            while (placed_at[next_free] >= 0) ++next_free;
-            best = next_free;
+            while (placed[next_free]) ++next_free;
+            best = int32_t(next_free);
         }
-        placed_at[best] = int32_t(done);
-        seq.push_back(b0 + best);
-        for_each_neighbour(b0 + best, [&](int64_t v) { ++score[v]; });
-        if (done >= window) for_each_neighbour(seq[done - window], [&](int64_t v) { --score[v]; });
+        placed[best] = 1;
+        seq.push_back(best);
+        for (int32_t e = adj_ptr[best]; e < adj_ptr[best + 1]; ++e) ++score[adj[e]];
+        if (done >= window) {
+            const int32_t gone = seq[done - window];
+            for (int32_t e = adj_ptr[gone]; e < adj_ptr[gone + 1]; ++e) --score[adj[e]];
+        }
     }
-    for (int64_t i = 0; i < len; ++i) out[b0 + i] = g.order[seq[i]];
+    for (int64_t i = 0; i < len; ++i) out[b0 + i] = g.order[b0 + seq[i]];
 }
 
 }  // namespace

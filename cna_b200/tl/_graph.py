@@ -77,7 +77,7 @@ def _bfs_far_node(indptr, indices, n, root, max_levels):
 
 def local_order_block():
     """Block size of the host-side local refinement of the cell order of resident graphs
-    (``CNA_B200_LOCAL_ORDER``; 0 = off).  Off by default: the pass costs ~1.5 s per million cells on
+    (``CNA_B200_LOCAL_ORDER``; 0 = off).  Off by default: the pass costs ~0.4 s per million cells on
     the host and its effect on the SpMM has so far been established with the cache model only
     (DESIGN.md section 7)."""
     return int(os.environ.get("CNA_B200_LOCAL_ORDER", "0"))
