@@ -406,20 +406,22 @@ def test_cell_reordering_is_transparent(cna, demo, synth, monkeypatch):
 
 
 @pytest.mark.skipif(os.environ.get("CNA_B200_TEST_LOCAL_ORDER") != "1",
-                    reason="local order refinement is off by default and not yet measured on the GPU "
-                           "(DESIGN.md section 7); set CNA_B200_TEST_LOCAL_ORDER=1 to run")
+                    reason="written without a GPU at hand (round 1 ran out of GPU budget): opt in with "
+                           "CNA_B200_TEST_LOCAL_ORDER=1 until it has been run once")
 def test_local_order_refinement_is_transparent(cna, monkeypatch):
-    """CNA_B200_LOCAL_ORDER: the refined cell order is still a permutation that keeps every block of
-    the Cuthill-McKee order in place, and results do not change."""
+    """The local refinement of the cell order of resident graphs (csrc/order_host.cpp) is still a
+    permutation that keeps every block of the Cuthill-McKee order in place, and results do not change."""
     from cna_b200.tl._graph import DeviceGraph
     A = cases.demo_anndata().obsp["connectivities"]
+    N = A.shape[0]
+    monkeypatch.setenv("CNA_B200_LOCAL_ORDER", "0")
     base = DeviceGraph(A, reorder=True)
     monkeypatch.setenv("CNA_B200_LOCAL_ORDER", "512")
     g = DeviceGraph(A, reorder=True)
-    N = A.shape[0]
     order, inv = g.order.cpu().numpy(), g.inv.cpu().numpy()
     assert sorted(order.tolist()) == list(range(N)) and (inv[order] == np.arange(N)).all()
     cm = base.order.cpu().numpy()
+    assert (order != cm).any()
     for b in range(0, N, 512):
         assert set(order[b:b + 512]) == set(cm[b:b + 512])
     Ap = sp.csr_matrix((g.data.cpu().numpy(), g.indices.cpu().numpy(), g.indptr.cpu().numpy()), shape=A.shape)
@@ -429,11 +431,12 @@ def test_local_order_refinement_is_transparent(cna, monkeypatch):
         pass
     d = D()
     d.obsp = {"connectivities": A}
+    d.obs = cases.demo_anndata().obs
     s0 = np.random.default_rng(0).normal(size=(N, 3))
     monkeypatch.setenv("CNA_B200_REORDER", "1")
-    refined = cna.tl.diffuse(d, s0, 2)
+    refined = cna.tl.diffuse(cna.tl.to_device(d), s0, 2)
     monkeypatch.setenv("CNA_B200_LOCAL_ORDER", "0")
-    np.testing.assert_allclose(refined, cna.tl.diffuse(d, s0, 2), rtol=1e-11, atol=1e-15)
+    np.testing.assert_allclose(refined, cna.tl.diffuse(cna.tl.to_device(d), s0, 2), rtol=1e-11, atol=1e-15)
 
 
 def test_obs_columns_do_not_alias_the_staging_buffer(cna):

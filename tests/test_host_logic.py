@@ -343,3 +343,31 @@ def test_obs_column_adoption_semantics():
         assert obs["coef_fdr"].isna().all() and list(obs.columns) == ["id", "coef", "coef_fdr"]
         obs.iloc[0, obs.columns.get_loc("coef")] = -1.0  # user-side writes keep working
         assert obs["coef"].iloc[0] == -1.0 and obs["coef"].iloc[1] == 8.0
+
+
+def test_device_graph_refine_order_bookkeeping(monkeypatch):
+    """DeviceGraph._refine_order (tensors on the CPU here): the refined order replaces the Cuthill-McKee
+    one, ``inv`` is its inverse, dtypes are what the CUDA entry points expect."""
+    import scipy.sparse as sp
+    from cna_b200.tl import _graph
+    monkeypatch.setattr(_graph, "device", lambda: torch.device("cpu"))
+    rng = np.random.default_rng(2)
+    n = 3000
+    A = sp.random(n, n, density=8 / n, random_state=3, format="csr")
+    A = (A + A.T).tocsr()
+    A.sort_indices()
+    g = object.__new__(_graph.DeviceGraph)
+    g.n_total = n
+    start = rng.permutation(n)
+    g.order = torch.as_tensor(start, dtype=torch.int64)
+    g.inv = torch.empty(n, dtype=torch.int32)
+    g.inv[g.order] = torch.arange(n, dtype=torch.int32)
+    g._refine_order(A, 512)
+    assert g.order.dtype == torch.int64 and g.inv.dtype == torch.int32
+    order, inv = g.order.numpy(), g.inv.numpy()
+    assert sorted(order.tolist()) == list(range(n)) and (inv[order] == np.arange(n)).all()
+    for b in range(0, n, 512):
+        assert set(order[b:b + 512]) == set(start[b:b + 512])
+    assert _graph.local_order_block() == _graph.LOCAL_ORDER_BLOCK
+    monkeypatch.setenv("CNA_B200_LOCAL_ORDER", "0")
+    assert _graph.local_order_block() == 0
