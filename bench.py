@@ -300,7 +300,7 @@ def run_ours(args):
         from cna_b200.sharded import shard_to_device
         handle = shard_to_device(data)
         step_dev = lambda: cna.tl.association(handle, **kw)  # noqa: E731
-        step_e2e = lambda: cna.tl.association(shard_to_device(data), **kw)  # noqa: E731
+        step_e2e = lambda: cna.tl.association(shard_to_device(data, resident=False), **kw)  # noqa: E731
     else:
         handle = cna.tl.to_device(data)
         step_dev = lambda: cna.tl.association(handle, **kw)  # noqa: E731

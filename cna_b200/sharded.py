@@ -100,14 +100,16 @@ class ShardedData:
     ``cna_b200.tl.association`` / ``nam`` in place of ``data``; results are written to the full
     ``data.obs`` on every rank."""
 
-    def __init__(self, data, comm=None):
+    def __init__(self, data, comm=None, resident=True):
+        """``resident=False``: a shard built for one call (cheaper cell ordering: no pseudo-peripheral
+        root sweep, no local refinement), like the graph ``association(data)`` builds for a host object."""
         from .tl._graph import DeviceGraph, get_connectivity
         self._host = data
         self.comm = comm or Comm()
         A = get_connectivity(data)
         n_total = A.shape[0]
         r0, r1, rows_per = shard_bounds(n_total, self.comm.world, self.comm.rank)
-        self.graph = DeviceGraph(A, shard=(self.comm, r0, r1, rows_per))
+        self.graph = DeviceGraph(A, shard=(self.comm, r0, r1, rows_per), resident=resident)
         self.obsp = getattr(data, "obsp", None)
         self.uns = getattr(data, "uns", None)
         self._codes = {}
@@ -117,5 +119,5 @@ class ShardedData:
         return self._host.obs
 
 
-def shard_to_device(data, comm=None):
-    return data if isinstance(data, ShardedData) else ShardedData(data, comm)
+def shard_to_device(data, comm=None, resident=True):
+    return data if isinstance(data, ShardedData) else ShardedData(data, comm, resident=resident)
