@@ -216,12 +216,18 @@ class DeviceGraph:
 
     def _refine_order(self, A, block):
         """Greedy re-ordering of the rows inside every block of the Cuthill-McKee order, on the host
-        (csrc/order_host.cpp): more shared neighbours between the rows of a CTA of the diffusion SpMM."""
-        refined = _lib.host_refine_order(A.indptr, A.indices, self.order.cpu().numpy(), self.inv.cpu().numpy(),
-                                         block)
-        self.order = _to_dev(refined, torch.int64)
-        self.inv = torch.empty(self.n_total, dtype=torch.int32, device=self.order.device)
-        self.inv[self.order] = torch.arange(self.n_total, dtype=torch.int32, device=self.order.device)
+        (csrc/order_host.cpp): more shared neighbours between the rows of a CTA of the diffusion SpMM.
+        A pure layout optimisation: if it cannot be done the Cuthill-McKee order stays, with a warning."""
+        try:
+            refined = _lib.host_refine_order(A.indptr, A.indices, self.order.cpu().numpy(),
+                                             self.inv.cpu().numpy(), block)
+            order = _to_dev(refined, torch.int64)
+            inv = torch.empty(self.n_total, dtype=torch.int32, device=order.device)
+            inv[order] = torch.arange(self.n_total, dtype=torch.int32, device=order.device)
+        except Exception as exc:  # noqa: BLE001 - any failure leaves a valid (unrefined) order behind
+            warnings.warn(f"cna_b200: local refinement of the cell order skipped ({exc})")
+            return
+        self.order, self.inv = order, inv
 
     def _plan_halo(self, indices, row1):
         """kNN halo of this shard, gathered once: the sorted remote row ids its edges reference
