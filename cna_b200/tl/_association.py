@@ -97,7 +97,10 @@ def _adopt_column(obs, key, values):
     """``obs[key] = values`` without copying the N values a second time: the column adopts
     ``values`` (an array nothing else writes to; the ndarray keeps its buffer alive), where assigning
     the bare ndarray makes pandas copy it (~1 ms per million cells, on the critical path of a call)."""
-    obs[key] = pd.Series(values, index=obs.index, copy=False)
+    try:
+        obs[key] = pd.Series(values, index=obs.index, copy=False)
+    except Exception:  # noqa: BLE001 - an obs container that cannot adopt a Series gets the plain copy
+        obs[key] = values
 
 
 def default_ks(n):
