@@ -342,7 +342,8 @@ def run_ours(args):
                    "achieved": spmm["achieved"], "peak": spmm["peak"], "unit": "GB/s", "frac": spmm["frac"],
                    "traffic": SPMM_DRAM_TRAFFIC_GB if (args.config == "C" and world == 1) else None,
                    "traffic_unit": "GB per launch (dram__bytes_read.sum + dram__bytes_write.sum, "
-                                   "profiles/r01c_ncu_spmm_summary.txt)",
+                                   "profiles/r01c_ncu_spmm_summary.txt; captured on the Cuthill-McKee order, "
+                                   "before its block-local refinement was enabled)",
                    "algorithmic_gb": spmm["algorithmic_bytes"] / 1e9,
                    "peak_source": peaks["source"] + " (MEASURED_PEAKS.json hbm_gbs)"}
     line = {
