@@ -35,7 +35,7 @@ def load():
                 "Run `python -m cna_b200.build` on a machine with nvcc 12.9.") from exc
     lib = ctypes.CDLL(LIB_PATH)
     _declare(lib)
-    if lib.cna_abi_version() != 2:
+    if lib.cna_abi_version() != 3:
         raise ImportError("cna_b200: ABI version mismatch between _lib.py and libcna_b200.so")
     _lib = lib
     return lib
@@ -58,6 +58,7 @@ class ResidArgs(ctypes.Structure):
         ("y", _VP),
         ("x_out", _VP), ("ld_x", _I64), ("kurt", _VP), ("ncorr", _VP), ("row_valid", _VP),
         ("x16_hi", _VP), ("x16_lo", _VP), ("ld16", _I64),
+        ("qc_kurt", _VP), ("qc_median", _VP),
     ]
 
 
@@ -80,6 +81,9 @@ _SIGNATURES = {
     "cna_perm_minp": [_VP, _VP, _I64, _VP, _INT, _INT, _INT, _VP, _VP, _VP, _VP],
     "cna_null_hist": [_VP, _I64, _I64, _INT, _VP, _I64, _INT, _VP, _INT, _DBL, _VP, _VP],
     "cna_obs_hist": [_VP, _VP, _I64, _VP, _VP, _INT, _VP, _VP, _VP],
+    "cna_obs_hist_dev": [_VP, _VP, _I64, _VP, _VP, _INT, _VP, _VP, _VP, _VP],
+    "cna_median_f64": [_VP, _VP, _I64, _VP, _VP, _I64, _VP],
+    "cna_fdr_thresholds": [_VP, _INT, _VP, _VP, _VP, _VP],
     "cna_absmax": [_VP, _VP, _I64, _VP, _VP],
     "cna_cell_fdr": [_VP, _VP, _I64, _VP, _VP, _INT, _VP, _VP, _VP],
     "cna_knn_bruteforce": [_VP, _I64, _INT, _INT, _VP, _VP, _VP],
@@ -96,9 +100,11 @@ _SIGNATURES = {
     "cna_right_multiply_tc": [_VP, _VP, _I64, _I64, _INT, _VP, _VP, _I64, _INT, _VP, _I64, _VP],
     "cna_host_refine_order": [_VP, _VP, _I64, _VP, _VP, _I64, _INT, _VP, _INT],
     "cna_null_hist_tc": [_VP, _VP, _I64, _I64, _INT, _VP, _VP, _I64, _INT, _VP, _INT, _DBL, _VP, _VP],
+    "cna_null_hist_tc_dev": [_VP, _VP, _I64, _I64, _INT, _VP, _VP, _I64, _INT, _VP, _INT, _VP, _DBL, _VP, _VP],
 }
 EXPORTS = sorted(list(_SIGNATURES) + ["cna_abi_version", "cna_last_error", "cna_launch_count",
-                                      "cna_gram_tc_workspace", "cna_host_perm_blocks_async"])
+                                      "cna_gram_tc_workspace", "cna_host_perm_blocks_async",
+                                      "cna_median_workspace"])
 
 
 
@@ -111,6 +117,8 @@ def _declare(lib):
     lib.cna_launch_count.argtypes = []
     lib.cna_gram_tc_workspace.restype = ctypes.c_int64
     lib.cna_gram_tc_workspace.argtypes = [ctypes.c_int]
+    lib.cna_median_workspace.restype = ctypes.c_int64
+    lib.cna_median_workspace.argtypes = []
     lib.cna_host_perm_blocks_async.restype = ctypes.c_void_p
     lib.cna_host_perm_blocks_async.argtypes = _SIGNATURES["cna_host_perm_blocks"]
     for name, args in _SIGNATURES.items():
@@ -238,8 +246,12 @@ def batch_kurtosis(s, inv_count, seg_order, seg_off, kurt):
 
 
 def resid_pass(s, inv_count, colmap, row_keep, C, Wt, seg_order, seg_off, y, x_out, kurt, ncorr, row_valid,
-               planes=None):
+               planes=None, qc_kurt=None, qc_median=None):
+    """``row_keep`` (uint8 mask) or ``qc_kurt`` + ``qc_median`` (device: keep iff kurt < max(6, 2 median))
+    decide which rows survive the QC; both None keeps every row."""
     a = ResidArgs()
+    a.qc_kurt = _ptr(qc_kurt, torch.float64, "qc_kurt", allow_none=True) if row_keep is None else None
+    a.qc_median = _ptr(qc_median, torch.float64, "qc_median", allow_none=True) if a.qc_kurt else None
     a.s = _ptr(s, torch.float32, "s"); a.ld_s = s.shape[1]; a.n_rows = s.shape[0]
     a.inv_count = _ptr(inv_count, torch.float64, "inv_count")
     a.colmap = _ptr(colmap, torch.int32, "colmap"); a.n = colmap.numel()
@@ -319,6 +331,55 @@ def obs_hist(ncorr, row_valid, edges, thresholds, rank_hist, det_hist):
                                _ptr(edges, torch.float64, "edges"), _ptr(thresholds, torch.float64, "thresholds"),
                                edges.numel(), _ptr(rank_hist, torch.int32, "rank_hist"),
                                _ptr(det_hist, torch.int32, "det_hist"), _stream())
+
+
+_MEDIAN_WS = {}
+MEDIAN_SKIP = None  # float64 scalar whose bit pattern cna_median_f64 ignores (set on first use)
+
+
+def median_skip_value():
+    """The float64 (a signalling-NaN bit pattern) that marks entries ``median`` must ignore."""
+    global MEDIAN_SKIP
+    if MEDIAN_SKIP is None:
+        import numpy as np
+        MEDIAN_SKIP = np.array([0x7FF4DEADBEEF0001], dtype=np.uint64).view(np.float64)
+    return MEDIAN_SKIP
+
+
+def median(v, valid, out):
+    """out[0] = np.median of the float64 device vector ``v`` restricted to ``valid`` (uint8 mask or None)
+    and to entries that are not the skip pattern; NaN if any such entry is NaN or none exists.
+    out[1] = number of entries considered.  Stays on the device: nothing is copied back."""
+    need = int(load().cna_median_workspace())
+    ws = _MEDIAN_WS.get(v.device)
+    if ws is None:
+        ws = _MEDIAN_WS[v.device] = torch.empty(need, dtype=torch.uint8, device=v.device)
+    _call("cna_median_f64", _ptr(v, torch.float64, "v"), _ptr(valid, torch.uint8, "valid", allow_none=True),
+          v.numel(), _ptr(out, torch.float64, "out"), ws.data_ptr(), need, _stream())
+
+
+def fdr_thresholds(maxabs, thresholds, edges, count):
+    """Thresholds / histogram edges of _association.py:101-102 + _stats.py:51 from the device-resident
+    max |ncorr| (``maxabs`` [1] float64); ``count`` [1] int32 receives their number."""
+    _call("cna_fdr_thresholds", _ptr(maxabs, torch.float64, "maxabs"), thresholds.numel(),
+          _ptr(thresholds, torch.float64, "thresholds"), _ptr(edges, torch.float64, "edges"),
+          _ptr(count, torch.int32, "count"), _stream())
+
+
+def obs_hist_dev(ncorr, row_valid, edges, thresholds, count, rank_hist, det_hist):
+    _call("cna_obs_hist_dev", _ptr(ncorr, torch.float64, "ncorr"),
+          _ptr(row_valid, torch.uint8, "row_valid", allow_none=True), ncorr.numel(),
+          _ptr(edges, torch.float64, "edges"), _ptr(thresholds, torch.float64, "thresholds"), edges.numel(),
+          _ptr(count, torch.int32, "count"), _ptr(rank_hist, torch.int32, "rank_hist"),
+          _ptr(det_hist, torch.int32, "det_hist"), _stream())
+
+
+def null_hist_tc_dev(xp, n, ytp, n_null, edges, count, hist):
+    """``null_hist_tc`` with the number of edges read from the device (``count`` [1] int32)."""
+    _call("cna_null_hist_tc_dev", _ptr(xp.hi, torch.float16, "xh"), _ptr(xp.lo, torch.float16, "xl"), xp.ld,
+          xp.rows, int(n), _ptr(ytp.hi, torch.float16, "yth"), _ptr(ytp.lo, torch.float16, "ytl"), ytp.ld,
+          int(n_null), _ptr(edges, torch.float64, "edges"), edges.numel(), _ptr(count, torch.int32, "count"),
+          0.0, _ptr(hist, torch.int64, "hist"), _stream())
 
 
 def absmax(v, row_valid, out):

@@ -226,11 +226,15 @@ __device__ __forceinline__ int upper_le(const double *t, int n, double v) {
 
 __global__ void obs_hist_kernel(const double *__restrict__ ncorr, const uint8_t *__restrict__ valid,
                                 int64_t n, const double *__restrict__ edges,
-                                const double *__restrict__ thr, int n_edges, uint32_t *rank_hist,
+                                const double *__restrict__ thr, int n_edges_cap,
+                                const int32_t *__restrict__ n_edges_dev, uint32_t *rank_hist,
                                 uint32_t *det_hist) {
+    // n_edges_dev != NULL: the number of edges is whatever cna_fdr_thresholds left on the device
+    // (n_edges_cap then only sizes the shared-memory tables)
     extern __shared__ double sm[];
-    double *e = sm, *t = sm + n_edges;
-    uint32_t *hr = reinterpret_cast<uint32_t *>(t + n_edges), *hd = hr + n_edges;
+    double *e = sm, *t = sm + n_edges_cap;
+    uint32_t *hr = reinterpret_cast<uint32_t *>(t + n_edges_cap), *hd = hr + n_edges_cap;
+    const int n_edges = n_edges_dev ? min(__ldg(n_edges_dev), n_edges_cap) : n_edges_cap;
     for (int i = threadIdx.x; i < n_edges; i += blockDim.x) {
         e[i] = edges[i];
         t[i] = thr[i];
@@ -354,18 +358,25 @@ int cna_absmax(const double *v, const uint8_t *row_valid, int64_t n_rows, double
     return CNA_OK;
 }
 
-int cna_obs_hist(const double *ncorr, const uint8_t *row_valid, int64_t n_rows, const double *edges,
-                 const double *thresholds, int n_edges, uint32_t *rank_hist, uint32_t *det_hist,
-                 void *stream) {
+int cna_obs_hist_dev(const double *ncorr, const uint8_t *row_valid, int64_t n_rows, const double *edges,
+                     const double *thresholds, int n_edges, const int32_t *n_edges_dev, uint32_t *rank_hist,
+                     uint32_t *det_hist, void *stream) {
     CNA_REQUIRE(n_edges > 0 && n_edges <= 2048, "cna_obs_hist: 1..2048 edges supported");
     if (n_rows <= 0) return CNA_OK;
     int64_t blocks = (n_rows + 255) / 256;
     unsigned grid = unsigned(blocks < 592 ? blocks : 592);
     size_t smem = (2 * sizeof(double) + 2 * sizeof(uint32_t)) * n_edges;
     obs_hist_kernel<<<grid, 256, smem, as_stream(stream)>>>(ncorr, row_valid, n_rows, edges, thresholds,
-                                                          n_edges, rank_hist, det_hist);
+                                                          n_edges, n_edges_dev, rank_hist, det_hist);
     CNA_LAUNCHED("obs_hist_kernel");
     return CNA_OK;
+}
+
+int cna_obs_hist(const double *ncorr, const uint8_t *row_valid, int64_t n_rows, const double *edges,
+                 const double *thresholds, int n_edges, uint32_t *rank_hist, uint32_t *det_hist,
+                 void *stream) {
+    return cna_obs_hist_dev(ncorr, row_valid, n_rows, edges, thresholds, n_edges, nullptr, rank_hist, det_hist,
+                            stream);
 }
 
 int cna_cell_fdr(const double *ncorr, const uint8_t *row_valid, int64_t n_rows,

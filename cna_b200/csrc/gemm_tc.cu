@@ -204,10 +204,12 @@ struct XbTcArgs {
     int64_t ld_out;
     // HIST
     const double *edges;
-    int n_edges;
+    int n_edges;               // number of edges; with n_edges_dev: capacity of the tables
+    const int *n_edges_dev;    // optional: the count left on the device by cna_fdr_thresholds
     unsigned long long *hist;  // [n_edges], summed over all output columns
     double inv_n;
-    float reject_below;
+    float reject_below;        // with n_edges_dev: derived from edges[0] inside the kernel
+    double reject_scale;       // n^2 (1 - 1e-5)
 };
 
 template <Epi E>
@@ -231,6 +233,13 @@ xb_tc_kernel(const __grid_constant__ CUtensorMap tm_ah, const __grid_constant__ 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_row_tiles = int((a.n_rows + kBM - 1) / kBM);
     const int n_chunks = (a.n_out + kBN - 1) / kBN;
+    int n_edges = a.n_edges;
+    float reject_below = a.reject_below;
+    if (E == Epi::HIST && a.n_edges_dev) {
+        n_edges = min(__ldg(a.n_edges_dev), a.n_edges);
+        const double rb = (n_edges > 0 ? __ldg(a.edges) : 1e300) * a.reject_scale;
+        reject_below = rb > 0.0 ? float(rb) * (1.0f - 1e-6f) : 0.f;
+    }
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) {
@@ -249,20 +258,20 @@ xb_tc_kernel(const __grid_constant__ CUtensorMap tm_ah, const __grid_constant__ 
     }
     if (warp == 1) tmem_alloc(tmem_slot, 512);
     if (E == Epi::HIST) {
-        for (int t = threadIdx.x; t < a.n_edges; t += blockDim.x) {
+        for (int t = threadIdx.x; t < n_edges; t += blockDim.x) {
             edges_s[t] = a.edges[t];
             hist_s[t] = 0;
             // fp32 copies with a 2e-6 relative guard band (the fp32 value of z^2 carries < 3e-7 of
             // rounding): a product strictly inside (elo[b], ehi[b]) is in bin b beyond doubt
             elo_s[t] = float(a.edges[t] * (1.0 + 2e-6));
-            ehi_s[t] = (t + 1 < a.n_edges) ? float(a.edges[t + 1] * (1.0 - 2e-6)) : 3.0e38f;
+            ehi_s[t] = (t + 1 < n_edges) ? float(a.edges[t + 1] * (1.0 - 2e-6)) : 3.0e38f;
         }
-        if (threadIdx.x == 32) {
+        if (threadIdx.x == 32 && n_edges > 0) {
             // the thresholds are (close to) an arithmetic progression, so sqrt(edge) is close to
             // linear in the bin index: a one-multiply first guess, corrected against the table
-            double s0 = sqrt(fmax(a.edges[0], 0.0)), s1 = sqrt(fmax(a.edges[a.n_edges - 1], 0.0));
+            double s0 = sqrt(fmax(a.edges[0], 0.0)), s1 = sqrt(fmax(a.edges[n_edges - 1], 0.0));
             guess[0] = float(s0);
-            guess[1] = (s1 > s0) ? float((a.n_edges - 1) / (s1 - s0)) : 0.f;
+            guess[1] = (s1 > s0) ? float((n_edges - 1) / (s1 - s0)) : 0.f;
         }
     }
     tc_fence_before();
@@ -359,7 +368,7 @@ xb_tc_kernel(const __grid_constant__ CUtensorMap tm_ah, const __grid_constant__ 
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
                             float v = __uint_as_float(r[j]);
-                            if (v * v >= a.reject_below && col0 + j < a.n_out) mask |= 1u << j;
+                            if (v * v >= reject_below && col0 + j < a.n_out) mask |= 1u << j;
                         }
                         if (!row_ok) mask = 0;
                         // compact the survivors of the whole warp into its queue
@@ -382,13 +391,13 @@ xb_tc_kernel(const __grid_constant__ CUtensorMap tm_ah, const __grid_constant__ 
                             const float vf = qv[i];
                             const float zf = vf * inv_n_f, z2f = zf * zf;
                             int b = int((sqrtf(z2f) - g0) * g1);
-                            b = max(0, min(b, a.n_edges - 1));
+                            b = max(0, min(b, n_edges - 1));
                             if (!(z2f > elo_s[b] && z2f < ehi_s[b])) {
                                 // within rounding distance of an edge (or a missed guess): decide in fp64
                                 const double z = double(vf) * a.inv_n;
                                 const double z2 = z * z;
                                 if (!(z2 >= edges_s[0])) continue;
-                                while (b + 1 < a.n_edges && edges_s[b + 1] <= z2) ++b;  // largest b with edges[b] <= z2
+                                while (b + 1 < n_edges && edges_s[b + 1] <= z2) ++b;  // largest b with edges[b] <= z2
                                 while (b > 0 && edges_s[b] > z2) --b;
                             }
                             atomicAdd(hist_s + b, 1u);
@@ -410,7 +419,7 @@ xb_tc_kernel(const __grid_constant__ CUtensorMap tm_ah, const __grid_constant__ 
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, 512);
     if (E == Epi::HIST)  // a CTA sees < 2^32 products per bin between flushes (rows/148 x columns)
-        for (int t = threadIdx.x; t < a.n_edges; t += blockDim.x)
+        for (int t = threadIdx.x; t < n_edges; t += blockDim.x)
             if (hist_s[t]) atomicAdd(a.hist + t, static_cast<unsigned long long>(hist_s[t]));
 }
 
@@ -767,9 +776,9 @@ int cna_right_multiply_tc(const void *xh, const void *xl, int64_t ld16, int64_t 
     return xb_tc_launch(Epi::STORE, xh, xl, ld16, n_rows, n, bth, btl, ld16_b, n_out, a, as_stream(stream));
 }
 
-int cna_null_hist_tc(const void *xh, const void *xl, int64_t ld16, int64_t n_rows, int n, const void *yth,
-                     const void *ytl, int64_t ld16_y, int n_null, const double *edges, int n_edges, double edge0,
-                     uint64_t *hist, void *stream) {
+int cna_null_hist_tc_dev(const void *xh, const void *xl, int64_t ld16, int64_t n_rows, int n, const void *yth,
+                         const void *ytl, int64_t ld16_y, int n_null, const double *edges, int n_edges,
+                         const int32_t *n_edges_dev, double edge0, uint64_t *hist, void *stream) {
     CNA_REQUIRE(n_edges > 0 && n_edges <= 1024, "cna_null_hist_tc: 1..1024 edges supported (got %d)", n_edges);
     CNA_REQUIRE(n_rows * int64_t(n_null) / 64 < (int64_t(1) << 32), "cna_null_hist_tc: too many products per CTA");
     CNA_REQUIRE(edges && hist, "cna_null_hist_tc: null pointer");
@@ -777,11 +786,20 @@ int cna_null_hist_tc(const void *xh, const void *xl, int64_t ld16, int64_t n_row
     XbTcArgs a{};
     a.edges = edges;
     a.n_edges = n_edges;
+    a.n_edges_dev = n_edges_dev;
     a.hist = reinterpret_cast<unsigned long long *>(hist);
     a.inv_n = 1.0 / double(n);
-    double rb = edge0 * double(n) * double(n) * (1.0 - 1e-5);
+    a.reject_scale = double(n) * double(n) * (1.0 - 1e-5);
+    double rb = edge0 * a.reject_scale;
     a.reject_below = rb > 0.0 ? float(rb) * (1.0f - 1e-6f) : 0.f;
     return xb_tc_launch(Epi::HIST, xh, xl, ld16, n_rows, n, yth, ytl, ld16_y, n_null, a, as_stream(stream));
+}
+
+int cna_null_hist_tc(const void *xh, const void *xl, int64_t ld16, int64_t n_rows, int n, const void *yth,
+                     const void *ytl, int64_t ld16_y, int n_null, const double *edges, int n_edges, double edge0,
+                     uint64_t *hist, void *stream) {
+    return cna_null_hist_tc_dev(xh, xl, ld16, n_rows, n, yth, ytl, ld16_y, n_null, edges, n_edges, nullptr, edge0,
+                                hist, stream);
 }
 
 int64_t cna_gram_tc_workspace(int n) {

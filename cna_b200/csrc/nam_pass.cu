@@ -91,7 +91,7 @@ batch_kurtosis_kernel(const float *__restrict__ s, int64_t ld, int64_t n_rows,
 }
 
 // ---------------------------------------------------------------------------------------------
-// fused select / centre / residualise / standardise / ncorr pass
+// fused select / centre / residualise / standardise / ncorr pass: generic kernel (large n.(r + batches))
 // ---------------------------------------------------------------------------------------------
 // A warp owns R consecutive rows at a time: every W / C coefficient read from shared memory is used
 // for R rows, and the R independent shuffle reductions overlap each other's latency.
@@ -132,6 +132,11 @@ __global__ void __launch_bounds__(256) resid_kernel(cna_resid_args a) {
     __syncthreads();
 
     int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    double qc_thr = 0.0;
+    if (a.qc_kurt) {  // _nam.py:94: max(6, 2 * median) with Python's max (a NaN median gives 6)
+        const double two_med = 2.0 * a.qc_median[0];
+        qc_thr = two_med > 6.0 ? two_med : 6.0;
+    }
     double *pw = proj + w * R * r;
     double *rb = rowbuf + w * n, *mb = means + w * nb;
     const double dn = double(n);
@@ -168,7 +173,9 @@ __global__ void __launch_bounds__(256) resid_kernel(cna_resid_args a) {
         for (int i = 0; i < R; ++i) {
             double var0 = warp_sum(ss[i]) / (dn - 1.0);
             const int64_t row = row0 + i;
-            bool keep = (row < a.n_rows) && (a.row_keep ? (a.row_keep[row] != 0) : true);
+            bool keep = row < a.n_rows;
+            if (keep && a.row_keep) keep = a.row_keep[row] != 0;
+            else if (keep && a.qc_kurt) keep = a.qc_kurt[row] < qc_thr;  // NaN -> dropped, _nam.py:96
             valid[i] = keep && !(var0 == 0.0);  // _association.py:182-185
         }
         // rank-r update X <- X - (X Wt^T) C^T   (_nam.py:133-135 / :146-148 with M = I - C.W)
@@ -298,6 +305,246 @@ __global__ void __launch_bounds__(256) resid_kernel(cna_resid_args a) {
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// fused pass, formulation as linear functionals of the raw row (the default kernel)
+// ---------------------------------------------------------------------------------------------
+// Everything the pass needs from a row x (selected samples, scaled by 1/C) is a handful of linear
+// functionals of x plus two sums of squares:
+//     mean = 1.x / n            p = W.x  (r values; W.1 = 0 because the columns of C are centred)
+//     bmean_b = (1/|b|) sum_{k in b} x_k        dot = y.x
+//     x' = x - mean - C.p       (_nam.py:122, :133-148)        ss0 = |x - mean|^2,  ss = |x'|^2, s1 = 1.x'
+// so the row is read once into registers (lanes own columns), the m1 = 2 + r + nb functionals are
+// accumulated against one shared-memory table F [m1 x n] and reduced 16 at a time with a transposing
+// butterfly (3 instructions per reduced value instead of 15 for one shuffle tree each), and the batch
+// means / coefficient follow from the functionals:
+//     batch mean of x' = bmean_b - mean - Cbar_b.p,     x'.y = dot - mean * sum(y) - (C^T y).p
+// A warp owns R rows at a time, so every table entry read from shared memory serves R rows.
+struct ResidTables {
+    int m1;      // number of functionals: 0 = sum, 1 = y, 2 .. 2+r = W rows, then the batch means
+    int nbk;     // number of batch rows (0 when the kurtosis is not wanted)
+};
+
+// Reduce v[0..16) across the warp: afterwards lane L holds the warp total of v[L >> 1] in v[0].
+template <int HALF>
+__device__ __forceinline__ void butterfly_step(double (&v)[16], int lane) {
+    constexpr int BIT = 2 * HALF;
+    const bool upper = (lane & BIT) != 0;
+#pragma unroll
+    for (int j = 0; j < HALF; ++j) {
+        const double send = upper ? v[j] : v[j + HALF];
+        const double keep = upper ? v[j + HALF] : v[j];
+        v[j] = keep + __shfl_xor_sync(kFull, send, BIT);
+    }
+}
+__device__ __forceinline__ void butterfly16(double (&v)[16], int lane) {
+    butterfly_step<8>(v, lane);
+    butterfly_step<4>(v, lane);
+    butterfly_step<2>(v, lane);
+    butterfly_step<1>(v, lane);
+    v[0] += __shfl_xor_sync(kFull, v[0], 1);
+}
+
+template <int NQ, int R>
+__global__ void __launch_bounds__(256, 2) resid_lin_kernel(cna_resid_args a, ResidTables tb) {
+    extern __shared__ double sm[];
+    const int warps = blockDim.x >> 5;
+    const int n = a.n, r = a.r, nb = a.n_batches, m1 = tb.m1, nbk = tb.nbk;
+    double *F = sm;                          // [m1][n]
+    double *Ct = F + size_t(m1) * n;         // [r][n]
+    double *invc = Ct + size_t(r) * n;       // [n]
+    double *cbar = invc + n;                 // [nbk][r] batch means of the columns of C
+    double *cy = cbar + nbk * r;             // [r] C^T y, then [1] sum(y)
+    double *tot = cy + r + 1;                // [warps][R][m1 + 3]
+    int *colmap = reinterpret_cast<int *>(tot + size_t(warps) * R * (m1 + 3));  // [n]
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+
+    // ---- tables (a few thousand flops per CTA) ----
+    for (int t = threadIdx.x; t < n; t += blockDim.x) {
+        const int c = a.colmap[t];
+        colmap[t] = c;
+        invc[t] = a.inv_count[c];
+        F[t] = 1.0;
+        F[n + t] = a.y[t];
+    }
+    for (int t = threadIdx.x; t < r * n; t += blockDim.x) {
+        F[2 * n + t] = a.Wt[t];
+        Ct[t] = a.C[(t % n) * r + t / n];
+    }
+    for (int t = threadIdx.x; t < nbk * n; t += blockDim.x) F[size_t(2 + r) * n + t] = 0.0;
+    __syncthreads();
+    for (int b = w; b < nbk; b += warps) {
+        const int t0 = a.seg_off[b], t1 = a.seg_off[b + 1];
+        const double inv = 1.0 / double(t1 - t0);
+        for (int t = t0 + lane; t < t1; t += 32) F[size_t(2 + r + b) * n + a.seg_order[t]] = inv;
+        for (int rr = 0; rr < r; ++rr) {
+            double acc = 0.0;
+            for (int t = t0 + lane; t < t1; t += 32) acc += a.C[a.seg_order[t] * r + rr];
+            acc = warp_sum(acc);
+            if (lane == 0) cbar[b * r + rr] = acc * inv;
+        }
+    }
+    for (int rr = w; rr <= r; rr += warps) {  // rr == r: sum(y)
+        double acc = 0.0;
+        for (int t = lane; t < n; t += 32) acc += (rr < r ? a.C[t * r + rr] : 1.0) * a.y[t];
+        acc = warp_sum(acc);
+        if (lane == 0) cy[rr] = acc;
+    }
+    __syncthreads();
+
+    double *tw = tot + size_t(w) * R * (m1 + 3);
+    const double dn = double(n);
+    double thr = 0.0;
+    if (a.qc_kurt) {  // _nam.py:94: threshold = max(6, 2 * median) with Python's max (NaN -> 6)
+        const double two_med = 2.0 * a.qc_median[0];
+        thr = two_med > 6.0 ? two_med : 6.0;
+    }
+    const int64_t stride = int64_t(gridDim.x) * warps * R;
+    for (int64_t row0 = (int64_t(blockIdx.x) * warps + w) * R; row0 < a.n_rows; row0 += stride) {
+        double x[R][NQ];
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+            const int64_t row = row0 + i < a.n_rows ? row0 + i : row0;
+            const float *p = a.s + row * a.ld_s;
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                const int m = lane + 32 * q;
+                x[i][q] = m < n ? double(__ldg(p + colmap[m])) * invc[m] : 0.0;
+            }
+        }
+        // ---- the m1 functionals, 16 (= 16 / R per row) at a time ----
+        constexpr int FPC = 16 / R;  // functionals per chunk
+        for (int f0 = 0; f0 < m1; f0 += FPC) {
+            double acc[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc[j] = 0.0;
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                const int m = lane + 32 * q;
+                if (m < n) {
+#pragma unroll
+                    for (int f = 0; f < FPC; ++f) {
+                        const double c = f0 + f < m1 ? F[size_t(f0 + f) * n + m] : 0.0;
+#pragma unroll
+                        for (int i = 0; i < R; ++i) acc[f * R + i] = fma(x[i][q], c, acc[f * R + i]);
+                    }
+                }
+            }
+            butterfly16(acc, lane);
+            const int j = lane >> 1, f = j / R, i = j % R;
+            if (!(lane & 1) && f0 + f < m1) tw[i * (m1 + 3) + f0 + f] = acc[0];
+        }
+        __syncwarp();
+        // ---- x' and the sums of squares ----
+        double sq[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) sq[j] = 0.0;
+        double mean[R];
+#pragma unroll
+        for (int i = 0; i < R; ++i) mean[i] = tw[i * (m1 + 3)] / dn;
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            const int m = lane + 32 * q;
+            if (m < n) {
+#pragma unroll
+                for (int i = 0; i < R; ++i) {
+                    x[i][q] -= mean[i];  // _nam.py:122
+                    sq[i] = fma(x[i][q], x[i][q], sq[i]);
+                }
+            }
+        }
+        for (int rr = 0; rr < r; ++rr) {  // rank-r update X <- X - (X W^T) C^T  (_nam.py:133-135 / :146-148)
+            double pr[R];
+#pragma unroll
+            for (int i = 0; i < R; ++i) pr[i] = tw[i * (m1 + 3) + 2 + rr];
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                const int m = lane + 32 * q;
+                if (m < n) {
+                    const double cv = Ct[rr * n + m];
+#pragma unroll
+                    for (int i = 0; i < R; ++i) x[i][q] = fma(-pr[i], cv, x[i][q]);
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+#pragma unroll
+            for (int i = 0; i < R; ++i) {
+                sq[R + i] = fma(x[i][q], x[i][q], sq[R + i]);
+                if (2 * R + i < 16) sq[2 * R + i] += x[i][q];
+            }
+        }
+        butterfly16(sq, lane);
+        {
+            const int j = lane >> 1;
+            if (!(lane & 1) && j < 3 * R) tw[(j % R) * (m1 + 3) + m1 + j / R] = sq[0];
+        }
+        __syncwarp();
+        // ---- per-row scalars: lane i < R finishes row i ----
+        double inv_std = 0.0;
+        bool ok = false;
+        if (lane < R && row0 + lane < a.n_rows) {
+            const int64_t row = row0 + lane;
+            const double *t = tw + lane * (m1 + 3);
+            const double mu = t[0] / dn;
+            bool keep = true;
+            if (a.row_keep) keep = a.row_keep[row] != 0;
+            else if (a.qc_kurt) keep = a.qc_kurt[row] < thr;  // NaN -> dropped, _nam.py:96
+            ok = keep && !(t[m1] / (dn - 1.0) == 0.0);  // _association.py:182-185
+            double kurt = nan("");
+            if (nbk > 0 && ok) {  // _nam.py:78-82 on the residualised row
+                double mm = 0.0;
+                for (int b = 0; b < nbk; ++b) {
+                    double v = t[2 + r + b] - mu;
+                    for (int rr = 0; rr < r; ++rr) v = fma(-cbar[b * r + rr], t[2 + rr], v);
+                    mm += v;
+                }
+                mm /= nbk;
+                double m2 = 0.0, m4 = 0.0;
+                for (int b = 0; b < nbk; ++b) {
+                    double v = t[2 + r + b] - mu;
+                    for (int rr = 0; rr < r; ++rr) v = fma(-cbar[b * r + rr], t[2 + rr], v);
+                    const double d2 = (v - mm) * (v - mm);
+                    m2 += d2;
+                    m4 += d2 * d2;
+                }
+                kurt = kurtosis_from_moments(mm, m2 / nbk, m4 / nbk, false);
+            }
+            if (a.kurt) a.kurt[row] = kurt;
+            // ddof=1 standardisation (_nam.py:159; pandas std is taken around the mean of x')
+            const double s1 = t[m1 + 2] / dn;
+            inv_std = 1.0 / sqrt((t[m1 + 1] - dn * s1 * s1) / (dn - 1.0));
+            double d = t[1] - mu * cy[r];  // x'.y = x.y - mean * sum(y) - (C^T y).p
+            for (int rr = 0; rr < r; ++rr) d = fma(-cy[rr], t[2 + rr], d);
+            a.ncorr[row] = ok ? d * inv_std / dn : 0.0;  // _association.py:77
+            a.row_valid[row] = ok ? 1 : 0;
+        }
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+            const int64_t row = row0 + i;
+            if (row >= a.n_rows) break;  // uniform over the warp
+            const double sc = __shfl_sync(kFull, inv_std, i);
+            const bool valid = __shfl_sync(kFull, int(ok), i) != 0;
+            float *o = a.x_out ? a.x_out + row * a.ld_x : nullptr;
+            __half *ph = a.x16_hi ? static_cast<__half *>(a.x16_hi) + row * a.ld16 : nullptr;
+            __half *pl = a.x16_hi ? static_cast<__half *>(a.x16_lo) + row * a.ld16 : nullptr;
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                const int m = lane + 32 * q;
+                const double v = (m < n && valid) ? x[i][q] * sc : 0.0;  // rows of dropped cells are zero
+                if (o && m < a.ld_x) o[m] = float(v);
+                if (ph && m < a.ld16) {  // v = hi + lo to 2^-22
+                    const __half h = __float2half_rn(float(v));
+                    ph[m] = h;
+                    pl[m] = __float2half_rn(float(v - double(__half2float(h))));
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
 }  // namespace cna
 
 using namespace cna;
@@ -339,7 +586,43 @@ int cna_resid_pass(const cna_resid_args *args, void *stream) {
     const int threads = 256, warps = threads / 32;
     const bool want_kurt = a.kurt && a.n_batches > 1;
     CNA_REQUIRE(!want_kurt || (a.seg_order && a.seg_off), "cna_resid_pass: batch segments missing");
+    CNA_REQUIRE(!a.qc_kurt || a.qc_median, "cna_resid_pass: qc_kurt needs qc_median");
     int nq = (a.n + 31) / 32;
+    cudaStream_t st = as_stream(stream);
+    {   // the linear-functional kernel whenever its tables fit in shared memory
+        ResidTables tb;
+        tb.nbk = want_kurt ? a.n_batches : 0;
+        tb.m1 = 2 + a.r + tb.nbk;
+        const int R = nq <= 8 ? 4 : (nq <= 16 ? 2 : 1);
+        size_t smem = sizeof(double) * (size_t(tb.m1) * a.n + size_t(a.r) * a.n + a.n + size_t(tb.nbk) * a.r +
+                                        a.r + 1 + size_t(warps) * R * (tb.m1 + 3)) + sizeof(int) * size_t(a.n);
+        if (smem <= 100 * 1024) {
+            int64_t blocks_needed = (a.n_rows + int64_t(warps) * R - 1) / (int64_t(warps) * R);
+            int64_t cap = int64_t(num_sms()) * 8;
+            unsigned grid = unsigned(blocks_needed < cap ? blocks_needed : cap);
+#define CNA_RESID_LIN(NQ, RR)                                                                                   \
+    do {                                                                                                       \
+        CNA_CUDA(cudaFuncSetAttribute(resid_lin_kernel<NQ, RR>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                      int(smem)));                                                             \
+        resid_lin_kernel<NQ, RR><<<grid, threads, smem, st>>>(a, tb);                                          \
+    } while (0)
+            switch (nq <= 8 ? nq : (nq <= 16 ? 16 : 32)) {
+                case 1: CNA_RESID_LIN(1, 4); break;
+                case 2: CNA_RESID_LIN(2, 4); break;
+                case 3: CNA_RESID_LIN(3, 4); break;
+                case 4: CNA_RESID_LIN(4, 4); break;
+                case 5: CNA_RESID_LIN(5, 4); break;
+                case 6: CNA_RESID_LIN(6, 4); break;
+                case 7: CNA_RESID_LIN(7, 4); break;
+                case 8: CNA_RESID_LIN(8, 4); break;
+                case 16: CNA_RESID_LIN(16, 2); break;
+                default: CNA_RESID_LIN(32, 1);
+            }
+#undef CNA_RESID_LIN
+            CNA_LAUNCHED("resid_lin_kernel");
+            return CNA_OK;
+        }
+    }
     const int R = nq <= 8 ? 4 : (nq <= 16 ? 2 : 1);  // rows per warp (register budget: R * NQ doubles)
     size_t smem = sizeof(double) * (2 * size_t(a.r) * a.n + 2 * size_t(a.n) + size_t(warps) * R * a.r +
                                     (want_kurt ? size_t(warps) * (a.n + a.n_batches) : 0)) +
@@ -349,7 +632,6 @@ int cna_resid_pass(const cna_resid_args *args, void *stream) {
     int64_t blocks_needed = (a.n_rows + int64_t(warps) * R - 1) / (int64_t(warps) * R);
     int64_t cap = int64_t(num_sms()) * 8;
     unsigned grid = unsigned(blocks_needed < cap ? blocks_needed : cap);
-    cudaStream_t st = as_stream(stream);
 #define CNA_RESID(NQ, RR, EX, RT)                                                                          \
     do {                                                                                                   \
         CNA_CUDA(cudaFuncSetAttribute(resid_kernel<NQ, RR, EX, RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, \

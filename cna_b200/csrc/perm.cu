@@ -18,20 +18,31 @@ perm_stats_kernel(const double *__restrict__ y, const int32_t *__restrict__ perm
                   const double *__restrict__ Ut, int kmax, const int32_t *__restrict__ ks, int nks,
                   double *__restrict__ ssered, double *__restrict__ ssefull,
                   float *__restrict__ ycond, int64_t ld_y, int n_local, __half *__restrict__ yt_hi,
-                  __half *__restrict__ yt_lo, int64_t ld16) {
+                  __half *__restrict__ yt_lo, int64_t ld16, int stage_u, int stage_wc) {
+    // stage_u / stage_wc: the PC matrix / the design matrices fit in shared memory; otherwise they are
+    // read where they lie (L2-resident: every warp of every CTA streams the same few hundred KB)
     extern __shared__ double sm[];
     double *ys = sm;               // [n]
-    double *Ws = ys + n;           // [r][n]
-    double *Cs = Ws + r * n;       // [r][n] (transposed)
-    double *Us = Cs + r * n;       // [kmax][n]
-    double *proj = Us + kmax * n;  // [warps][r]
-    int *kss = reinterpret_cast<int *>(proj + (blockDim.x >> 5) * r);  // [nks]
+    double *proj = ys + n;         // [warps][r]
+    int *kss = reinterpret_cast<int *>(proj + (blockDim.x >> 5) * r);  // [nks], padded to 8 bytes
+    double *next_free = reinterpret_cast<double *>(kss + ((nks + 1) & ~1));
+    const double *Ws = W, *Cs = nullptr, *Us = Ut;
     for (int t = threadIdx.x; t < n; t += blockDim.x) ys[t] = y[t];
-    for (int t = threadIdx.x; t < r * n; t += blockDim.x) {
-        Ws[t] = W[t];
-        Cs[t] = C[(t % n) * r + t / n];
+    if (stage_wc) {
+        double *w_s = next_free, *c_s = w_s + r * n;  // [r][n] each (C transposed)
+        next_free = c_s + r * n;
+        for (int t = threadIdx.x; t < r * n; t += blockDim.x) {
+            w_s[t] = W[t];
+            c_s[t] = C[(t % n) * r + t / n];
+        }
+        Ws = w_s;
+        Cs = c_s;
     }
-    for (int t = threadIdx.x; t < kmax * n; t += blockDim.x) Us[t] = Ut[t];
+    if (stage_u) {
+        double *u_s = next_free;  // [kmax][n]
+        for (int t = threadIdx.x; t < kmax * n; t += blockDim.x) u_s[t] = Ut[t];
+        Us = u_s;
+    }
     for (int t = threadIdx.x; t < nks; t += blockDim.x) kss[t] = ks[t];
     __syncthreads();
 
@@ -62,7 +73,7 @@ perm_stats_kernel(const double *__restrict__ y, const int32_t *__restrict__ perm
 #pragma unroll
             for (int q = 0; q < NQ; ++q) {
                 int m = lane + 32 * q;
-                if (m < n) z[q] -= Cs[rr * n + m] * pr;
+                if (m < n) z[q] -= (Cs ? Cs[rr * n + m] : C[m * r + rr]) * pr;
             }
         }
         __syncwarp();
@@ -226,9 +237,16 @@ extern "C" int cna_perm_stats(const double *y, const int32_t *perm, int64_t K, i
     if (kmax == 0) nks = 0;
     if (K == 0) return CNA_OK;
     const int threads = 256, warps = threads / 32;
-    size_t smem = sizeof(double) * (size_t(n) + 2 * size_t(r) * n + size_t(kmax) * n + size_t(warps) * r) +
-                  sizeof(int) * size_t(nks);
-    CNA_REQUIRE(smem <= 200 * 1024, "cna_perm_stats: n=%d r=%d kmax=%d needs %zu bytes of shared memory", n, r, kmax, smem);
+    // y, the per-warp projections and ks always live in shared memory; the design matrices (2 r n
+    // doubles) and the PCs (kmax n doubles) only while they fit: beyond ~570 samples with the default
+    // ks the PCs are streamed from L2 instead
+    const size_t limit = 200 * 1024;
+    size_t smem = sizeof(double) * (size_t(n) + size_t(warps) * r) + sizeof(int) * size_t((nks + 1) & ~1);
+    const size_t wc_bytes = sizeof(double) * 2 * size_t(r) * n, u_bytes = sizeof(double) * size_t(kmax) * n;
+    const int stage_wc = (r > 0 && smem + wc_bytes <= limit) ? 1 : 0;
+    if (stage_wc) smem += wc_bytes;
+    const int stage_u = (kmax > 0 && smem + u_bytes <= limit) ? 1 : 0;
+    if (stage_u) smem += u_bytes;
     int64_t blocks = (K + warps - 1) / warps;
     int64_t cap = int64_t(num_sms()) * 2;
     unsigned grid = unsigned(blocks < cap ? blocks : cap);
@@ -241,7 +259,8 @@ extern "C" int cna_perm_stats(const double *y, const int32_t *perm, int64_t K, i
         perm_stats_kernel<NQ><<<grid, threads, smem, st>>>(y, perm, K, n, C, W, r, Ut, kmax, ks, nks, \
                                                             ssered, ssefull, ycond, ld_y, n_local,    \
                                                             static_cast<__half *>(yt_hi),             \
-                                                            static_cast<__half *>(yt_lo), ld16);      \
+                                                            static_cast<__half *>(yt_lo), ld16,       \
+                                                            stage_u, stage_wc);                       \
     } while (0)
     if (nq <= 2) CNA_PERM(2);
     else if (nq <= 4) CNA_PERM(4);

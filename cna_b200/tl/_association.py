@@ -69,28 +69,65 @@ def check_inputs(data, y, sid_name, batches, covs, donorids, allow_low_sample_si
 _PINNED = {}
 
 
-def _to_host_pinned(t, slot="results"):
-    """Device tensor -> numpy array through a cached page-locked staging buffer (a pageable D2H of
-    the two per-cell float64 columns costs more than the kernels that produced them).  The returned
-    array is a view of the staging buffer of that ``slot``: consume it before the next call."""
-    key = (t.dtype, tuple(t.shape))
+def _pinned(slot, shape, dtype):
+    """A cached page-locked host tensor per ``slot`` (re-allocated when the shape changes).  The
+    caller consumes it before the next call of the same slot."""
+    key = (dtype, tuple(shape))
     held = _PINNED.get(slot)
-    buf = held[1] if held is not None and held[0] == key else None
-    if buf is None:
-        buf = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
-        _PINNED[slot] = (key, buf)
-    buf.copy_(t, non_blocking=True)
-    torch.cuda.current_stream().synchronize()
-    return buf.numpy()
+    if held is None or held[0] != key:
+        held = _PINNED[slot] = (key, torch.empty(shape, dtype=dtype, pin_memory=True))
+    return held[1]
 
 
-def _to_host_owned(t):
-    """Device tensor -> numpy array in a page-locked buffer of its own (torch's pinned-memory cache
-    hands the block of the column written by the previous call back once pandas lets go of it)."""
+class _Readback:
+    """Several small device tensors -> one page-locked staging buffer with one event: ``get()`` waits
+    for the event only, not for whatever has been queued on the stream since."""
+
+    def __init__(self, slot, tensors):
+        self.views = []
+        total = sum(t.numel() * t.element_size() for t in tensors)
+        buf = _pinned(slot, (max(total, 1),), torch.uint8)
+        off = 0
+        for t in tensors:
+            nbytes = t.numel() * t.element_size()
+            host = buf[off:off + nbytes].view(t.dtype).reshape(t.shape)
+            host.copy_(t, non_blocking=True)
+            self.views.append(host)
+            off += nbytes
+        self.event = torch.cuda.Event()
+        self.event.record()
+
+    def get(self):
+        self.event.synchronize()
+        return [v.numpy() for v in self.views]
+
+
+_SIDE = {}
+
+
+def _side_stream(dev):
+    """One side stream per device for the copies of the per-cell result columns (they overlap the
+    kernels queued after the pass that produced them)."""
+    key = (dev.type, dev.index)
+    if key not in _SIDE:
+        _SIDE[key] = torch.cuda.Stream(device=dev)
+    return _SIDE[key]
+
+
+def _to_host_owned(t, stream=None):
+    """Device tensor -> page-locked host tensor of its own, copied on ``stream`` (after everything
+    queued so far on the current stream).  Returns (host tensor, event)."""
     buf = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
-    buf.copy_(t, non_blocking=True)
-    torch.cuda.current_stream().synchronize()
-    return buf.numpy()
+    cur = torch.cuda.current_stream()
+    stream = stream or cur
+    if stream is not cur:
+        stream.wait_stream(cur)
+    with torch.cuda.stream(stream):
+        buf.copy_(t, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+    t.record_stream(stream)
+    return buf, ev
 
 
 def _adopt_column(obs, key, values):
@@ -111,16 +148,6 @@ def default_ks(n):
 
 
 _POOL = None
-_HELPER = None
-
-
-def _helper_pool():
-    global _HELPER
-    if _HELPER is None:
-        from concurrent.futures import ThreadPoolExecutor
-        _HELPER = ThreadPoolExecutor(max_workers=1, thread_name_prefix="cna-svd")
-    return _HELPER
-
 
 
 def _f_sf(f, dfn, dfd):
@@ -156,45 +183,151 @@ def _pick(p, r2, ks):
     return np.asarray(ks)[pick], p[rows, pick], r2[rows, pick]
 
 
-def _association(res, perms, Nnull=1000, local_test=True, show_progress=False, idle_work=None):
+THRESHOLD_CAP = 512  # capacity of the device threshold tables (np.arange(m/4, m, m/400) has 300 or 301)
+
+# diagnostics of the most recent association() call on this process (bench.py's `check` block):
+# leading singular values of the residualised NAM, FDR thresholds, the k chosen, timings are not kept
+LAST = Namespace()
+
+
+class _Columns:
+    """The two per-cell output columns (``_association.py:228-237``).  ``data.obs[key_added]`` is known
+    as soon as the NAM is residualised and the per-cell FDR as soon as the null histograms are: both
+    are copied back on a side stream, behind the kernels that produce them and beside everything queued
+    afterwards, each into a page-locked buffer of its own that the obs column then adopts."""
+
+    def __init__(self, data, key_added, stn, res, gather):
+        self.data, self.key, self.stn, self.res, self.gather = data, key_added, stn, res, gather
+        self.coef = self.fdr = None
+        self.side = _side_stream(res.ncorr.device)
+
+    def _full(self, t):
+        """This rank's rows (stored order) -> all cells in the caller's order."""
+        stn = self.stn
+        if stn.comm is not None:
+            pad = torch.zeros((stn.rows_per,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+            pad[: stn.N] = t
+            t = stn.comm.all_gather_rows(pad)[: len(self.data.obs)]
+        return t if stn.graph is None else stn.graph.unpermute(t)
+
+    def start_coef(self):
+        res = self.res
+        coef = torch.where(res.valid.bool(), res.ncorr, torch.full_like(res.ncorr, float("nan")))
+        if self.gather:
+            self.coef = _to_host_owned(self._full(coef), self.side)
+
+    def start_fdr(self, fdrs):
+        """``fdrs`` = the threshold/FDR table, or None (local_test=False: the reference writes the
+        coefficients and then crashes looking up FDRs at :235; here the FDR column is simply not
+        written)."""
+        if fdrs is None:
+            return
+        res = self.res
+        thr = fdrs.threshold.to_numpy()
+        pmin = np.fmin.accumulate(fdrs.fdr.to_numpy())  # Series.min() skips NaN (:234)
+        coef_d = torch.empty_like(res.ncorr)
+        fdr_d = torch.empty_like(res.ncorr)
+        _lib.cell_fdr(res.ncorr, res.valid, _to_dev(thr), _to_dev(pmin), coef_d, fdr_d)
+        if self.gather:
+            self.fdr = _to_host_owned(self._full(fdr_d), self.side)
+
+    def write(self):
+        obs = self.data.obs
+        if self.coef is not None:
+            if self.key in obs:
+                warnings.warn(f"Key '{self.key}' already exists in data.obs. Overwriting.")
+            self.coef[1].synchronize()
+            _adopt_column(obs, self.key, self.coef[0].numpy())
+            mark("coef column written")
+        if self.fdr is not None:
+            self.fdr[1].synchronize()
+            _adopt_column(obs, f"{self.key}_fdr", self.fdr[0].numpy())
+        mark("obs written")
+
+
+def _association(res, perms, Nnull=1000, local_test=True, show_progress=False, columns=None):
     """``_nam.py:163`` (Gram + SVD of the residualised NAM) and ``_association.py:10-129`` after
     seeding / permutation drawing (done by the caller so that they overlap with the NAM kernels).
     ``res`` carries the device-resident residualised NAM (``res.planes`` / ``res.x``), M, r, the
     standardised phenotype and ks; U, svs and the Gram are added to it.
 
-    Order of work: the Gram and max|ncorr| are launched and read back with one sync; the n x n SVD then
-    runs on a helper thread.  Meanwhile this thread launches the conditioned null phenotypes (which need
-    M but not U) and the null GEMM + histograms, turns the histograms into the FDR table and starts on
-    ``idle_work(fdrs, svd_done)`` (the per-cell output columns; a sequence of steps that stops early once
-    ``svd_done()`` is true).  With U: observed statistics, the PC regressions of all permutations are
-    launched, ``idle_work(fdrs, None)`` finishes its remaining steps while they run, then the global
-    p-value."""
+    The device work is queued in two phases, neither of which waits for the host:
+      A  Gram, max |ncorr|, the FDR thresholds derived from it (on the device) and one packed read-back
+         (Gram + the ridge walk's median + max |ncorr|);
+      B  the conditioned null phenotypes (need M but not U), the null GEMM with its histogram epilogue,
+         the observed histograms and one packed read-back (histograms + thresholds).
+    The host meanwhile decomposes the n x n Gram (the only thing the device has to wait for), tests the
+    observed phenotype, launches the PC regressions of all permutations and turns the histograms into
+    the FDR table.  Phase B is queued before the decomposition when the permutation draw has already
+    finished, after it otherwise."""
     out = select_output(show_progress)
-    M, r, n = res.M, res.r, res.n
+    r, n = res.r, res.n
     dev = res.ncorr.device
     y = res.y_std
-    ks = res.ks
-    kmax = int(max(ks))
+    ks = list(res.ks)
+    ks_dev = np.unique(np.asarray(ks, dtype=np.int64))  # the device kernels want ascending, distinct ks
+    ks_pos = np.searchsorted(ks_dev, np.asarray(ks, dtype=np.int64))
+    kmax = int(ks_dev[-1])
     comm = res.comm
     Kl = min(1000, Nnull) if local_test else 0
-
-    G_d = _nam.gram_device(res.x, n, comm=comm, planes=res.planes)
-    mx = torch.zeros(1, dtype=torch.float64, device=dev)
-    if local_test:
-        _lib.absmax(res.ncorr, res.valid, mx)
-        if comm is not None:
-            comm.all_reduce(mx, op="max")
-    Gh = G_d.cpu().numpy()
-    mark("gram on host")
     want_null_table = res.svd_top is None  # full result surface: every null p-value from scipy
+    y_d = _to_dev(y)
 
-    def launch_pc_regressions(U):
+    # ---- phase A ----
+    def phase_a():
+        G_d = _nam.gram_device(res.x, n, comm=comm, planes=res.planes)
+        mx = torch.zeros(1, dtype=torch.float64, device=dev)
+        tabs = None
+        if local_test:
+            _lib.absmax(res.ncorr, res.valid, mx)
+            if comm is not None:
+                comm.all_reduce(mx, op="max")
+            thr_d = torch.empty(THRESHOLD_CAP, dtype=torch.float64, device=dev)
+            edges_d = torch.empty(THRESHOLD_CAP, dtype=torch.float64, device=dev)
+            count_d = torch.empty(1, dtype=torch.int32, device=dev)
+            _lib.fdr_thresholds(mx, thr_d, edges_d, count_d)  # :101-102, _stats.py:51
+            tabs = (thr_d, edges_d, count_d)
+        med = res.ridge_median if res.ridge_median is not None else torch.zeros(2, dtype=torch.float64, device=dev)
+        return _Readback("phase_a", [G_d, med, mx]), tabs
+
+    # ---- phase B ----
+    def phase_b(tabs):
+        # permutations: indices from the host RNG (bit-exact), everything else on the device
+        if perms is not None:
+            perm_d = perms.result_device(dev)
+        else:  # a shard other than rank 0: the indices are drawn once, by rank 0
+            perm_d = torch.empty((Nnull, n), dtype=torch.int32, device=dev)
+        if comm is not None:
+            comm.broadcast(perm_d, src=0)
+        mark("permutations uploaded")
+        C_d = _to_dev(res.C) if r else None
+        W_d = _to_dev(np.ascontiguousarray(res.W_last)) if r else None
+        back = None
+        if local_test:  # :92-103
+            print("computing neighborhood-level FDRs", file=out)
+            thr_d, edges_d, count_d = tabs
+            hist = torch.zeros(THRESHOLD_CAP, dtype=torch.int64, device=dev)  # summed over the Kl nulls
+            obs = torch.zeros((2, THRESHOLD_CAP), dtype=torch.int32, device=dev)
+            # ycond_ = M.y_[:, :Kl] / std (ddof=1) (:94-97) as transposed fp16 hi/lo planes, then
+            # (cells x n) . (n x Kl) on the tensor cores with the histogram epilogue straight out of TMEM
+            ytp = _lib.Planes(Kl, n, dev, zero=True)
+            _lib.perm_stats(y_d, perm_d[:Kl], C_d, W_d, None, None, None, None, None, Kl, planes=ytp)
+            _lib.null_hist_tc_dev(res.planes, n, ytp, Kl, edges_d, count_d, hist)
+            _lib.obs_hist_dev(res.ncorr, res.valid, edges_d, thr_d, count_d, obs[0], obs[1])
+            if comm is not None:  # counts over all shards
+                comm.all_reduce(hist)
+                comm.all_reduce(obs)
+            back = _Readback("phase_b", [hist, obs, thr_d, count_d])
+        mark("null kernels launched")
+        return perm_d, C_d, W_d, back
+
+    def launch_pc_regressions(U, perm_d, C_d, W_d):
         """PC regressions of every permuted phenotype (:84) -> SSEs and, unless the full table of null
         p-values is wanted on the host, the F survival function + min over ks on the device."""
         ssered_d = torch.empty(Nnull, dtype=torch.float64, device=dev)
-        ssefull_d = torch.empty((Nnull, len(ks)), dtype=torch.float64, device=dev)
+        ssefull_d = torch.full((Nnull, len(ks_dev)), float("nan"), dtype=torch.float64, device=dev)
         Ut_d = _to_dev(np.ascontiguousarray(U[:, :kmax].T))
-        ks_d = _to_dev(np.asarray(ks, dtype=np.int32))
+        ks_d = _to_dev(ks_dev.astype(np.int32))
         _lib.perm_stats(y_d, perm_d, C_d, W_d, Ut_d, ks_d, ssered_d, ssefull_d, None, 0)
         if want_null_table:
             return ssered_d, ssefull_d, None
@@ -202,16 +335,11 @@ def _association(res, perms, Nnull=1000, local_test=True, show_progress=False, i
         argk_d = torch.empty(Nnull, dtype=torch.int32, device=dev)
         r2_d = torch.empty(Nnull, dtype=torch.float64, device=dev)
         _lib.perm_minp(ssered_d, ssefull_d, ks_d, n, r, minp_d, argk_d, r2_d)
-        return ssered_d, ssefull_d, (minp_d, r2_d)
-
-    def fetch(sse_d):
-        if sse_d[2] is None:
-            return (sse_d[0].cpu().numpy(), sse_d[1].cpu().numpy(), None)
-        return (sse_d[0], sse_d[1], (sse_d[2][0].cpu().numpy(), sse_d[2][1].cpu().numpy()))
+        return ssered_d, ssefull_d, _Readback("minp", [minp_d, r2_d])
 
     def observed_test(U):
         """Observed phenotype (:64-74): n-sized host arithmetic in float64."""
-        ycond = M.dot(y)
+        ycond = res.M.dot(y)
         ycond = ycond / ycond.std(ddof=1)  # a pandas Series in the reference -> ddof=1
         ssered = np.array([ycond.dot(ycond)])
         ssefull = np.array([[np.sum((U[:, :k].dot(U[:, :k].T.dot(ycond)) - ycond) ** 2) for k in ks]])
@@ -227,20 +355,20 @@ def _association(res, perms, Nnull=1000, local_test=True, show_progress=False, i
 
     def global_pvalue(p, sse_d):
         """:84-88 from the regressions of the permuted phenotypes."""
-        sse_host = fetch(sse_d)
-        if sse_host[2] is None:
-            nullp, nullr2 = _f_pvalues(sse_host[0], sse_host[1], ks, n, r)
+        if sse_d[2] is None:  # every null p-value from scipy, in the caller's order of ks
+            ssered, ssefull = sse_d[0].cpu().numpy(), sse_d[1].cpu().numpy()[:, ks_pos]
+            nullp, nullr2 = _f_pvalues(ssered, ssefull, ks, n, r)
             _, nullminps, nullr2s = _pick(nullp, nullr2, ks)
         else:
             # min-p per permutation from the device (fp64 incomplete beta, ~1e-13 of scipy); the few that
             # fall within 1e-9 relative of the decision threshold are re-evaluated with scipy so that the
             # count below is exactly the reference's
-            nullminps, nullr2s = sse_host[2]
+            nullminps, nullr2s = (a.copy() for a in sse_d[2].get())
             thr = p + 1e-8
             near = np.abs(nullminps - thr) <= 1e-9 * thr
             if near.any():
                 ix = torch.as_tensor(np.nonzero(near)[0], device=dev)
-                pp, rr2 = _f_pvalues(sse_host[0][ix].cpu().numpy(), sse_host[1][ix].cpu().numpy(), ks, n, r)
+                pp, rr2 = _f_pvalues(sse_d[0][ix].cpu().numpy(), sse_d[1][ix].cpu().numpy()[:, ks_pos], ks, n, r)
                 _, nullminps[near], nullr2s[near] = _pick(pp, rr2, ks)
         nhit = int((nullminps <= p + 1e-8).sum())
         if nhit == 0:
@@ -249,71 +377,55 @@ def _association(res, perms, Nnull=1000, local_test=True, show_progress=False, i
         mark("global p done")
         return (nhit + 1) / (Nnull + 1), nullminps, nullr2s
 
-    # The n x n SVD (_nam.py:105) needs only the Gram: it runs on a helper thread (LAPACK releases the
-    # GIL) while this thread launches the null kernels and writes the per-cell outputs.
-    svd_future = _helper_pool().submit(_nam.svd_of_gram, Gh, res.svd_top)
+    def fdr_table(back):
+        """:105-118 from the histograms (and the thresholds the device derived from max |ncorr|)."""
+        hist_h, obs_h, thr_h, count_h = back.get()
+        T = int(count_h[0])
+        if T >= THRESHOLD_CAP:
+            raise _lib.CnaError(f"more than {THRESHOLD_CAP - 1} FDR thresholds")
+        thresholds = thr_h[:T].copy()
+        fdr_vals = _stats.fdr_from_counts(hist_h[:T], obs_h[0, :T], n_null=Kl)  # _stats.py:64-83
+        num_detected = _stats.tails_from_hist(obs_h[1, :T].astype(np.int64))  # :105-108
+        fdrs = pd.DataFrame({"threshold": thresholds, "fdr": fdr_vals, "num_detected": num_detected})
+        t5 = t10 = None
+        if not np.nanmin(fdr_vals) > 0.05:  # :111-114 (Series.min skips NaN; first row with fdr <= 0.05)
+            t5 = thresholds[np.nonzero(fdr_vals <= 0.05)[0][0]]
+        if not np.nanmin(fdr_vals) > 0.1:  # :115-118
+            t10 = thresholds[np.nonzero(fdr_vals <= 0.1)[0][0]]
+        mark("fdr table done")
+        return fdrs, t5, t10
 
-    fdrs, fdr_5p_t, fdr_10p_t = None, None, None
-    try:
-        # ---- permutations: indices from the host RNG (bit-exact), everything else on the device ----
-        if perms is not None:
-            perm_d = perms.result_device(dev)
-        else:  # a shard other than rank 0: the indices are drawn once, by rank 0
-            perm_d = torch.empty((Nnull, n), dtype=torch.int32, device=dev)
-        if comm is not None:
-            comm.broadcast(perm_d, src=0)
-        mark("permutations uploaded")
-        y_d = _to_dev(y)
-        C_d = _to_dev(res.C) if r else None
-        W_d = _to_dev(np.ascontiguousarray(res.W_last)) if r else None
-
-        # ---- neighbourhood-level null (:92-103) ----
-        if local_test:
-            print("computing neighborhood-level FDRs", file=out)
-            maxcorr = max(float(mx.item()), 0.001)  # :101
-            thresholds = np.arange(maxcorr / 4, maxcorr, maxcorr / 400)  # :102
-            edges = _stats.threshold_edges(thresholds)
-            T = len(thresholds)
-            edges_d, thr_d = _to_dev(edges), _to_dev(thresholds)
-            hist = torch.zeros(T, dtype=torch.int64, device=dev)  # summed over the Kl nulls
-            obs = torch.zeros((2, T), dtype=torch.int32, device=dev)
-            # ycond_ = M.y_[:, :Kl] / std (ddof=1) (:94-97) as transposed fp16 hi/lo planes, then
-            # (cells x n) . (n x Kl) on the tensor cores with the histogram epilogue straight out of TMEM
-            ytp = _lib.Planes(Kl, n, dev, zero=True)
-            _lib.perm_stats(y_d, perm_d[:Kl], C_d, W_d, None, None, None, None, None, Kl, planes=ytp)
-            _lib.null_hist_tc(res.planes, n, ytp, Kl, edges_d, float(edges[0]), hist)
-            _lib.obs_hist(res.ncorr, res.valid, edges_d, thr_d, obs[0], obs[1])
-            if comm is not None:  # counts over all shards
-                comm.all_reduce(hist)
-                comm.all_reduce(obs)
-        mark("null kernels launched")
-
-        if local_test:  # :105-118; needs the histograms only
-            obs_h = obs.cpu().numpy()
-            fdr_vals = _stats.fdr_from_counts(hist.cpu().numpy(), obs_h[0], n_null=Kl)  # _stats.py:64-83
-            num_detected = _stats.tails_from_hist(obs_h[1].astype(np.int64))  # :105-108
-            fdrs = pd.DataFrame({"threshold": thresholds, "fdr": fdr_vals, "num_detected": num_detected})
-            if not np.nanmin(fdr_vals) > 0.05:  # :111-114 (Series.min skips NaN; first row with fdr <= 0.05)
-                fdr_5p_t = thresholds[np.nonzero(fdr_vals <= 0.05)[0][0]]
-            if not np.nanmin(fdr_vals) > 0.1:  # :115-118
-                fdr_10p_t = thresholds[np.nonzero(fdr_vals <= 0.1)[0][0]]
-            mark("fdr table done")
-        if idle_work is not None:
-            idle_work(fdrs, svd_future.done)  # per-cell outputs, for as long as the SVD thread is busy
-    except BaseException:
-        svd_future.result()
-        raise
-    U, svs, res.G = svd_future.result()
+    back_a, tabs = phase_a()
+    if columns is not None:
+        columns.start_coef()
+    early_b = perms is None or perms.done()
+    b = phase_b(tabs) if early_b else None
+    while True:
+        Gh, med_h, mx_h = back_a.get()
+        mark("gram on host")
+        if res.settle(float(med_h[0])):
+            break
+        # the first ridge did not bring the median batch kurtosis down to 6 (_nam.py:154): the walk has
+        # now been finished ridge by ridge and everything queued on the speculative NAM is repeated
+        back_a, tabs = phase_a()
+        if columns is not None:
+            columns.start_coef()
+        b = phase_b(tabs) if b is not None else None
+    U, svs, res.G = _nam.svd_of_gram(Gh.copy(), res.svd_top)
     res.U, res.svs = U, svs
     o = observed_test(U)
-    sse_d = launch_pc_regressions(U)
-    if idle_work is not None:
-        idle_work(fdrs, None)  # whatever is left of them, while the GPU runs the regressions
+    if b is None:
+        b = phase_b(tabs)
+    perm_d, C_d, W_d, back_b = b
+    sse_d = launch_pc_regressions(U, perm_d, C_d, W_d)
+    fdrs, fdr_5p_t, fdr_10p_t = fdr_table(back_b) if local_test else (None, None, None)
+    if columns is not None:
+        columns.start_fdr(fdrs)
     pfinal, nullminps, nullr2s = global_pvalue(o.p, sse_d)
 
     return Namespace(p=pfinal, nullminps=nullminps, k=o.k, ncorrs=None, fdrs=fdrs,
                      fdr_5p_t=fdr_5p_t, fdr_10p_t=fdr_10p_t, yresid_hat=o.yresid_hat, yresid=o.yresid,
-                     ks=ks, beta=o.beta, r2=o.r2, r2_perpc=o.r2_perpc,
+                     ks=res.ks, beta=o.beta, r2=o.r2, r2_perpc=o.r2_perpc,
                      nullr2_mean=nullr2s.mean(), nullr2_std=nullr2s.std())
 
 
@@ -321,7 +433,10 @@ def association(data, y, sid_name, batches=None, covs=None, donorids=None, ks=No
                 max_frac_pcs=0.15, nsteps=None, show_progress=False, allow_low_sample_size=False,
                 return_full=False, ridges=None, **kwargs):
     """``_association.py:193-242``.  Returns the global p-value, or the full result Namespace when
-    ``return_full``; writes ``data.obs[key_added]`` and ``data.obs[key_added + '_fdr']``."""
+    ``return_full``; writes ``data.obs[key_added]`` and ``data.obs[key_added + '_fdr']``.
+
+    Limits (checked before any device work): at most 1024 samples in ``data.obs[sid_name]`` and at
+    most 1024 selected samples."""
     out = select_output(show_progress)
     bad = set(kwargs) - {"Nnull", "force_permute_all", "local_test", "seed"}
     if bad:  # the reference forwards **kwargs to _association(), which rejects anything else
@@ -333,6 +448,8 @@ def association(data, y, sid_name, batches=None, covs=None, donorids=None, ks=No
             raise TypeError(f"'{name}' must be a pandas {kind.__name__}, but got {type(val)}")
     # one factorisation of the sample-id column serves the input checks (:140-143) and the NAM (:51)
     codes = _graph.sample_codes(data, sid_name)
+    if len(codes[0]) > 1024:
+        raise ValueError(f"cna_b200 supports at most 1024 samples (data.obs['{sid_name}'] has {len(codes[0])})")
     batches, filter_samples = check_inputs(data, y, sid_name, batches, covs, donorids,
                                            allow_low_sample_size, present=codes[0])
     mark("check_inputs done")
@@ -367,108 +484,40 @@ def association(data, y, sid_name, batches=None, covs=None, donorids=None, ks=No
     perms = (_stats.PermutationDraw(y_std, perm_batches, donor_f, Nnull)
              if comm is None or comm.rank == 0 else None)
     mark("permutation draw started")
-
-    # ---- launch the diffusion (asynchronous unless nsteps is None) ----
-    print("computing NAM", file=out)
     try:
+        # ---- the diffusion, QC and residualisation: queued back to back, no host round trip ----
+        print("computing NAM", file=out)
         stn = _nam._nam_device(data, sid_name, nsteps=nsteps, show_progress=show_progress, codes=codes,
                                qc_batches=batches)
-    except BaseException:
+        mark("diffusion launched")
+        _nam._qc_device(stn, batches, show_progress=show_progress)
+        colmap = stn.labels.get_indexer(sids)  # NAM.reindex(y.index)[filter_samples], :178-181
+        res = _nam.resid_nam_device(stn, colmap, covs_f, batches_f, y_std, ridges=ridges,
+                                    show_progress=show_progress, want_x=return_full, speculate=True)
+        mark("resid pass launched")
+        res.y_std = y_std
+        res.ks = ks_eff
+        # only the leading max(ks) components are read unless the full result surface is requested
+        res.svd_top = None if return_full else int(max(ks_eff))
+        print("performing association test", file=out)
+        # every rank of a sharded run ends with the full columns in its copy of data.obs
+        columns = _Columns(data, key_added, stn, res, gather=True)
+        core = _association(res, perms, Nnull=Nnull, local_test=local_test, show_progress=show_progress,
+                            columns=columns)
+    finally:
         if perms is not None:
-            perms.cancel()
-        raise
-    mark("diffusion launched")
-
-    # ---- QC, residualisation, Gram + SVD ----
-    _nam._qc_device(stn, batches, show_progress=show_progress)
-    mark("QC done (first sync)")
-    colmap = stn.labels.get_indexer(sids)  # NAM.reindex(y.index)[filter_samples], :178-181
-    res = _nam.resid_nam_device(stn, colmap, covs_f, batches_f, y_std, ridges=ridges,
-                                show_progress=show_progress, want_x=return_full)
-    mark("resid pass done")
-    res.y_std = y_std
-    res.ks = ks_eff
-    # only the leading max(ks) components are read unless the full result surface is requested
-    res.svd_top = None if return_full else int(max(ks_eff))
-    print("performing association test", file=out)
-    N = stn.N
-    dev = res.ncorr.device
-    columns_written = []
-
-    def fdr_lookup_tables(fdrs):
-        if fdrs is None:
-            # local_test=False: the reference writes the coefficients and then crashes looking up FDRs
-            # (res.fdrs is None at :235); here the FDR column is simply not written.
-            return np.array([np.inf]), np.array([1.0])
-        return fdrs.threshold.to_numpy(), np.fmin.accumulate(fdrs.fdr.to_numpy())  # Series.min() skips NaN
-
-    def column_steps(fdrs):
-        """data.obs[key_added] (:228-231) is known as soon as the NAM is residualised and the per-cell
-        FDR (:234-237) as soon as the null histograms are: both are copied back and written in the
-        shadow of the SVD thread and of the permutation regressions.  One yield per step."""
-        coef = torch.where(res.valid.bool(), res.ncorr, torch.full_like(res.ncorr, float("nan")))
-        if stn.graph is not None:
-            coef = stn.graph.unpermute(coef)
-        host = _to_host_owned(coef)
-        yield
-        if key_added in data.obs:
-            warnings.warn(f"Key '{key_added}' already exists in data.obs. Overwriting.")
-        _adopt_column(data.obs, key_added, host)
-        mark("coef column written")
-        yield
-        if fdrs is not None:
-            thr, pmin = fdr_lookup_tables(fdrs)
-            coef_d = torch.empty(N, dtype=torch.float64, device=dev)
-            fdr_d = torch.empty(N, dtype=torch.float64, device=dev)
-            _lib.cell_fdr(res.ncorr, res.valid, _to_dev(thr), _to_dev(pmin), coef_d, fdr_d)
-            fdr_h = _to_host_owned(fdr_d if stn.graph is None else stn.graph.unpermute(fdr_d))
-            yield
-            _adopt_column(data.obs, f"{key_added}_fdr", fdr_h)
-        columns_written.append(True)
-        mark("obs written")
-
-    def write_columns(fdrs, stop):
-        """Runs the remaining steps, returning early (to be resumed) once ``stop()`` is true."""
-        if not steps:
-            steps.append(column_steps(fdrs))
-        for _ in steps[0]:
-            if stop is not None and stop():
-                return
-
-    steps = []
-    early = comm is None and not return_full
-    core = _association(res, perms, Nnull=Nnull, local_test=local_test, show_progress=show_progress,
-                        idle_work=write_columns if early else None)
+            perms.cancel()  # joins the draw and hands numpy's generator its advanced state back
+    columns.write()
     svs = res.svs
-    if columns_written:
-        report()
-        return core.p
-
-    # ---- neighbourhood-level outputs (:228-237) ----
-    coef_d = torch.empty(N, dtype=torch.float64, device=dev)
-    fdr_d = torch.empty(N, dtype=torch.float64, device=dev)
-    if key_added in data.obs:
-        warnings.warn(f"Key '{key_added}' already exists in data.obs. Overwriting.")
-    thr, pmin = fdr_lookup_tables(core.fdrs)
-    _lib.cell_fdr(res.ncorr, res.valid, _to_dev(thr), _to_dev(pmin), coef_d, fdr_d)
-    both = torch.stack([coef_d, fdr_d], dim=1)  # [cells x 2]
-    if comm is not None:  # every rank ends with the full per-cell columns
-        pad = torch.zeros((stn.rows_per, 2), dtype=torch.float64, device=dev)
-        pad[:N] = both
-        both = comm.all_gather_rows(pad)[: len(data.obs)]
-    if stn.graph is not None:
-        both = stn.graph.unpermute(both)  # back to the caller's cell order
-    both = _to_host_pinned(both.t())
-    mark("results on host")
-    data.obs[key_added] = both[0]  # pandas copies on assignment (`both` is the reusable staging buffer)
-    if core.fdrs is not None:
-        data.obs[f"{key_added}_fdr"] = both[1]
+    LAST.__dict__.clear()
+    LAST.__dict__.update(svs=np.array(svs[:min(8, len(svs))]), k=core.k, fdr_5p_t=core.fdr_5p_t,
+                         fdr_10p_t=core.fdr_10p_t, p=core.p, n=n, r=res.r, ridge_log=list(res.ridge_log))
     if not return_full:
-        mark("obs written")
         report()
         return core.p
 
     # ---- full result surface (_nam.py:168-175, _association.py:223-225) ----
+    dev = res.ncorr.device
     vmask = _nam.to_caller_order(stn, res.valid).bool()
     kept = vmask.cpu().numpy()
     cells = data.obs.index[kept]
@@ -485,7 +534,7 @@ def association(data, y, sid_name, batches=None, covs=None, donorids=None, ks=No
     full.namresid_svs = pd.Series(svs, index=pcs)[:npcs]
     full.namresid_varexp = pd.Series(svs / n / len(cells), index=pcs)
     full.__dict__.update(vars(core))
-    full.ncorrs = pd.Series(both[0][kept], index=cells)
+    full.ncorrs = pd.Series(data.obs[key_added].to_numpy()[kept], index=cells)
     full.yresid = pd.Series(core.yresid, index=sids)
     cm = torch.as_tensor(colmap, device=dev, dtype=torch.long)
     nam_sel = (_nam.to_caller_order(stn, stn.s)[vmask][:, cm].double() * stn.inv_count[cm])

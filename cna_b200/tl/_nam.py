@@ -22,32 +22,36 @@ def _round_up(x, m):
     return (x + m - 1) // m * m
 
 
-def device_median(t, valid=None, comm=None, rows_per=None):
-    """``np.median`` of a 1-D device tensor: mean of the two middle order statistics, NaN if any
-    (valid) element is NaN.  ``valid`` (bool/uint8 mask) restricts the median to a subset; with a
-    ``comm`` the median is over the concatenation of every rank's values (all-gather of one padded
-    float64 vector).  One device sort and one small copy back."""
-    t = t.double()
-    n_valid = torch.tensor(float(t.numel()), dtype=torch.float64, device=t.device)
-    if valid is not None:
-        vb = valid.bool()
-        t = torch.where(vb, t, torch.full_like(t, float("inf")))  # dropped cells sort to the end
-        n_valid = vb.sum().double()
+_SKIP_BITS = 0x7FF4DEADBEEF0001  # CNA_MEDIAN_SKIP_BITS: entries cna_median_f64 ignores
+
+
+def median_device(t, valid=None, comm=None, rows_per=None):
+    """``np.median`` of a 1-D float64 device tensor, left on the device: returns a float64 tensor
+    [2] = (median, number of entries considered).  The median is the mean of the two middle order
+    statistics, NaN if any (valid) element is NaN or there is none.  ``valid`` (bool/uint8 mask)
+    restricts it to a subset; with a ``comm`` it is over the concatenation of every rank's values (one
+    all-gather of a padded vector in which masked and padding entries carry the skip pattern).
+    Asynchronous: ``cna_median_f64`` (radix select), no sort, nothing copied back."""
+    if t.dtype != torch.float64:
+        t = t.double()
+    t = t.contiguous()
+    out = torch.empty(2, dtype=torch.float64, device=t.device)
     if comm is not None:
-        pad = torch.full((rows_per,), float("inf"), dtype=torch.float64, device=t.device)
-        pad[: t.numel()] = t
-        t = comm.all_gather_rows(pad)
-        n_valid = comm.all_reduce(n_valid.reshape(1)).reshape(())
-    if t.numel() == 0:
-        return float("nan")
-    v, _ = torch.sort(t)  # NaNs sort last, after +inf
-    n = int(n_valid.item())
-    if n == 0:
-        return float("nan")
-    lo, hi, last = torch.stack([v[(n - 1) // 2], v[n // 2], v[-1]]).tolist()
-    if last != last:
-        return float("nan")
-    return (lo + hi) / 2
+        bits = t.view(torch.int64)
+        if valid is not None:
+            bits = torch.where(valid.bool(), bits, torch.full_like(bits, _SKIP_BITS))
+        pad = torch.full((rows_per,), _SKIP_BITS, dtype=torch.int64, device=t.device)
+        pad[: t.numel()] = bits
+        t, valid = comm.all_gather_rows(pad).view(torch.float64), None
+    elif valid is not None:
+        valid = valid.to(torch.uint8).contiguous()
+    _lib.median(t, valid, out)
+    return out
+
+
+def device_median(t, valid=None, comm=None, rows_per=None):
+    """``median_device`` copied back: a Python float (one synchronisation)."""
+    return float(median_device(t, valid=valid, comm=comm, rows_per=rows_per)[0].item())
 
 
 # ---------------------------------------------------------------------------------------------
@@ -107,8 +111,8 @@ class NamState:
         with np.errstate(divide="ignore"):
             self.inv_count = _to_dev(1.0 / counts)
         self.cell_index = cell_index
-        self.keep = None  # None = all cells kept
-        self.qc_threshold = None
+        self._keep = None         # explicit uint8 keep mask (tests, callers that bring their own)
+        self.qc_median = None     # device [2]: median of qc_kurt (cna_median_f64); None = no QC, keep all
         self.medkurt = []
         self.nsteps = 0
         self.comm = None  # set for cell-axis shards (cna_b200.sharded)
@@ -121,6 +125,29 @@ class NamState:
     @property
     def N(self):
         return self.s.shape[0]
+
+    @property
+    def qc_threshold(self):
+        """``_nam.py:94``: max(6, 2 * median batch kurtosis) (Python's max: a NaN median gives 6); None
+        without a QC.  Reads the median back from the device."""
+        if self.qc_median is None:
+            return None
+        return max(6, 2 * float(self.qc_median[0].item()))
+
+    @property
+    def keep(self):
+        """uint8 device mask of the cells that pass the QC (``_nam.py:96``), or None when every cell is
+        kept.  The hot path never materialises it: the residualisation pass takes the decision per row
+        from ``qc_kurt`` and the device-resident median."""
+        if self._keep is not None or self.qc_median is None:
+            return self._keep
+        two_med = 2 * self.qc_median[0]
+        thr = torch.where(two_med > 6, two_med, torch.full_like(two_med, 6.0))
+        return (self.qc_kurt < thr).to(torch.uint8)  # NaN -> dropped
+
+    @keep.setter
+    def keep(self, mask):
+        self._keep = mask
 
 
 def _r2_p20(s, old, S):
@@ -138,7 +165,7 @@ def _qc_plan(batches, labels, ld, dev):
     if batches is None or len(np.unique(batches)) == 1:
         return None
     ub, order, off = _batch_segments(batches.reindex(labels).to_numpy())  # _nam.py:79
-    if not 2 <= len(ub) <= 8:
+    if not 2 <= len(ub) <= 8 or ld // 4 > 128:  # the fused kernel's limits: <= 8 batches, <= 512 columns
         return None
     col_batch = np.full(ld, -1, dtype=np.int8)
     for b in range(len(ub)):
@@ -238,29 +265,27 @@ def _batch_segments(batch_values):
 
 
 def _qc_device(st, batches, show_progress=False):
-    """``_nam.py:85-99``.  Sets ``st.keep`` (uint8 device mask, or None when every cell is kept)."""
+    """``_nam.py:85-99``.  Leaves the per-cell batch kurtosis (``st.qc_kurt``) and its median
+    (``st.qc_median``) on the device; the keep decision ``kurt < max(6, 2 median)`` is taken by whoever
+    consumes the rows (``cna_resid_pass``, ``st.keep``).  Nothing is copied back unless progress output
+    is wanted."""
     out = select_output(show_progress)
+    st._keep, st.qc_median = None, None
     if len(np.unique(batches)) == 1:  # _nam.py:89
-        st.keep = None
         return
     b = batches.reindex(st.labels)  # _nam.py:79
     dev = st.s.device
-    if st.qc_kurt is not None and st.qc_batches is not None and b.equals(st.qc_batches):
-        kurt = st.qc_kurt  # already produced by the last diffusion step
-    else:
+    if not (st.qc_kurt is not None and st.qc_batches is not None and b.equals(st.qc_batches)):
+        # not already produced by the last diffusion step
         ub, order, off = _batch_segments(b.to_numpy())
-        kurt = torch.empty(st.N, dtype=torch.float64, device=dev)
-        _lib.batch_kurtosis(st.s, st.inv_count, _to_dev(order), _to_dev(off), kurt)
-    med = device_median(kurt, comm=st.comm, rows_per=st.rows_per)
-    threshold = max(6, 2 * med)  # _nam.py:94 (python max: a NaN median gives 6)
-    print("throwing out neighborhoods with batch kurtosis >=", threshold, file=out)
-    keep = kurt < threshold  # NaN -> dropped, _nam.py:96
+        st.qc_kurt = torch.empty(st.N, dtype=torch.float64, device=dev)
+        _lib.batch_kurtosis(st.s, st.inv_count, _to_dev(order), _to_dev(off), st.qc_kurt)
+    st.qc_median = median_device(st.qc_kurt, comm=st.comm, rows_per=st.rows_per)  # _nam.py:94
     if show_progress:
-        nkeep = keep.sum().double().reshape(1)
+        print("throwing out neighborhoods with batch kurtosis >=", st.qc_threshold, file=out)
+        nkeep = st.keep.sum().double().reshape(1)
         print("keeping", int((st.comm.all_reduce(nkeep) if st.comm is not None else nkeep).item()),
               "neighborhoods", file=out)
-    st.keep = keep.to(torch.uint8)
-    st.qc_threshold = threshold
 
 
 def nam(data, sid_name, batches=None, nsteps=None, self_weight=1, max_frac_pcs=0.15, suffix="",
@@ -285,16 +310,17 @@ def to_caller_order(st, t):
 
 
 def keep_mask(st):
-    if st.keep is None:
+    keep = st.keep
+    if keep is None:
         return np.repeat(True, st.N)
-    return to_caller_order(st, st.keep).bool().cpu().numpy()
+    return to_caller_order(st, keep).bool().cpu().numpy()
 
 
 def nam_frame(st, sid_name, rows=None, cols=None):
     """Materialise (a part of) the QC'd NAM as the reference's samples x cells DataFrame."""
     x = to_caller_order(st, st.s)[:, :st.S].double() * st.inv_count  # _nam.py:73
     keep = keep_mask(st)
-    if st.keep is not None:
+    if not keep.all():
         x = x[torch.as_tensor(keep, device=x.device)]
     arr = x.t().contiguous().cpu().numpy()
     df = pd.DataFrame(arr, index=st.labels, columns=st.cell_index[keep], dtype=float)
@@ -448,13 +474,21 @@ def projector(C, nb, ridge):
     return np.linalg.solve(CtC, C.T)
 
 
-def resid_nam_device(st, colmap, covs, batches, y_std, ridges=None, show_progress=False, want_x=True):
+def resid_nam_device(st, colmap, covs, batches, y_std, ridges=None, show_progress=False, want_x=True,
+                     speculate=False):
     """``_nam.py:118-177`` + ``_association.py:178-185`` + ``:77`` on the device.
 
     colmap : int array, state column of each of the n selected samples (phenotype order)
     covs   : [n x c] array or None;  batches : length-n array;  y_std : standardised phenotype.
     Returns a Namespace with the device tensors ``x`` [N x ld] (rows of dropped cells are zero),
-    ``ncorr`` [N], ``valid`` [N] and the host matrices M, C, W_last, W_cum, r, ridge log."""
+    ``ncorr`` [N], ``valid`` [N] and the host matrices M, C, W_last, r, ridge log.
+
+    The ridge walk (:141-155) stops at the first ridge whose median batch kurtosis is <= 6.  With
+    ``speculate`` only the first ridge is run and its median stays on the device (``res.ridge_median``):
+    the caller queues the downstream kernels behind it, reads the median back together with their
+    results and calls ``res.settle(median)``, which either confirms the guess or walks the remaining
+    ridges (returning False: the downstream work must be repeated).  Without it the walk synchronises
+    after every ridge, like the reference."""
     out = select_output(show_progress)
     n = len(colmap)
     dev = st.s.device
@@ -462,7 +496,7 @@ def resid_nam_device(st, colmap, covs, batches, y_std, ridges=None, show_progres
     r = C.shape[1]
     ld = _round_up(n, 8)
     # the fp32 matrix is only needed for the full result surface and for the CUDA-core Gram that
-    # takes over beyond the tensor-core kernel's 256-sample limit
+    # takes over beyond the tensor-core kernel's 512-sample limit
     want_x = want_x or n > TC_GRAM_MAX_N
     x = torch.empty((st.N, ld), dtype=torch.float32, device=dev) if want_x else None
     planes = _lib.Planes(st.N, n, dev)
@@ -470,14 +504,17 @@ def resid_nam_device(st, colmap, covs, batches, y_std, ridges=None, show_progres
     valid = torch.empty(st.N, dtype=torch.uint8, device=dev)
     colmap_d = _to_dev(np.asarray(colmap, dtype=np.int32))
     y_d = _to_dev(np.asarray(y_std, dtype=np.float64))
-    res = Namespace(x=x, planes=planes, ncorr=ncorr, valid=valid, n=n, r=r, C=C, ridge_log=[], comm=st.comm)
+    res = Namespace(x=x, planes=planes, ncorr=ncorr, valid=valid, n=n, r=r, C=C, ridge_log=[], comm=st.comm,
+                    ridge_median=None, settle=lambda med=None: True)
+    C_d = _to_dev(C) if r else None
+    row_keep = st._keep  # an explicit mask wins; otherwise the QC decision is taken inside the pass
+    qc_kurt = st.qc_kurt if (row_keep is None and st.qc_median is not None) else None
 
     def run(Wcum, seg=None, kurt=None):
-        C_d = _to_dev(C) if r else None
         W_d = _to_dev(np.ascontiguousarray(Wcum)) if r else None
-        _lib.resid_pass(st.s, st.inv_count, colmap_d, st.keep, C_d, W_d,
+        _lib.resid_pass(st.s, st.inv_count, colmap_d, row_keep, C_d, W_d,
                         seg[0] if seg else None, seg[1] if seg else None, y_d, x, kurt, ncorr, valid,
-                        planes=planes)
+                        planes=planes, qc_kurt=qc_kurt, qc_median=st.qc_median if qc_kurt is not None else None)
 
     if nb == 0:
         if r > 0:  # _nam.py:133
@@ -488,22 +525,49 @@ def resid_nam_device(st, colmap, covs, batches, y_std, ridges=None, show_progres
             res.M = np.eye(n)
         res.W_last = W
         run(W)
-    else:
-        _, order, off = _batch_segments(batches)
-        seg = (_to_dev(order), _to_dev(off))
-        kurt = torch.empty(st.N, dtype=torch.float64, device=dev)
-        Wcum = np.zeros((r, n))
-        for ridge in (DEFAULT_RIDGES if ridges is None else ridges):  # :141-144
-            W = projector(C, nb, ridge)
-            # the reference applies M = I - C.W cumulatively (:148); the product of such
-            # projectors is again I - C.W' with W' = W_prev + W - (W C) W_prev
-            Wcum = Wcum + W - W.dot(C).dot(Wcum)
-            run(Wcum, seg, kurt)
-            med = device_median(kurt, valid=valid, comm=st.comm, rows_per=st.rows_per)  # :150-155
-            res.ridge_log.append((ridge, med))
-            print("\twith ridge", ridge, "median batch kurtosis = ", med, file=out)
-            if med <= 6:
-                break
+        return res
+
+    _, order, off = _batch_segments(batches)
+    seg = (_to_dev(order), _to_dev(off))
+    kurt = torch.empty(st.N, dtype=torch.float64, device=dev)
+    ridge_list = list(DEFAULT_RIDGES if ridges is None else ridges)
+    walk = Namespace(Wcum=np.zeros((r, n)), next=0)
+
+    def step():
+        """One ridge of :141-148; returns the device median of the batch kurtosis (:150-153)."""
+        ridge = ridge_list[walk.next]
+        walk.next += 1
+        W = projector(C, nb, ridge)
+        # the reference applies M = I - C.W cumulatively (:148); the product of such projectors is
+        # again I - C.W' with W' = W_prev + W - (W C) W_prev
+        walk.Wcum = walk.Wcum + W - W.dot(C).dot(walk.Wcum)
+        run(walk.Wcum, seg, kurt)
         res.W_last = W
         res.M = np.eye(n) - C.dot(W)  # only the last M survives (:169)
+        return ridge, median_device(kurt, valid=valid, comm=st.comm, rows_per=st.rows_per)
+
+    def log(ridge, med):
+        res.ridge_log.append((ridge, med))
+        print("\twith ridge", ridge, "median batch kurtosis = ", med, file=out)
+        return med <= 6 or walk.next >= len(ridge_list)  # :154-155
+
+    def settle(med=None):
+        """Confirm the speculative first ridge with its median (read back by the caller), or walk on."""
+        res.settle = lambda med=None: True
+        if med is None:
+            med = float(res.ridge_median[0].item())
+        if log(ridge_list[0], med):
+            return True
+        while True:
+            ridge, med_d = step()
+            if log(ridge, float(med_d[0].item())):
+                return False
+
+    if not ridge_list:
+        raise UnboundLocalError("cannot access local variable 'M' where it is not associated with a value")
+    ridge, res.ridge_median = step()
+    if speculate and not show_progress:
+        res.settle = settle
+    else:
+        settle()
     return res

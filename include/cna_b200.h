@@ -29,7 +29,10 @@
 extern "C" {
 #endif
 
-#define CNA_B200_ABI_VERSION 2
+#define CNA_B200_ABI_VERSION 3
+
+/* bit pattern (a signalling NaN) of vector entries cna_median_f64 ignores: padding of gathered shards */
+#define CNA_MEDIAN_SKIP_BITS 0x7FF4DEADBEEF0001ull
 
 enum {
     CNA_OK = 0,
@@ -138,6 +141,11 @@ typedef struct cna_resid_args {
     void *x16_hi;
     void *x16_lo;
     int64_t ld16;
+    /* QC keep decision taken inside the pass (used when row_keep is NULL): keep row i iff
+     * qc_kurt[i] < max(6, 2 * qc_median[0]) (_nam.py:94-96; qc_median is what cna_median_f64 left on the
+     * device, so no host round trip separates the QC from the residualisation).  Both NULL: keep all. */
+    const double *qc_kurt;
+    const double *qc_median;
 } cna_resid_args;
 
 /* replaces: _association.py:178-185 (reindex, filter, zero-variance drop), _nam.py:122 (centre),
@@ -242,6 +250,35 @@ int cna_null_hist_tc(const void *xh, const void *xl, int64_t ld16, int64_t n_row
 int cna_obs_hist(const double *ncorr, const uint8_t *row_valid, int64_t n_rows, const double *edges,
                  const double *thresholds, int n_edges, uint32_t *rank_hist, uint32_t *det_hist,
                  void *stream);
+
+/* The same histograms with the number of edges left on the device by cna_fdr_thresholds (n_edges is
+ * then the capacity of the tables; n_edges_dev == NULL: exactly cna_obs_hist). */
+int cna_obs_hist_dev(const double *ncorr, const uint8_t *row_valid, int64_t n_rows, const double *edges,
+                     const double *thresholds, int n_edges, const int32_t *n_edges_dev, uint32_t *rank_hist,
+                     uint32_t *det_hist, void *stream);
+
+/* cna_null_hist_tc with the number of edges (and the rejection bound derived from edges[0]) read from
+ * device memory: the null GEMM can be queued behind cna_fdr_thresholds without the host ever seeing
+ * max |ncorr|.  n_edges = capacity; edge0 is ignored when n_edges_dev != NULL. */
+int cna_null_hist_tc_dev(const void *xh, const void *xl, int64_t ld16, int64_t n_rows, int n,
+                         const void *yth, const void *ytl, int64_t ld16_y, int n_null, const double *edges,
+                         int n_edges, const int32_t *n_edges_dev, double edge0, uint64_t *hist, void *stream);
+
+/* np.median of a float64 device vector, left on the device: out[0] = median over the entries with
+ * valid[i] != 0 (valid may be NULL) whose bit pattern is not CNA_MEDIAN_SKIP_BITS; NaN when one of them
+ * is NaN or none exists (numpy's semantics); out[1] = number of entries considered.  Radix select on the
+ * sortable bit pattern (4 passes of 16 bits + one pass for the lower median of an even population);
+ * workspace of cna_median_workspace() bytes, contents irrelevant on entry.
+ * replaces: _nam.py:59, :94, :153 `np.median(...)` (and the host round trip a host median implies). */
+int64_t cna_median_workspace(void);
+int cna_median_f64(const double *v, const uint8_t *valid, int64_t n, double *out, void *workspace,
+                   int64_t workspace_bytes, void *stream);
+
+/* thresholds[0..T) = np.arange(m/4, m, m/400) with m = max(maxabs[0], 0.001), edges[i] = t_i^2 - 1e-8 -
+ * 1e-5 t_i^2, n_thresholds[0] = T (<= cap; entries beyond T are zero), computed with numpy's own sequence
+ * of float64 operations.  replaces: _association.py:101-102, _stats.py:51. */
+int cna_fdr_thresholds(const double *maxabs, int cap, double *thresholds, double *edges, int32_t *n_thresholds,
+                       void *stream);
 
 /* out[0] = max_i |v_i| over valid rows (0 if none).  replaces: _association.py:101. out zeroed by caller. */
 int cna_absmax(const double *v, const uint8_t *row_valid, int64_t n_rows, double *out, void *stream);

@@ -453,6 +453,66 @@ def test_obs_columns_do_not_alias_the_staging_buffer(cna):
     np.testing.assert_allclose(data.obs["second"].to_numpy(), -first, rtol=1e-12, atol=1e-15)
 
 
+def test_device_median_numpy_semantics(cna):
+    """cna_median_f64 (radix select, result left on the device) against np.median: odd / even sizes,
+    duplicates around the middle, masks, the skip pattern, infinities, signed zeros, NaN, empty."""
+    import torch
+    from cna_b200 import _lib
+    from cna_b200.tl._nam import device_median, median_device
+    rng = np.random.default_rng(0)
+    for n in (1, 2, 3, 7, 10, 1001, 4096, 100_003, 1_000_000):
+        v = rng.normal(size=n)
+        assert device_median(torch.as_tensor(v).cuda()) == np.median(v)
+        w = np.round(v, 1 if n > 100 else 0)  # many duplicates, also across the middle
+        assert device_median(torch.as_tensor(w).cuda()) == np.median(w)
+        k = rng.gamma(2.0, 1.0, n) * 10 ** rng.integers(-3, 3)  # clustered exponents, like kurtoses
+        assert device_median(torch.as_tensor(k).cuda()) == np.median(k)
+        mask = rng.random(n) > 0.4
+        mask[0] = True
+        got = median_device(torch.as_tensor(v).cuda(), valid=torch.as_tensor(mask).cuda()).cpu().numpy()
+        assert got[0] == np.median(v[mask]) and got[1] == mask.sum()
+    v = rng.normal(size=1000)
+    v[::7] = np.inf
+    v[1::7] = -np.inf
+    v[2::50] = 0.0
+    v[3::50] = -0.0
+    assert device_median(torch.as_tensor(v).cuda()) == np.median(v)
+    skip = np.full(300, _lib.median_skip_value()[0])
+    both = torch.as_tensor(np.concatenate([v, skip])).cuda()
+    got = median_device(both).cpu().numpy()
+    assert got[0] == np.median(v) and got[1] == len(v)
+    v[3] = np.nan
+    assert np.isnan(device_median(torch.as_tensor(v).cuda()))
+    masked = np.ones(len(v), dtype=bool)
+    masked[3] = False  # a masked NaN does not count
+    assert device_median(torch.as_tensor(v).cuda(), valid=torch.as_tensor(masked).cuda()) == np.median(v[masked])
+    assert np.isnan(device_median(torch.empty(0, dtype=torch.float64, device="cuda")))
+    assert np.isnan(device_median(torch.ones(5, dtype=torch.float64, device="cuda"),
+                                  valid=torch.zeros(5, dtype=torch.uint8, device="cuda")))
+
+
+def test_device_fdr_thresholds_match_numpy(cna):
+    """cna_fdr_thresholds against np.arange(m/4, m, m/400) and _stats.threshold_edges, bit for bit."""
+    import torch
+    from cna_b200 import _lib
+    from cna_b200.tl import _stats
+    from cna_b200.tl._association import THRESHOLD_CAP
+    rng = np.random.default_rng(1)
+    ms = np.concatenate([10 ** rng.uniform(-4, 0.3, 400), [0.0, 1e-9, 0.001, 0.25, 1.0]])
+    thr_d = torch.empty(THRESHOLD_CAP, dtype=torch.float64, device="cuda")
+    edges_d = torch.empty(THRESHOLD_CAP, dtype=torch.float64, device="cuda")
+    cnt_d = torch.empty(1, dtype=torch.int32, device="cuda")
+    for m in ms:
+        _lib.fdr_thresholds(torch.tensor([m], dtype=torch.float64, device="cuda"), thr_d, edges_d, cnt_d)
+        mm = max(float(m), 0.001)
+        want = np.arange(mm / 4, mm, mm / 400)
+        T = int(cnt_d.item())
+        assert T == len(want)
+        np.testing.assert_array_equal(thr_d.cpu().numpy()[:T], want)
+        np.testing.assert_array_equal(edges_d.cpu().numpy()[:T], _stats.threshold_edges(want))
+        assert (thr_d.cpu().numpy()[T:] == 0).all()
+
+
 def _default_ks(n):
     from cna_b200.tl._association import default_ks
     return default_ks(n)

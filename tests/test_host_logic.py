@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/cna_b200.h but not exported"
     assert declared == set(_lib.EXPORTS)
-    assert lib.cna_abi_version() == 2
+    assert lib.cna_abi_version() == 3
     assert isinstance(lib.cna_last_error(), bytes)
     # every entry point is documented: a "replaces:" citation in the header, a row in INTEGRATION.md
     integration = open(os.path.join(ROOT, "INTEGRATION.md")).read()
@@ -171,15 +171,21 @@ def test_f_statistics_match_oracle():
     np.testing.assert_allclose(r22, rr, rtol=1e-12)
 
 
-def test_device_median_numpy_semantics():
-    from cna_b200.tl._nam import device_median
+def test_fdr_threshold_arithmetic_matches_numpy_arange():
+    """csrc/select.cu derives the FDR thresholds on the device with numpy's own sequence of float64
+    operations (arange: length = ceil((stop - start) / step), values start + i * ((start + step) - start)).
+    This pins that restatement against np.arange itself; the kernel is compared with np.arange on the GPU."""
+    import math
     rng = np.random.default_rng(0)
-    for n in (1, 2, 7, 10, 1001):
-        v = rng.normal(size=n)
-        assert device_median(torch.as_tensor(v)) == np.median(v)
-    v[3] = np.nan
-    assert np.isnan(device_median(torch.as_tensor(v)))
-    assert np.isnan(device_median(torch.empty(0, dtype=torch.float64)))
+    for it in range(20000):
+        m = float(10 ** rng.uniform(-3, 0.5))
+        ref = np.arange(m / 4, m, m / 400)
+        start, step = m / 4, m / 400
+        T = math.ceil((m - start) / step)
+        delta = (start + step) - start
+        t = start + np.arange(T, dtype=np.float64) * delta
+        t[0], t[1] = start, start + step
+        assert T == len(ref) and np.array_equal(t, ref)
 
 
 def test_batch_segments():

@@ -53,8 +53,7 @@ def test_shard_bounds_and_slicing():
 
 
 def _comm_checks(rank, world):
-    from cna_b200.sharded import Comm, shard_bounds
-    from cna_b200.tl._nam import device_median
+    from cna_b200.sharded import Comm
     comm = Comm()
     assert (comm.rank, comm.world) == (rank, world)
     t = torch.full((3,), float(rank + 1), dtype=torch.float64)
@@ -67,23 +66,35 @@ def _comm_checks(rank, world):
     assert [p.numel() for p in comm.all_gather_padded(torch.zeros(0, dtype=torch.int64))] == [0, 0]
     b = torch.arange(5, dtype=torch.int32) if rank == 0 else torch.zeros(5, dtype=torch.int32)
     assert comm.broadcast(b).tolist() == list(range(5))
-    # global median == numpy median of the concatenation, with masks, NaNs and a short tail shard
-    rng = np.random.default_rng(0)
-    for n in (11, 12, 2, 1):
-        full = rng.normal(size=n)
-        valid = rng.random(n) > 0.3
-        valid[0] = True
-        r0, r1, rows_per = shard_bounds(n, world, rank)
-        loc = torch.as_tensor(full[r0:r1])
-        assert device_median(loc, comm=comm, rows_per=rows_per) == np.median(full)
-        got = device_median(loc, valid=torch.as_tensor(valid[r0:r1]), comm=comm, rows_per=rows_per)
-        assert got == np.median(full[valid])
-        full[0] = np.nan
-        assert np.isnan(device_median(torch.as_tensor(full[r0:r1]), comm=comm, rows_per=rows_per))
 
 
 def test_comm_helpers_gloo_world2():
     _spawn(_comm_checks, 2)
+
+
+def _median_checks(rank, world):
+    """global median == numpy median of the concatenation, with masks, NaNs and a short tail shard"""
+    from cna_b200.sharded import Comm, shard_bounds
+    from cna_b200.tl._nam import device_median
+    torch.cuda.set_device(0)
+    comm = Comm()
+    rng = np.random.default_rng(0)
+    for n in (11, 12, 2, 1, 5001):
+        full = rng.normal(size=n)
+        valid = rng.random(n) > 0.3
+        valid[0] = True
+        r0, r1, rows_per = shard_bounds(n, world, rank)
+        loc = torch.as_tensor(full[r0:r1]).cuda()
+        assert device_median(loc, comm=comm, rows_per=rows_per) == np.median(full)
+        got = device_median(loc, valid=torch.as_tensor(valid[r0:r1]).cuda(), comm=comm, rows_per=rows_per)
+        assert got == np.median(full[valid])
+        full[0] = np.nan
+        assert np.isnan(device_median(torch.as_tensor(full[r0:r1]).cuda(), comm=comm, rows_per=rows_per))
+
+
+@pytest.mark.gpu
+def test_sharded_median_world2():
+    _spawn(_median_checks, 2)
 
 
 def _sharded_vs_single(rank, world, spec, reorder=False):
