@@ -213,6 +213,38 @@ def pin_graph(A):
     return undo
 
 
+def check_block(obs, key="coef"):
+    """Result fingerprint of the last association() call (every rank of a sharded run ends with the full
+    data.obs columns): discriminates a correct run from a fast wrong one, and is compared across N and
+    against the CPU oracle (profiles/r02_oracle_C.json)."""
+    from cna_b200.tl import _association as A
+    coef = obs[key].to_numpy()
+    fdr = obs[key + "_fdr"].to_numpy() if key + "_fdr" in obs else np.full(len(coef), np.nan)
+    last = A.LAST
+    return {
+        "p": float(last.p), "k": int(last.k), "n_kept": int(np.isfinite(coef).sum()),
+        "n_fdr05": int((fdr <= 0.05).sum()), "n_fdr10": int((fdr <= 0.10).sum()),
+        "fdr_5p_t": None if last.fdr_5p_t is None else float(last.fdr_5p_t),
+        "fdr_10p_t": None if last.fdr_10p_t is None else float(last.fdr_10p_t),
+        "svs": [float(v) for v in last.svs[:4]], "sum_abs_coef": float(np.nansum(np.abs(coef))),
+    }
+
+
+def checks_agree(a, b, rtol=1e-5):
+    """Integer fields exactly, floats to the north-star tolerance (the Gram is summed in a different
+    order on a different number of GPUs; cells within rounding of an FDR threshold may flip)."""
+    for key in ("p", "k", "n_kept"):
+        if a[key] != b[key]:
+            return False
+    for key in ("n_fdr05", "n_fdr10"):
+        if abs(a[key] - b[key]) > max(3, 1e-4 * max(a[key], b[key])):
+            return False
+    for key in ("fdr_5p_t", "fdr_10p_t", "sum_abs_coef"):
+        if (a[key] is None) != (b[key] is None) or (a[key] is not None and abs(a[key] - b[key]) > rtol * abs(b[key])):
+            return False
+    return bool(np.allclose(a["svs"], b["svs"], rtol=rtol))
+
+
 def rooflines(prof, steps, N, S, n, nnz, K, Kl, s_steps, peaks):
     """Per-kernel achieved rates from the CUDA-event profile of the timed steps.
     Algorithmic bytes / flops per launch follow SURVEY.md 8(d) and DESIGN.md."""
@@ -312,11 +344,15 @@ def run_ours(args):
             step_dev()
         launches0 = _lib.launch_count()
         with ClockSampler(local) as clk:
-            _lib.profile_start()
             ms = timed(step_dev, args.steps)
-            prof = _lib.profile_stop()
         launches = _lib.launch_count() - launches0
-        p_value = step_dev()
+        # per-kernel CUDA-event pairs are recorded in a separate, untimed pass of the same step
+        prof_steps = min(args.steps, 5)
+        _lib.profile_start()
+        for _ in range(prof_steps):
+            p_value = step_dev()
+        prof = _lib.profile_stop()
+        check = check_block(data.obs)
         e2e = None
         if not args.no_e2e:
             undo = pin_graph(A)
@@ -324,6 +360,8 @@ def run_ours(args):
                 step_e2e()
             ms_e2e = timed(step_e2e, args.steps)
             undo()
+            check_e2e = check_block(data.obs)
+            check["e2e_agrees"] = checks_agree(check_e2e, check)
             h2d = (A.data.nbytes + A.indices.nbytes + A.indptr.nbytes) + 4 * N * world
             d2h = 2 * 8 * N + 8 * n * n + 8 * K * 5
             e2e = {"value": N * args.steps / (ms_e2e * 1e-3), "unit": "cells/s", "ms_per_step": ms_e2e / args.steps,
@@ -332,9 +370,17 @@ def run_ours(args):
     if rank != 0:
         dist.destroy_process_group()
         return
+    if world > 1:  # the same call on one GPU (outside every timed region): the shards must reproduce it
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            cna.tl.association(cna.tl.to_device(data), **kw)
+        single = check_block(data.obs)
+        check["single_gpu"] = single
+        check["agrees_with_single_gpu"] = checks_agree(check, single)
+        assert check["agrees_with_single_gpu"], (check, single)
     peaks = measured_peaks()
     # per-kernel work of one launch = this rank's share of the cells (and of the stored edges)
-    roofs = rooflines(prof, args.steps, N // world, S, n, nnz // world, K, Kl, s_steps, peaks)
+    roofs = rooflines(prof, prof_steps, N // world, S, n, nnz // world, K, Kl, s_steps, peaks)
     spmm = next((r for r in roofs if r["kernel"] == "cna_diffuse_step_f32"), None)
     primary = None
     if spmm:
@@ -353,7 +399,7 @@ def run_ours(args):
         "config": {"workload": workload_name(args.config), "nnz": nnz, "l2": "inputs larger than L2 (no flush)",
                    "parallelism": f"cell-axis shards x{world}" if world > 1 else "single GPU",
                    "p_value": p_value, "datagen_s": round(gen_s, 1)},
-        "clocks": clk.summary(), "e2e": e2e, "gpu_launches": launches / args.steps,
+        "clocks": clk.summary(), "e2e": e2e, "gpu_launches": launches / args.steps, "check": check,
         "roofline": primary, "rooflines": roofs,
     }
     if not args.no_cpu_baseline and world == 1:

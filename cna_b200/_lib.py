@@ -70,6 +70,8 @@ _SIGNATURES = {
     "cna_diffuse_step_f32": [_VP, _VP, _VP, _VP, _VP, _VP, _I64, _INT, _I64, _I64, _VP],
     "cna_diffuse_step_f32_qc": [_VP, _VP, _VP, _VP, _VP, _VP, _I64, _INT, _I64, _I64, _VP, _VP, _VP, _INT, _VP, _VP],
     "cna_diffuse_step_f64": [_VP, _VP, _VP, _VP, _VP, _VP, _I64, _INT, _I64, _I64, _VP],
+    "cna_diffuse_tile_limits": [_VP, _VP],
+    "cna_diffuse_step_f32_tiled": [_VP, _VP, _VP, _VP, _VP, _I64, _I64, _INT, _I64, _I64, _VP, _VP, _VP, _INT, _INT, _VP],
     "cna_row_kurtosis": [_VP, _I64, _I64, _INT, _VP, _VP, _VP],
     "cna_batch_kurtosis": [_VP, _I64, _I64, _VP, _VP, _VP, _INT, _INT, _VP, _VP],
     "cna_resid_pass": [ctypes.POINTER(ResidArgs), _VP],
@@ -98,7 +100,6 @@ _SIGNATURES = {
     "cna_split_f16": [_VP, _I64, _I64, _INT, _INT, _VP, _VP, _I64, _I64, _VP],
     "cna_gram_tc": [_VP, _VP, _I64, _I64, _INT, _VP, _VP, _I64, _VP],
     "cna_right_multiply_tc": [_VP, _VP, _I64, _I64, _INT, _VP, _VP, _I64, _INT, _VP, _I64, _VP],
-    "cna_host_refine_order": [_VP, _VP, _I64, _VP, _VP, _I64, _INT, _VP, _INT],
     "cna_null_hist_tc": [_VP, _VP, _I64, _I64, _INT, _VP, _VP, _I64, _INT, _VP, _INT, _DBL, _VP, _VP],
     "cna_null_hist_tc_dev": [_VP, _VP, _I64, _I64, _INT, _VP, _VP, _I64, _INT, _VP, _INT, _VP, _DBL, _VP, _VP],
 }
@@ -228,6 +229,22 @@ def diffuse_step_qc(indptr, indices, vals, diag, src, dst, n_cols, col_batch, in
           src.shape[1], int(row_offset), _ptr(col_batch, torch.int8, "col_batch"),
           _ptr(inv_count_ld, torch.float64, "inv_count"), _ptr(batch_inv, torch.float64, "batch_inv"),
           batch_inv.numel(), _ptr(kurt, torch.float64, "kurt"), _stream())
+
+
+def diffuse_tile_limits():
+    """(output rows per tile, distinct source rows per tile) of the shared-memory-staged SpMM."""
+    a, b = ctypes.c_int32(0), ctypes.c_int32(0)
+    load().cna_diffuse_tile_limits(ctypes.addressof(a), ctypes.addressof(b))
+    return a.value, b.value
+
+
+def diffuse_step_tiled(indptr, plan, diag, src, dst, n_cols, n_rows=None, row_offset=0, stage_mode=0):
+    """``plan``: TilePlan (tile_row, tile_u, usrc, epair) of the graph whose rows ``indptr`` describes."""
+    _call("cna_diffuse_step_f32_tiled", _ptr(indptr, torch.int32, "indptr"), _ptr(plan.epair, torch.int32, "epair"),
+          _ptr(diag, torch.float32, "diag"), _ptr(src, torch.float32, "src"), _ptr(dst, torch.float32, "dst"),
+          dst.shape[0] if n_rows is None else int(n_rows), src.shape[0], int(n_cols), src.shape[1], int(row_offset),
+          _ptr(plan.tile_row, torch.int32, "tile_row"), _ptr(plan.tile_u, torch.int32, "tile_u"),
+          _ptr(plan.usrc, torch.int32, "usrc"), plan.n_tiles, int(stage_mode), _stream())
 
 
 def row_kurtosis(s, n_samples, inv_count, kurt):
@@ -536,24 +553,6 @@ def host_perm_blocks(block_off, src_pos, num, n_threads=0):
     with _LegacyState() as st:
         _host_call("cna_host_perm_blocks", *st.args(), len(block_off) - 1, block_off.ctypes.data,
                    None if sp is None else sp.ctypes.data, int(num), out.ctypes.data, total, int(n_threads))
-    return out
-
-
-def host_refine_order(indptr, indices, order, inv, block, window=8, n_threads=0):
-    """Greedy re-ordering of the rows inside every ``block`` of a cell order (host arrays in, host
-    array out; see cna_host_refine_order in the header).  ``indptr`` / ``indices``: the caller-order
-    CSR; ``order``: stored position -> caller row; ``inv``: its inverse."""
-    import numpy as np
-    indptr = np.ascontiguousarray(indptr, dtype=np.int32)
-    indices = np.ascontiguousarray(indices, dtype=np.int32)
-    order = np.ascontiguousarray(order, dtype=np.int64)
-    inv = np.ascontiguousarray(inv, dtype=np.int32)
-    n = len(indptr) - 1
-    if len(order) != n or len(inv) != n:
-        raise ValueError("order / inv must have one entry per row")
-    out = np.empty(n, dtype=np.int64)
-    _host_call("cna_host_refine_order", indptr.ctypes.data, indices.ctypes.data, n, order.ctypes.data,
-               inv.ctypes.data, int(block), int(window), out.ctypes.data, int(n_threads))
     return out
 
 

@@ -9,6 +9,7 @@
 // Reference: src/cna/tools/_nam.py:78-99 (QC), :118-159 (_resid_nam), _association.py:175-185
 // (reindex, filter, zero-variance drop), :77 (ncorrs).
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -347,36 +348,45 @@ __device__ __forceinline__ void butterfly16(double (&v)[16], int lane) {
 
 template <int NQ, int R>
 __global__ void __launch_bounds__(256, 2) resid_lin_kernel(cna_resid_args a, ResidTables tb) {
+    // Every table row is padded to LDN = 32 NQ columns with zeros and the number of functionals to a
+    // multiple of FPC with zero rows, and the padding columns of a row are read as 0 * s[row][colmap[0]],
+    // so the inner loops carry no bounds checks and address the tables with compile-time offsets.
+    constexpr int LDN = 32 * NQ;
+    constexpr int FPC = 16 / R;  // functionals per butterfly
     extern __shared__ double sm[];
     const int warps = blockDim.x >> 5;
-    const int n = a.n, r = a.r, nb = a.n_batches, m1 = tb.m1, nbk = tb.nbk;
-    double *F = sm;                          // [m1][n]
-    double *Ct = F + size_t(m1) * n;         // [r][n]
-    double *invc = Ct + size_t(r) * n;       // [n]
-    double *cbar = invc + n;                 // [nbk][r] batch means of the columns of C
+    const int n = a.n, r = a.r, m1 = tb.m1, nbk = tb.nbk;
+    const int m1p = (m1 + FPC - 1) / FPC * FPC, tws = m1p + 3;
+    double *F = sm;                          // [m1p][LDN]: ones, y, W rows, batch-mean rows
+    double *Ct = F + m1p * LDN;              // [r][LDN]
+    double *invc = Ct + r * LDN;             // [LDN]
+    double *cbar = invc + LDN;               // [nbk][r] batch means of the columns of C
     double *cy = cbar + nbk * r;             // [r] C^T y, then [1] sum(y)
-    double *tot = cy + r + 1;                // [warps][R][m1 + 3]
-    int *colmap = reinterpret_cast<int *>(tot + size_t(warps) * R * (m1 + 3));  // [n]
+    double *tot = cy + r + 1;                // [warps][R][tws]
+    int *colmap = reinterpret_cast<int *>(tot + warps * R * tws);  // [LDN]
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 
     // ---- tables (a few thousand flops per CTA) ----
-    for (int t = threadIdx.x; t < n; t += blockDim.x) {
-        const int c = a.colmap[t];
+    for (int t = threadIdx.x; t < (m1p + r) * LDN; t += blockDim.x) F[t] = 0.0;  // F and Ct
+    for (int t = threadIdx.x; t < LDN; t += blockDim.x) {
+        const int c = t < n ? a.colmap[t] : a.colmap[0];
         colmap[t] = c;
-        invc[t] = a.inv_count[c];
+        invc[t] = t < n ? a.inv_count[c] : 0.0;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < n; t += blockDim.x) {
         F[t] = 1.0;
-        F[n + t] = a.y[t];
+        F[LDN + t] = a.y[t];
     }
     for (int t = threadIdx.x; t < r * n; t += blockDim.x) {
-        F[2 * n + t] = a.Wt[t];
-        Ct[t] = a.C[(t % n) * r + t / n];
+        const int rr = t / n, m = t % n;
+        F[(2 + rr) * LDN + m] = a.Wt[t];
+        Ct[rr * LDN + m] = a.C[m * r + rr];
     }
-    for (int t = threadIdx.x; t < nbk * n; t += blockDim.x) F[size_t(2 + r) * n + t] = 0.0;
-    __syncthreads();
     for (int b = w; b < nbk; b += warps) {
         const int t0 = a.seg_off[b], t1 = a.seg_off[b + 1];
         const double inv = 1.0 / double(t1 - t0);
-        for (int t = t0 + lane; t < t1; t += 32) F[size_t(2 + r + b) * n + a.seg_order[t]] = inv;
+        for (int t = t0 + lane; t < t1; t += 32) F[(2 + r + b) * LDN + a.seg_order[t]] = inv;
         for (int rr = 0; rr < r; ++rr) {
             double acc = 0.0;
             for (int t = t0 + lane; t < t1; t += 32) acc += a.C[a.seg_order[t] * r + rr];
@@ -392,47 +402,44 @@ __global__ void __launch_bounds__(256, 2) resid_lin_kernel(cna_resid_args a, Res
     }
     __syncthreads();
 
-    double *tw = tot + size_t(w) * R * (m1 + 3);
-    const double dn = double(n);
+    double *tw = tot + w * R * tws;
+    const double dn = double(n), inv_n = 1.0 / dn, inv_nm1 = 1.0 / (dn - 1.0);
     double thr = 0.0;
     if (a.qc_kurt) {  // _nam.py:94: threshold = max(6, 2 * median) with Python's max (NaN -> 6)
         const double two_med = 2.0 * a.qc_median[0];
         thr = two_med > 6.0 ? two_med : 6.0;
     }
-    const int64_t stride = int64_t(gridDim.x) * warps * R;
-    for (int64_t row0 = (int64_t(blockIdx.x) * warps + w) * R; row0 < a.n_rows; row0 += stride) {
+    const int *cml = colmap + lane;
+    const double *icl = invc + lane;
+    const double *Fl = F + lane, *Cl = Ct + lane;
+    const int stride = gridDim.x * warps * R;
+    for (int64_t row0 = int64_t(blockIdx.x * warps + w) * R; row0 < a.n_rows; row0 += stride) {
         double x[R][NQ];
 #pragma unroll
         for (int i = 0; i < R; ++i) {
             const int64_t row = row0 + i < a.n_rows ? row0 + i : row0;
             const float *p = a.s + row * a.ld_s;
 #pragma unroll
-            for (int q = 0; q < NQ; ++q) {
-                const int m = lane + 32 * q;
-                x[i][q] = m < n ? double(__ldg(p + colmap[m])) * invc[m] : 0.0;
-            }
+            for (int q = 0; q < NQ; ++q) x[i][q] = double(__ldg(p + cml[32 * q])) * icl[32 * q];
         }
-        // ---- the m1 functionals, 16 (= 16 / R per row) at a time ----
-        constexpr int FPC = 16 / R;  // functionals per chunk
-        for (int f0 = 0; f0 < m1; f0 += FPC) {
+        // ---- the functionals, 16 (= FPC per row) at a time ----
+        for (int f0 = 0; f0 < m1p; f0 += FPC) {
             double acc[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) acc[j] = 0.0;
+            const double *Fp = Fl + f0 * LDN;
 #pragma unroll
             for (int q = 0; q < NQ; ++q) {
-                const int m = lane + 32 * q;
-                if (m < n) {
 #pragma unroll
-                    for (int f = 0; f < FPC; ++f) {
-                        const double c = f0 + f < m1 ? F[size_t(f0 + f) * n + m] : 0.0;
+                for (int f = 0; f < FPC; ++f) {
+                    const double c = Fp[f * LDN + 32 * q];
 #pragma unroll
-                        for (int i = 0; i < R; ++i) acc[f * R + i] = fma(x[i][q], c, acc[f * R + i]);
-                    }
+                    for (int i = 0; i < R; ++i) acc[f * R + i] = fma(x[i][q], c, acc[f * R + i]);
                 }
             }
             butterfly16(acc, lane);
-            const int j = lane >> 1, f = j / R, i = j % R;
-            if (!(lane & 1) && f0 + f < m1) tw[i * (m1 + 3) + f0 + f] = acc[0];
+            const int j = lane >> 1;
+            if (!(lane & 1)) tw[(j % R) * tws + f0 + j / R] = acc[0];
         }
         __syncwarp();
         // ---- x' and the sums of squares ----
@@ -441,30 +448,26 @@ __global__ void __launch_bounds__(256, 2) resid_lin_kernel(cna_resid_args a, Res
         for (int j = 0; j < 16; ++j) sq[j] = 0.0;
         double mean[R];
 #pragma unroll
-        for (int i = 0; i < R; ++i) mean[i] = tw[i * (m1 + 3)] / dn;
+        for (int i = 0; i < R; ++i) mean[i] = tw[i * tws] * inv_n;
 #pragma unroll
         for (int q = 0; q < NQ; ++q) {
-            const int m = lane + 32 * q;
-            if (m < n) {
+            const double one = Fl[32 * q];  // 1 for real columns, 0 for padding
 #pragma unroll
-                for (int i = 0; i < R; ++i) {
-                    x[i][q] -= mean[i];  // _nam.py:122
-                    sq[i] = fma(x[i][q], x[i][q], sq[i]);
-                }
+            for (int i = 0; i < R; ++i) {
+                x[i][q] = fma(-mean[i], one, x[i][q]);  // _nam.py:122
+                sq[i] = fma(x[i][q], x[i][q], sq[i]);
             }
         }
         for (int rr = 0; rr < r; ++rr) {  // rank-r update X <- X - (X W^T) C^T  (_nam.py:133-135 / :146-148)
             double pr[R];
 #pragma unroll
-            for (int i = 0; i < R; ++i) pr[i] = tw[i * (m1 + 3) + 2 + rr];
+            for (int i = 0; i < R; ++i) pr[i] = -tw[i * tws + 2 + rr];
+            const double *Cp = Cl + rr * LDN;
 #pragma unroll
             for (int q = 0; q < NQ; ++q) {
-                const int m = lane + 32 * q;
-                if (m < n) {
-                    const double cv = Ct[rr * n + m];
+                const double cv = Cp[32 * q];
 #pragma unroll
-                    for (int i = 0; i < R; ++i) x[i][q] = fma(-pr[i], cv, x[i][q]);
-                }
+                for (int i = 0; i < R; ++i) x[i][q] = fma(pr[i], cv, x[i][q]);
             }
         }
 #pragma unroll
@@ -478,7 +481,7 @@ __global__ void __launch_bounds__(256, 2) resid_lin_kernel(cna_resid_args a, Res
         butterfly16(sq, lane);
         {
             const int j = lane >> 1;
-            if (!(lane & 1) && j < 3 * R) tw[(j % R) * (m1 + 3) + m1 + j / R] = sq[0];
+            if (!(lane & 1) && j < 3 * R) tw[(j % R) * tws + m1p + j / R] = sq[0];
         }
         __syncwarp();
         // ---- per-row scalars: lane i < R finishes row i ----
@@ -486,26 +489,26 @@ __global__ void __launch_bounds__(256, 2) resid_lin_kernel(cna_resid_args a, Res
         bool ok = false;
         if (lane < R && row0 + lane < a.n_rows) {
             const int64_t row = row0 + lane;
-            const double *t = tw + lane * (m1 + 3);
-            const double mu = t[0] / dn;
+            const double *t = tw + lane * tws;
+            const double mu = t[0] * inv_n;
             bool keep = true;
             if (a.row_keep) keep = a.row_keep[row] != 0;
             else if (a.qc_kurt) keep = a.qc_kurt[row] < thr;  // NaN -> dropped, _nam.py:96
-            ok = keep && !(t[m1] / (dn - 1.0) == 0.0);  // _association.py:182-185
+            ok = keep && !(t[m1p] == 0.0);  // variance of the selected samples == 0, _association.py:182-185
             double kurt = nan("");
             if (nbk > 0 && ok) {  // _nam.py:78-82 on the residualised row
                 double mm = 0.0;
                 for (int b = 0; b < nbk; ++b) {
-                    double v = t[2 + r + b] - mu;
-                    for (int rr = 0; rr < r; ++rr) v = fma(-cbar[b * r + rr], t[2 + rr], v);
-                    mm += v;
+                    double vb = t[2 + r + b] - mu;
+                    for (int rr = 0; rr < r; ++rr) vb = fma(-cbar[b * r + rr], t[2 + rr], vb);
+                    mm += vb;
                 }
                 mm /= nbk;
                 double m2 = 0.0, m4 = 0.0;
                 for (int b = 0; b < nbk; ++b) {
-                    double v = t[2 + r + b] - mu;
-                    for (int rr = 0; rr < r; ++rr) v = fma(-cbar[b * r + rr], t[2 + rr], v);
-                    const double d2 = (v - mm) * (v - mm);
+                    double vb = t[2 + r + b] - mu;
+                    for (int rr = 0; rr < r; ++rr) vb = fma(-cbar[b * r + rr], t[2 + rr], vb);
+                    const double d2 = (vb - mm) * (vb - mm);
                     m2 += d2;
                     m4 += d2 * d2;
                 }
@@ -513,31 +516,31 @@ __global__ void __launch_bounds__(256, 2) resid_lin_kernel(cna_resid_args a, Res
             }
             if (a.kurt) a.kurt[row] = kurt;
             // ddof=1 standardisation (_nam.py:159; pandas std is taken around the mean of x')
-            const double s1 = t[m1 + 2] / dn;
-            inv_std = 1.0 / sqrt((t[m1 + 1] - dn * s1 * s1) / (dn - 1.0));
+            const double s1 = t[m1p + 2] * inv_n;
+            inv_std = rsqrt((t[m1p + 1] - dn * s1 * s1) * inv_nm1);
             double d = t[1] - mu * cy[r];  // x'.y = x.y - mean * sum(y) - (C^T y).p
             for (int rr = 0; rr < r; ++rr) d = fma(-cy[rr], t[2 + rr], d);
-            a.ncorr[row] = ok ? d * inv_std / dn : 0.0;  // _association.py:77
+            a.ncorr[row] = ok ? d * inv_std * inv_n : 0.0;  // _association.py:77
             a.row_valid[row] = ok ? 1 : 0;
         }
 #pragma unroll
         for (int i = 0; i < R; ++i) {
             const int64_t row = row0 + i;
             if (row >= a.n_rows) break;  // uniform over the warp
-            const double sc = __shfl_sync(kFull, inv_std, i);
-            const bool valid = __shfl_sync(kFull, int(ok), i) != 0;
+            const double sc = __shfl_sync(kFull, ok ? inv_std : 0.0, i);  // rows of dropped cells are zero
             float *o = a.x_out ? a.x_out + row * a.ld_x : nullptr;
             __half *ph = a.x16_hi ? static_cast<__half *>(a.x16_hi) + row * a.ld16 : nullptr;
             __half *pl = a.x16_hi ? static_cast<__half *>(a.x16_lo) + row * a.ld16 : nullptr;
 #pragma unroll
             for (int q = 0; q < NQ; ++q) {
                 const int m = lane + 32 * q;
-                const double v = (m < n && valid) ? x[i][q] * sc : 0.0;  // rows of dropped cells are zero
-                if (o && m < a.ld_x) o[m] = float(v);
-                if (ph && m < a.ld16) {  // v = hi + lo to 2^-22
-                    const __half h = __float2half_rn(float(v));
+                const float v = float(x[i][q] * sc);
+                // NQ <= 8 is instantiated exactly (NQ == ceil(n / 32)): only the last column group can run past the row
+                if (o && ((NQ <= 8 && q < NQ - 1) || m < a.ld_x)) o[m] = v;
+                if (ph && ((NQ <= 8 && q < NQ - 1) || m < a.ld16)) {  // v = hi + lo to 2^-22 (the difference is exact in fp32)
+                    const __half h = __float2half_rn(v);
                     ph[m] = h;
-                    pl[m] = __float2half_rn(float(v - double(__half2float(h))));
+                    pl[m] = __float2half_rn(v - __half2float(h));
                 }
             }
         }
@@ -593,9 +596,12 @@ int cna_resid_pass(const cna_resid_args *args, void *stream) {
         ResidTables tb;
         tb.nbk = want_kurt ? a.n_batches : 0;
         tb.m1 = 2 + a.r + tb.nbk;
-        const int R = nq <= 8 ? 4 : (nq <= 16 ? 2 : 1);
-        size_t smem = sizeof(double) * (size_t(tb.m1) * a.n + size_t(a.r) * a.n + a.n + size_t(tb.nbk) * a.r +
-                                        a.r + 1 + size_t(warps) * R * (tb.m1 + 3)) + sizeof(int) * size_t(a.n);
+        static const int r_env = getenv("CNA_RESID_R") ? atoi(getenv("CNA_RESID_R")) : 0;  // experiments
+        const int R = (r_env == 2 && nq >= 5 && nq <= 8) ? 2 : (nq <= 8 ? 4 : (nq <= 16 ? 2 : 1));
+        const int fpc = 16 / R, m1p = (tb.m1 + fpc - 1) / fpc * fpc;
+        const int nqt = nq <= 8 ? nq : (nq <= 16 ? 16 : 32), ldn = 32 * nqt;
+        size_t smem = sizeof(double) * (size_t(m1p + a.r + 1) * ldn + size_t(tb.nbk) * a.r + a.r + 1 +
+                                        size_t(warps) * R * (m1p + 3)) + sizeof(int) * size_t(ldn);
         if (smem <= 100 * 1024) {
             int64_t blocks_needed = (a.n_rows + int64_t(warps) * R - 1) / (int64_t(warps) * R);
             int64_t cap = int64_t(num_sms()) * 8;
@@ -611,10 +617,10 @@ int cna_resid_pass(const cna_resid_args *args, void *stream) {
                 case 2: CNA_RESID_LIN(2, 4); break;
                 case 3: CNA_RESID_LIN(3, 4); break;
                 case 4: CNA_RESID_LIN(4, 4); break;
-                case 5: CNA_RESID_LIN(5, 4); break;
-                case 6: CNA_RESID_LIN(6, 4); break;
-                case 7: CNA_RESID_LIN(7, 4); break;
-                case 8: CNA_RESID_LIN(8, 4); break;
+                case 5: if (R == 2) CNA_RESID_LIN(5, 2); else CNA_RESID_LIN(5, 4); break;
+                case 6: if (R == 2) CNA_RESID_LIN(6, 2); else CNA_RESID_LIN(6, 4); break;
+                case 7: if (R == 2) CNA_RESID_LIN(7, 2); else CNA_RESID_LIN(7, 4); break;
+                case 8: if (R == 2) CNA_RESID_LIN(8, 2); else CNA_RESID_LIN(8, 4); break;
                 case 16: CNA_RESID_LIN(16, 2); break;
                 default: CNA_RESID_LIN(32, 1);
             }

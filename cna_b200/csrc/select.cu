@@ -13,7 +13,8 @@
 
 namespace cna {
 
-constexpr int kSelBits = 16, kSelBins = 1 << kSelBits, kSelPasses = 64 / kSelBits;
+constexpr int kSelBits = 11, kSelBins = 1 << kSelBits, kSelPasses = (64 + kSelBits - 1) / kSelBits;  // 6 passes
+constexpr int kSelThreads = 1024;
 constexpr unsigned long long kSkipBits = CNA_MEDIAN_SKIP_BITS;
 
 struct SelectState {
@@ -22,8 +23,9 @@ struct SelectState {
     unsigned long long n_valid;   // finite or infinite, non-NaN, not masked
     unsigned long long n_nan;
     unsigned long long max_less;  // largest key strictly below the selected one (0 if none)
+    unsigned long long n_less;    // elements strictly below the selected key
     unsigned int blocks_done;
-    unsigned int n_less;          // elements strictly below the selected key
+    unsigned int pad;
 };
 
 __device__ __forceinline__ unsigned long long sortable(double v) {
@@ -35,79 +37,82 @@ __device__ __forceinline__ double unsortable(unsigned long long k) {
     return __longlong_as_double((long long)u);
 }
 
-// PASS p looks at digit p (from the top) of every key whose higher digits equal the prefix found so
-// far.  The last block to finish scans the histogram, extends the prefix and clears the histogram for
-// the next pass.  Pass 0 also counts the population and the NaNs and turns "the upper median" into a
-// rank.
+// PASS p looks at digit p (from the top, 11 bits, the last one 9) of every key whose higher digits equal
+// the prefix found so far.  Counts go to a shared-memory histogram per CTA (kurtoses share their exponent:
+// the hot bins would serialise in L2), non-empty bins are flushed to the global one, and the last CTA to
+// finish scans it, extends the prefix and clears it for the next pass.  Pass 0 also counts the
+// population and the NaNs and turns "the upper median" into a rank.
 template <int PASS>
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(kSelThreads)
 select_pass_kernel(const double *__restrict__ v, const uint8_t *__restrict__ valid, int64_t n,
                    unsigned int *__restrict__ hist, SelectState *__restrict__ st) {
-    const int lane = threadIdx.x & 31;
-    const int shift = 64 - kSelBits * (PASS + 1);
-    const unsigned long long prefix = PASS == 0 ? 0ull : st->prefix;
+    constexpr int kHigh = PASS * kSelBits;                                   // bits already decided
+    constexpr int kBits = 64 - kHigh < kSelBits ? 64 - kHigh : kSelBits;     // width of this digit
+    constexpr int kShift = 64 - kHigh - kBits;
+    __shared__ unsigned int h[kSelBins];
+    __shared__ unsigned long long wsum[kSelThreads / 32];
+    __shared__ bool last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int b = threadIdx.x; b < kSelBins; b += kSelThreads) h[b] = 0;
+    __syncthreads();
+    unsigned long long prefix = 0;
+    if (PASS > 0) prefix = st->prefix;
     unsigned int my_nan = 0;
-    const int64_t stride = int64_t(gridDim.x) * blockDim.x;
-    const int64_t n_pad = (n + 31) / 32 * 32;  // whole warps stay in the loop: match_any needs them
-    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n_pad; i += stride) {
-        unsigned int bin = 0x80000000u | lane;  // no partner, not counted
-        if (i < n && (!valid || valid[i])) {
-            const double x = v[i];
-            const unsigned long long raw = (unsigned long long)__double_as_longlong(x);
-            if (raw == kSkipBits) {
-            } else if (x != x) {
-                if (PASS == 0) ++my_nan;
-            } else {
-                const unsigned long long key = sortable(x);
-                if (PASS == 0 || (key >> (shift + kSelBits)) == (prefix >> (shift + kSelBits)))
-                    bin = (unsigned int)((key >> shift) & (kSelBins - 1));
-            }
+    const int64_t stride = int64_t(gridDim.x) * kSelThreads;
+    for (int64_t i = int64_t(blockIdx.x) * kSelThreads + threadIdx.x; i < n; i += stride) {
+        if (valid && !valid[i]) continue;
+        const double x = v[i];
+        if (x != x) {  // NaN (counted, numpy's median is then NaN) or the skip pattern (ignored)
+            if (PASS == 0 && (unsigned long long)__double_as_longlong(x) != kSkipBits) ++my_nan;
+            continue;
         }
-        // values cluster (kurtoses share their exponent): one atomic per distinct digit per warp
-        const unsigned int peers = __match_any_sync(kFull, bin);
-        if (!(bin & 0x80000000u) && lane == __ffs(peers) - 1) atomicAdd(hist + bin, (unsigned int)__popc(peers));
+        const unsigned long long key = sortable(x);
+        if (PASS > 0 && ((key ^ prefix) >> (64 - (PASS > 0 ? kHigh : 1))) != 0) continue;
+        atomicAdd(h + (unsigned int)((key >> kShift) & ((1u << kBits) - 1)), 1u);
     }
     if (PASS == 0) {
         my_nan = __reduce_add_sync(kFull, my_nan);
         if (lane == 0 && my_nan) atomicAdd(&st->n_nan, (unsigned long long)my_nan);
     }
-    __shared__ bool last;
-    __shared__ unsigned long long part[512];
+    __syncthreads();
+    for (int b = threadIdx.x; b < kSelBins; b += kSelThreads)
+        if (h[b]) atomicAdd(hist + b, h[b]);
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) last = atomicAdd(&st->blocks_done, 1u) == gridDim.x - 1;
     __syncthreads();
     if (!last) return;
     __threadfence();
-    // ---- the last block: find the digit that holds the wanted rank ----
-    constexpr int kPer = kSelBins / 512;
-    unsigned long long sum = 0;
-    for (int b = 0; b < kPer; ++b) sum += __ldcg(hist + threadIdx.x * kPer + b);
-    part[threadIdx.x] = sum;
+    // ---- the last CTA: the bin whose cumulative count first exceeds the wanted rank (2 bins per thread) ----
+    const unsigned long long c0 = __ldcg(hist + 2 * threadIdx.x), c1 = __ldcg(hist + 2 * threadIdx.x + 1);
+    unsigned long long incl = c0 + c1;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long up = __shfl_up_sync(kFull, incl, o);
+        if (lane >= o) incl += up;
+    }
+    if (lane == 31) wsum[warp] = incl;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        unsigned long long total = 0;
-        for (int t = 0; t < 512; ++t) total += part[t];
-        unsigned long long rank = st->rank;
-        if (PASS == 0) {
-            st->n_valid = total;
-            rank = total / 2;  // upper median; the lower one is resolved by select_finish_kernel
-        }
-        unsigned long long before = 0;
-        int t = 0;
-        while (t < 511 && before + part[t] <= rank) before += part[t++];
-        int b = t * kPer;
-        for (;; ++b) {
-            const unsigned long long c = __ldcg(hist + b);
-            if (before + c > rank || b == t * kPer + kPer - 1) break;
-            before += c;
-        }
-        st->prefix = prefix | ((unsigned long long)b << shift);
-        st->rank = rank - before;
+    unsigned long long base = 0, total = 0;
+    for (int k = 0; k < kSelThreads / 32; ++k) {
+        const unsigned long long t = wsum[k];
+        if (k < warp) base += t;
+        total += t;
+    }
+    incl += base;
+    const unsigned long long excl = incl - (c0 + c1);
+    unsigned long long rank = PASS == 0 ? total / 2 : st->rank;  // pass 0: the upper median
+    if (PASS == 0 && threadIdx.x == 0) st->n_valid = total;
+    __syncthreads();  // every thread has read st->rank before it is rewritten
+    bool mine = rank < total ? (excl <= rank && rank < incl) : threadIdx.x == kSelThreads - 1;  // empty: NaN anyway
+    if (mine) {
+        const bool second = rank < total && rank >= excl + c0;
+        const unsigned long long b = 2 * threadIdx.x + (second ? 1 : 0);
+        st->prefix = prefix | (b << kShift);
+        st->rank = rank < total ? rank - excl - (second ? c0 : 0) : 0;
         st->blocks_done = 0;
     }
-    __syncthreads();
-    for (int b = threadIdx.x; b < kSelBins; b += 512) hist[b] = 0;
+    for (int b = threadIdx.x; b < kSelBins; b += kSelThreads) hist[b] = 0;
 }
 
 // With the selected key known: count / find the largest of the elements below it (the lower median of an
@@ -116,8 +121,7 @@ __global__ void __launch_bounds__(512)
 select_finish_kernel(const double *__restrict__ v, const uint8_t *__restrict__ valid, int64_t n,
                      SelectState *__restrict__ st, double *__restrict__ out) {
     const unsigned long long sel = st->prefix;
-    unsigned long long best = 0;
-    unsigned int less = 0;
+    unsigned long long best = 0, less = 0;
     const int64_t stride = int64_t(gridDim.x) * blockDim.x;
     for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
         if (valid && !valid[i]) continue;
@@ -129,10 +133,10 @@ select_finish_kernel(const double *__restrict__ v, const uint8_t *__restrict__ v
             best = key > best ? key : best;
         }
     }
-    less = __reduce_add_sync(kFull, less);
     for (int o = 16; o > 0; o >>= 1) {
         const unsigned long long other = __shfl_xor_sync(kFull, best, o);
         best = other > best ? other : best;
+        less += __shfl_xor_sync(kFull, less, o);
     }
     if ((threadIdx.x & 31) == 0) {
         if (less) atomicAdd(&st->n_less, less);
@@ -155,7 +159,7 @@ select_finish_kernel(const double *__restrict__ v, const uint8_t *__restrict__ v
         double lo = hi;
         // even population: the lower median has rank nv/2 - 1; it is below `hi` only when no duplicate of
         // `hi` sits in front of rank nv/2
-        if ((nv & 1ull) == 0 && (unsigned long long)(*((volatile unsigned int *)&st->n_less)) == nv / 2)
+        if ((nv & 1ull) == 0 && *((volatile unsigned long long *)&st->n_less) == nv / 2)
             lo = unsortable(*((volatile unsigned long long *)&st->max_less));
         med = __dmul_rn(__dadd_rn(lo, hi), 0.5);  // np.mean of the two middle values
     }
@@ -205,16 +209,19 @@ int cna_median_f64(const double *v, const uint8_t *valid, int64_t n, double *out
     unsigned int *hist = static_cast<unsigned int *>(workspace);
     SelectState *st = reinterpret_cast<SelectState *>(hist + kSelBins);
     CNA_CUDA(cudaMemsetAsync(workspace, 0, size_t(cna_median_workspace()), s));
-    int64_t blocks = (n + 511) / 512;
-    const int64_t cap = int64_t(num_sms()) * 4;
+    int64_t blocks = (n + 4 * kSelThreads - 1) / (4 * kSelThreads);
+    const int64_t cap = int64_t(num_sms());
     unsigned grid = unsigned(blocks < 1 ? 1 : (blocks < cap ? blocks : cap));
-    select_pass_kernel<0><<<grid, 512, 0, s>>>(v, valid, n, hist, st);
-    select_pass_kernel<1><<<grid, 512, 0, s>>>(v, valid, n, hist, st);
-    select_pass_kernel<2><<<grid, 512, 0, s>>>(v, valid, n, hist, st);
-    select_pass_kernel<3><<<grid, 512, 0, s>>>(v, valid, n, hist, st);
+    static_assert(kSelPasses == 6, "one launch per digit below");
+    select_pass_kernel<0><<<grid, kSelThreads, 0, s>>>(v, valid, n, hist, st);
+    select_pass_kernel<1><<<grid, kSelThreads, 0, s>>>(v, valid, n, hist, st);
+    select_pass_kernel<2><<<grid, kSelThreads, 0, s>>>(v, valid, n, hist, st);
+    select_pass_kernel<3><<<grid, kSelThreads, 0, s>>>(v, valid, n, hist, st);
+    select_pass_kernel<4><<<grid, kSelThreads, 0, s>>>(v, valid, n, hist, st);
+    select_pass_kernel<5><<<grid, kSelThreads, 0, s>>>(v, valid, n, hist, st);
     select_finish_kernel<<<grid, 512, 0, s>>>(v, valid, n, st, out);
     CNA_LAUNCHED("select_pass_kernel");
-    count_launch(4);
+    count_launch(kSelPasses);
     return CNA_OK;
 }
 

@@ -102,7 +102,7 @@ class ShardedData:
 
     def __init__(self, data, comm=None, resident=True):
         """``resident=False``: a shard built for one call (cheaper cell ordering: no pseudo-peripheral
-        root sweep, no local refinement), like the graph ``association(data)`` builds for a host object."""
+        root sweep), like the graph ``association(data)`` builds for a host object."""
         from .tl._graph import DeviceGraph, get_connectivity
         self._host = data
         self.comm = comm or Comm()

@@ -398,8 +398,10 @@ def _association(res, perms, Nnull=1000, local_test=True, show_progress=False, c
     back_a, tabs = phase_a()
     if columns is not None:
         columns.start_coef()
-    early_b = perms is None or perms.done()
-    b = phase_b(tabs) if early_b else None
+    # phase B needs the permutation indices: queued now when the draw has already finished (or when this
+    # rank only receives them), otherwise as soon as the Gram is here if the draw has finished by then,
+    # otherwise after the decomposition
+    b = phase_b(tabs) if (perms is None or perms.done()) else None
     while True:
         Gh, med_h, mx_h = back_a.get()
         mark("gram on host")
@@ -411,6 +413,8 @@ def _association(res, perms, Nnull=1000, local_test=True, show_progress=False, c
         if columns is not None:
             columns.start_coef()
         b = phase_b(tabs) if b is not None else None
+    if b is None and perms.done():
+        b = phase_b(tabs)
     U, svs, res.G = _nam.svd_of_gram(Gh.copy(), res.svd_top)
     res.U, res.svs = U, svs
     o = observed_test(U)

@@ -75,17 +75,6 @@ def _bfs_far_node(indptr, indices, n, root, max_levels):
     return int(frontier.min().item())  # min: independent of the order of discovery
 
 
-LOCAL_ORDER_BLOCK = 16384  # rows per block of the local refinement of the cell order of resident graphs
-
-
-def local_order_block():
-    """Block size of the host-side local refinement of the cell order of resident graphs
-    (``CNA_B200_LOCAL_ORDER`` overrides; 0 = off).  16 384 rows: in the cache model calibrated against
-    the measured L1 hit rate and DRAM traffic of the SpMM it takes the L1 hit rate
-    of the gathers from 23.5 % to 41 % at unchanged DRAM traffic (65 536 rows: 44 %, +24 % DRAM)."""
-    return int(os.environ.get("CNA_B200_LOCAL_ORDER", str(LOCAL_ORDER_BLOCK)))
-
-
 def cuthill_mckee_order(indptr, indices, n, max_levels=4096, max_roots=8, far_root=True):
     """Cuthill-McKee ordering of a symmetric CSR on the device (csrc/reorder.cu): breadth-first levels
     from a pseudo-peripheral root, each level sorted by (position of its first parent, node id).
@@ -186,10 +175,6 @@ class DeviceGraph:
             mark("graph: cell order computed")
             if res is not None:
                 self.order, self.inv = res
-                block = local_order_block()
-                if resident and block > 0 and self.n_total >= 8 * block:  # blocks well inside the band
-                    self._refine_order(A, block)
-                    mark("graph: cell order refined")
                 deg = (indptr[1:] - indptr[:-1])[self.order]
                 new_indptr = torch.zeros(self.n_total + 1, dtype=torch.int32, device=indptr.device)
                 new_indptr[1:] = torch.cumsum(deg, 0)
@@ -213,21 +198,6 @@ class DeviceGraph:
         self.nnz = int(indices.numel())
         self.indptr, self.indices, self.data = indptr, indices, data
         self._scaled = {}
-
-    def _refine_order(self, A, block):
-        """Greedy re-ordering of the rows inside every block of the Cuthill-McKee order, on the host
-        (csrc/order_host.cpp): more shared neighbours between the rows of a CTA of the diffusion SpMM.
-        A pure layout optimisation: if it cannot be done the Cuthill-McKee order stays, with a warning."""
-        try:
-            refined = _lib.host_refine_order(A.indptr, A.indices, self.order.cpu().numpy(),
-                                             self.inv.cpu().numpy(), block)
-            order = _to_dev(refined, torch.int64)
-            inv = torch.empty(self.n_total, dtype=torch.int32, device=order.device)
-            inv[order] = torch.arange(self.n_total, dtype=torch.int32, device=order.device)
-        except Exception as exc:  # noqa: BLE001 - any failure leaves a valid (unrefined) order behind
-            warnings.warn(f"cna_b200: local refinement of the cell order skipped ({exc})")
-            return
-        self.order, self.inv = order, inv
 
     def _plan_halo(self, indices, row1):
         """kNN halo of this shard, gathered once: the sorted remote row ids its edges reference
@@ -283,6 +253,65 @@ class DeviceGraph:
                              row_offset=self.row0)
             self._scaled[key] = (vals, diag)
         return self._scaled[key]
+
+
+class TilePlan:
+    """Plan of the shared-memory-staged diffusion step (csrc/diffuse_tiled.cu) for one resident CSR:
+    consecutive output rows are cut into tiles of at most ``tile_rows`` rows whose edges reference at
+    most ``tile_sources`` distinct source rows (a tile that would exceed it is halved until it fits).
+
+      tile_row [T + 1] int32   first output row of each tile
+      tile_u   [T + 1] int32   offsets into ``usrc`` (multiples of 4)
+      usrc     int32           sorted distinct source rows of every tile, padded to a multiple of 4
+      epair    [nnz, 2] int32  per stored edge (CSR order): 128 * (position of its source in the tile's
+                               list), bits of the fp32 weight
+
+    Built with a handful of device sorts when the graph is made resident (not on the timed path)."""
+
+    def __init__(self, indptr, indices, vals, n_src_rows):
+        tile_rows, cap = _lib.diffuse_tile_limits()
+        dev = indptr.device
+        n = indptr.numel() - 1
+        deg = (indptr[1:] - indptr[:-1]).long()
+        row_of_edge = torch.repeat_interleave(torch.arange(n, device=dev), deg)
+        cols = indices.long()
+        starts = torch.arange(0, max(n, 1), tile_rows, device=dev)
+        for _ in range(8):
+            tile_of_row = torch.searchsorted(starts, torch.arange(n, device=dev), right=True) - 1
+            keys = tile_of_row[row_of_edge] * n_src_rows + cols
+            ukeys, inv = torch.unique(keys, sorted=True, return_inverse=True)
+            utile = torch.div(ukeys, n_src_rows, rounding_mode="floor")
+            ucount = torch.bincount(utile, minlength=starts.numel())
+            bad = torch.nonzero(ucount > cap).reshape(-1)
+            if bad.numel() == 0:
+                break
+            ends = torch.cat([starts[1:], torch.tensor([n], device=dev)])
+            mid = (starts[bad] + ends[bad]) // 2
+            if (mid == starts[bad]).any():
+                raise _lib.CnaError(f"a single row references more than {cap} distinct rows")
+            starts = torch.sort(torch.cat([starts, mid])).values
+        else:
+            raise _lib.CnaError("could not cut the graph into tiles")
+        T = starts.numel()
+        padded = (ucount + 3) // 4 * 4
+        tile_u = torch.zeros(T + 1, dtype=torch.int64, device=dev)
+        tile_u[1:] = torch.cumsum(padded, 0)
+        first = torch.zeros(T + 1, dtype=torch.int64, device=dev)  # offsets into the unpadded unique list
+        first[1:] = torch.cumsum(ucount, 0)
+        usrc = torch.empty(int(tile_u[-1].item()), dtype=torch.int64, device=dev)
+        # padding entries repeat the tile's first source row (any valid row will do: never referenced)
+        usrc[:] = torch.repeat_interleave((ukeys % n_src_rows)[first[:-1].clamp(max=max(ukeys.numel() - 1, 0))],
+                                          padded) if ukeys.numel() else 0
+        pos_in_tile = torch.arange(ukeys.numel(), device=dev) - first[utile]
+        usrc[tile_u[utile] + pos_in_tile] = ukeys % n_src_rows
+        lpos = inv - first[tile_of_row[row_of_edge]]
+        self.epair = torch.stack([(lpos * 128).to(torch.int32), vals.view(torch.int32)], dim=1).contiguous()
+        self.tile_row = torch.cat([starts, torch.tensor([n], device=dev)]).to(torch.int32)
+        self.tile_u = tile_u.to(torch.int32)
+        self.usrc = usrc.to(torch.int32)
+        self.n_tiles = T
+        self.n_sources = int(ucount.sum().item())
+        self.nnz = int(cols.numel())
 
 
 class ResidentData:

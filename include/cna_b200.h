@@ -90,6 +90,22 @@ int cna_diffuse_step_f64(const int32_t *indptr, const int32_t *indices, const do
                          const double *diag, const double *in, double *out, int64_t n_rows,
                          int n_cols, int64_t ld, int64_t in_row_offset, void *stream);
 
+/* The same step with the gathered rows staged in shared memory (csrc/diffuse_tiled.cu): bit-identical
+ * results, a source row crosses L2 -> SM once per tile instead of once per edge.  The plan is made once per
+ * resident graph (cna_b200/tl/_graph.py:TilePlan): consecutive output rows are cut into tiles of at most
+ * `tile_rows` rows whose edges reference at most `tile_sources` distinct source rows
+ * (cna_diffuse_tile_limits); tile_row[n_tiles + 1] = first row of each tile; usrc = the distinct source rows
+ * (positions in `in`, whose row count is in_rows) of every tile, each list padded to a multiple of 4 with
+ * valid rows; tile_u[n_tiles + 1] = offsets into usrc; epair[nnz] = per stored edge, in CSR order,
+ * {uint32 128 * (position of its source in the tile's list), float weight}.
+ * stage_mode 0: cp.async.bulk.tensor tile::gather4 (TMA), 1: cp.async.
+ * replaces: _nam.py:33 (as cna_diffuse_step_f32). */
+int cna_diffuse_tile_limits(int32_t *tile_rows, int32_t *tile_sources);
+int cna_diffuse_step_f32_tiled(const int32_t *indptr, const void *epair, const float *diag, const float *in,
+                               float *out, int64_t n_rows, int64_t in_rows, int n_cols, int64_t ld,
+                               int64_t in_row_offset, const int32_t *tile_row, const int32_t *tile_u,
+                               const int32_t *usrc, int n_tiles, int stage_mode, void *stream);
+
 /* Per-cell excess kurtosis (biased, Fisher) across samples of s[i,:]*inv_count[:].
  * replaces: _nam.py:59 `st.kurtosis(s/C, axis=1)`.  kurt[n_rows] fp64 (NaN where scipy gives NaN). */
 int cna_row_kurtosis(const float *s, int64_t ld, int64_t n_rows, int n_samples,
@@ -344,16 +360,6 @@ void *cna_host_perm_blocks_async(uint32_t *key, int *pos, int *has_gauss, double
                                  int32_t *out, int64_t ld_out, int n_threads);
 int cna_host_perm_done(void *handle);
 int cna_host_perm_wait(void *handle);
-
-/* Host-side local refinement of a cell order (csrc/order_host.cpp): every block of `block`
- * consecutive stored positions keeps its place, the rows inside it are re-ordered greedily so that the
- * next row is the unplaced row with the most edges into the last `window` placed rows (more shared
- * neighbours between the rows of a CTA = more L1 hits in the diffusion SpMM).  indptr / indices: the
- * caller-order CSR in host memory; order[n]: stored position -> caller row; inv[n]: its inverse;
- * order_out[n]: the refined stored position -> caller row.  Deterministic; n_threads = 0 picks the
- * host's core count.  No reference counterpart (a property of the layout in HBM, like cna_bfs_expand). */
-int cna_host_refine_order(const int32_t *indptr, const int32_t *indices, int64_t n, const int64_t *order,
-                          const int32_t *inv, int64_t block, int window, int64_t *order_out, int n_threads);
 
 /* ------------------------------------------------------------------------------------------
  * utilities used by the data generator (not on the timed path)

@@ -405,40 +405,6 @@ def test_cell_reordering_is_transparent(cna, demo, synth, monkeypatch):
     np.testing.assert_allclose(nam_r.to_numpy(), nam_p.to_numpy(), rtol=1e-6, atol=1e-12)
 
 
-@pytest.mark.skipif(os.environ.get("CNA_B200_TEST_LOCAL_ORDER") != "1",
-                    reason="written without a GPU at hand (round 1 ran out of GPU budget): opt in with "
-                           "CNA_B200_TEST_LOCAL_ORDER=1 until it has been run once")
-def test_local_order_refinement_is_transparent(cna, monkeypatch):
-    """The local refinement of the cell order of resident graphs (csrc/order_host.cpp) is still a
-    permutation that keeps every block of the Cuthill-McKee order in place, and results do not change."""
-    from cna_b200.tl._graph import DeviceGraph
-    A = cases.demo_anndata().obsp["connectivities"]
-    N = A.shape[0]
-    monkeypatch.setenv("CNA_B200_LOCAL_ORDER", "0")
-    base = DeviceGraph(A, reorder=True)
-    monkeypatch.setenv("CNA_B200_LOCAL_ORDER", "512")
-    g = DeviceGraph(A, reorder=True)
-    order, inv = g.order.cpu().numpy(), g.inv.cpu().numpy()
-    assert sorted(order.tolist()) == list(range(N)) and (inv[order] == np.arange(N)).all()
-    cm = base.order.cpu().numpy()
-    assert (order != cm).any()
-    for b in range(0, N, 512):
-        assert set(order[b:b + 512]) == set(cm[b:b + 512])
-    Ap = sp.csr_matrix((g.data.cpu().numpy(), g.indices.cpu().numpy(), g.indptr.cpu().numpy()), shape=A.shape)
-    assert abs(Ap - A[order][:, order]).max() == 0
-
-    class D:
-        pass
-    d = D()
-    d.obsp = {"connectivities": A}
-    d.obs = cases.demo_anndata().obs
-    s0 = np.random.default_rng(0).normal(size=(N, 3))
-    monkeypatch.setenv("CNA_B200_REORDER", "1")
-    refined = cna.tl.diffuse(cna.tl.to_device(d), s0, 2)
-    monkeypatch.setenv("CNA_B200_LOCAL_ORDER", "0")
-    np.testing.assert_allclose(refined, cna.tl.diffuse(cna.tl.to_device(d), s0, 2), rtol=1e-11, atol=1e-15)
-
-
 def test_obs_columns_do_not_alias_the_staging_buffer(cna):
     """The per-cell results travel through a reusable pinned staging buffer: a second call must not
     change the columns written by the first."""
@@ -453,6 +419,28 @@ def test_obs_columns_do_not_alias_the_staging_buffer(cna):
     np.testing.assert_allclose(data.obs["second"].to_numpy(), -first, rtol=1e-12, atol=1e-15)
 
 
+@pytest.mark.parametrize("n,S,deg", [(3000, 50, 7), (5000, 200, 30), (700, 333, 9), (257, 3, 4)])
+def test_tiled_diffusion_step_is_bit_identical(cna, n, S, deg):
+    """cna_diffuse_step_f32_tiled (shared-memory-staged rows: TMA tile::gather4 or cp.async) performs the
+    additions of every row in the same order as cna_diffuse_step_f32: identical bits, hub row included."""
+    import torch
+    from cna_b200 import _lib
+    from cna_b200.tl import _graph
+    A = _random_graph(n, deg, seed=n + S, hub=n // 2 if n < 2000 else None)  # hub row: n / 3 neighbours
+    g = _graph.DeviceGraph(A, reorder=False)
+    vals, diag = g.scaled(1, torch.float32)
+    ld = (S + 7) // 8 * 8
+    src = torch.zeros((n, ld), device="cuda")
+    src[:, :S] = torch.rand((n, S), device="cuda")
+    ref = torch.empty_like(src)
+    _lib.diffuse_step(g.indptr, g.indices, vals, diag, src, ref, S)
+    plan = _graph.TilePlan(g.indptr, g.indices, vals, g.n)
+    for mode in (0, 1):
+        out = torch.full_like(src, float("nan"))
+        _lib.diffuse_step_tiled(g.indptr, plan, diag, src, out, S, stage_mode=mode)
+        assert torch.equal(out[:, :S], ref[:, :S])
+
+
 def test_device_median_numpy_semantics(cna):
     """cna_median_f64 (radix select, result left on the device) against np.median: odd / even sizes,
     duplicates around the middle, masks, the skip pattern, infinities, signed zeros, NaN, empty."""
@@ -465,7 +453,7 @@ def test_device_median_numpy_semantics(cna):
         assert device_median(torch.as_tensor(v).cuda()) == np.median(v)
         w = np.round(v, 1 if n > 100 else 0)  # many duplicates, also across the middle
         assert device_median(torch.as_tensor(w).cuda()) == np.median(w)
-        k = rng.gamma(2.0, 1.0, n) * 10 ** rng.integers(-3, 3)  # clustered exponents, like kurtoses
+        k = rng.gamma(2.0, 1.0, n) * 10.0 ** rng.integers(-3, 3)  # clustered exponents, like kurtoses
         assert device_median(torch.as_tensor(k).cuda()) == np.median(k)
         mask = rng.random(n) > 0.4
         mask[0] = True
@@ -654,3 +642,40 @@ def test_end_to_end_vs_oracle_at_other_shapes(cna, N, S, k, nsteps):
             continue
         edge = np.abs(np.abs(np.nan_to_num(d_cpu.obs["coef"].to_numpy())) - thr) < 1e-5 * max(thr, 1e-3)
         assert ((a <= level) == (b <= level))[~edge].all()
+
+
+def test_config_B_vs_oracle(cna):
+    """BASELINE.json configs[1] at its exact shape (100 000 cells, 100 samples, k = 15, s = 3, 1000
+    permutations; bench.py --config B builds the same dataset): whole association() against the
+    oracle.  Exact: p, k, the kept cells; the FDR-passing sets agree except for cells within rounding of
+    the threshold; singular values and coefficients to 1e-5."""
+    import warnings
+    from cna_b200 import synth
+    from oracle import cna_oracle as orc
+    data, meta = synth.make_dataset(100_000, 100, 15, seed=0)
+    kw = dict(y=meta.case, sid_name="id", batches=meta.batch, covs=meta[["age"]], nsteps=3, Nnull=1000, seed=0)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        d_cpu = type(data)(data.obs.copy(), data.obsp["connectivities"])
+        want = orc.association(d_cpu, return_full=True, **kw)
+        d_gpu = type(data)(data.obs.copy(), data.obsp["connectivities"])
+        got = cna.tl.association(d_gpu, return_full=True, **kw)
+        d_res = type(data)(data.obs.copy(), data.obsp["connectivities"])
+        p_res = cna.tl.association(cna.tl.to_device(d_res), **kw)  # the path bench.py's `value` times
+    assert got.p == want.p == p_res
+    assert int(got.k) == int(want.k) and list(got.ks) == list(want.ks) and got.r == want.r
+    np.testing.assert_array_equal(got.kept, want.kept)
+    np.testing.assert_allclose(got.ncorrs.to_numpy(), want.ncorrs.to_numpy(), rtol=RTOL, atol=1e-6)
+    np.testing.assert_allclose(got.namresid_svs.to_numpy()[:10], want.namresid_svs.to_numpy()[:10], rtol=RTOL)
+    np.testing.assert_allclose(got.nullminps, want.nullminps, rtol=1e-4, atol=1e-12)
+    np.testing.assert_allclose(got.fdrs.threshold.to_numpy(), want.fdrs.threshold.to_numpy(), rtol=RTOL)
+    a, b = d_gpu.obs["coef_fdr"].to_numpy(), d_cpu.obs["coef_fdr"].to_numpy()
+    np.testing.assert_array_equal(d_res.obs["coef_fdr"].to_numpy(), a)
+    np.testing.assert_array_equal(d_res.obs["coef"].to_numpy(), d_gpu.obs["coef"].to_numpy())
+    for level, thr in ((0.05, want.fdr_5p_t), (0.1, want.fdr_10p_t)):
+        if thr is None:
+            assert (a <= level).sum() == 0
+            continue
+        edge = np.abs(np.abs(np.nan_to_num(d_cpu.obs["coef"].to_numpy())) - thr) < 1e-5 * max(thr, 1e-3)
+        assert ((a <= level) == (b <= level))[~edge].all()
+        assert (b <= level).sum() > 0

@@ -282,49 +282,6 @@ def test_obs_to_sample_matches_reference_semantics():
         pd.testing.assert_frame_equal(got, ref.obs_to_sample(d, ["case", "male", "batch"], "id"))
 
 
-def test_host_refine_order_is_a_blockwise_permutation_and_raises_neighbour_overlap():
-    """csrc/order_host.cpp: rows are only moved inside their block, the result does not depend on the
-    thread count or on how the caller labels the rows, and consecutive rows share more neighbours."""
-    from sklearn.neighbors import NearestNeighbors
-    import scipy.sparse as sp
-    from cna_b200 import _lib
-    rng = np.random.default_rng(5)
-    n, k, block = 6000, 12, 1024
-    pts = rng.normal(size=(n, 3))
-    nbr = NearestNeighbors(n_neighbors=k + 1).fit(pts).kneighbors(pts, return_distance=False)[:, 1:]
-    A = sp.csr_matrix((np.ones(n * k), (np.repeat(np.arange(n), k), nbr.ravel())), shape=(n, n))
-    A = ((A + A.T) > 0).astype(np.float64).tocsr()
-    A.sort_indices()
-    order = np.arange(n, dtype=np.int64)
-    inv = np.arange(n, dtype=np.int32)
-    out = _lib.host_refine_order(A.indptr, A.indices, order, inv, block, window=8, n_threads=1)
-    assert np.array_equal(np.sort(out), np.arange(n))
-    for b in range(0, n, block):
-        assert set(out[b:b + block]) == set(range(b, min(n, b + block)))
-    for threads in (0, 3):
-        assert np.array_equal(out, _lib.host_refine_order(A.indptr, A.indices, order, inv, block, 8, threads))
-
-    def overlap7(seq):  # share of a row's neighbours also gathered by the 7 rows before it
-        nb = [set(A.indices[A.indptr[r]:A.indptr[r + 1]]) for r in seq]
-        vals = [len(nb[i] & set().union(*nb[i - 7:i])) / max(len(nb[i]), 1) for i in range(7, n, 5)]
-        return float(np.mean(vals))
-
-    assert overlap7(out) > overlap7(order) + 0.15
-
-    # the caller's labelling does not matter: relabel the rows, pass the matching order / inv
-    relabel = rng.permutation(n)  # caller row of stored position i
-    back = np.argsort(relabel)
-    P = sp.csr_matrix((np.ones(n), (relabel, np.arange(n))), shape=(n, n))
-    B = (P @ A @ P.T).tocsr()
-    B.sort_indices()
-    out2 = _lib.host_refine_order(B.indptr, B.indices, relabel.astype(np.int64), back.astype(np.int32), block, 8, 2)
-    for b in range(0, n, block):
-        assert set(back[out2[b:b + block]]) == set(range(b, min(n, b + block)))
-    assert abs(overlap7(back[out2]) - overlap7(out)) < 0.05
-    with pytest.raises(_lib.CnaError):
-        _lib.host_refine_order(A.indptr, A.indices, order, inv, 0)
-
-
 def test_obs_column_adoption_semantics():
     """association() hands its per-cell result buffers to ``data.obs`` without a second copy: the column
     must hold the values, keep the buffer alive, survive the next call's overwrite of the same key, and
@@ -351,29 +308,33 @@ def test_obs_column_adoption_semantics():
         assert obs["coef"].iloc[0] == -1.0 and obs["coef"].iloc[1] == 8.0
 
 
-def test_device_graph_refine_order_bookkeeping(monkeypatch):
-    """DeviceGraph._refine_order (tensors on the CPU here): the refined order replaces the Cuthill-McKee
-    one, ``inv`` is its inverse, dtypes are what the CUDA entry points expect."""
+def test_tile_plan_is_consistent():
+    """TilePlan (tl/_graph.py) of the shared-memory-staged diffusion step: every edge's position points
+    at its own source row in its tile's list, lists are padded to multiples of 4 with valid rows, tiles
+    that would exceed the source capacity are halved, a row no tile can hold is refused."""
     import scipy.sparse as sp
+    from cna_b200 import _lib
     from cna_b200.tl import _graph
-    monkeypatch.setattr(_graph, "device", lambda: torch.device("cpu"))
-    rng = np.random.default_rng(2)
+    tile_rows, cap = _lib.diffuse_tile_limits()
     n = 3000
-    A = sp.random(n, n, density=8 / n, random_state=3, format="csr")
-    A = (A + A.T).tocsr()
-    A.sort_indices()
-    g = object.__new__(_graph.DeviceGraph)
-    g.n_total = n
-    start = rng.permutation(n)
-    g.order = torch.as_tensor(start, dtype=torch.int64)
-    g.inv = torch.empty(n, dtype=torch.int32)
-    g.inv[g.order] = torch.arange(n, dtype=torch.int32)
-    g._refine_order(A, 512)
-    assert g.order.dtype == torch.int64 and g.inv.dtype == torch.int32
-    order, inv = g.order.numpy(), g.inv.numpy()
-    assert sorted(order.tolist()) == list(range(n)) and (inv[order] == np.arange(n)).all()
-    for b in range(0, n, 512):
-        assert set(order[b:b + 512]) == set(start[b:b + 512])
-    assert _graph.local_order_block() == _graph.LOCAL_ORDER_BLOCK
-    monkeypatch.setenv("CNA_B200_LOCAL_ORDER", "0")
-    assert _graph.local_order_block() == 0
+    A = sp.random(n, n, density=0.006, format="lil", random_state=1)
+    A[7, :700] = 1.0
+    A[8, 300:1100] = 2.0
+    A = A.tocsr()
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a))  # noqa: E731
+    plan = _graph.TilePlan(t(A.indptr.astype(np.int32)), t(A.indices.astype(np.int32)), t(A.data.astype(np.float32)), n)
+    tr, tu, us, ep = plan.tile_row.numpy(), plan.tile_u.numpy(), plan.usrc.numpy(), plan.epair.numpy()
+    assert tr[0] == 0 and tr[-1] == n and (np.diff(tr) > 0).all() and np.diff(tr).max() <= tile_rows
+    assert (np.diff(tu) % 4 == 0).all() and np.diff(tu).max() <= cap and plan.n_tiles == len(tr) - 1
+    assert ((us >= 0) & (us < n)).all()
+    assert (ep[:, 1].view(np.float32) == A.data.astype(np.float32)).all()
+    for k in range(plan.n_tiles):
+        e0, e1 = A.indptr[tr[k]], A.indptr[tr[k + 1]]
+        pos = ep[e0:e1, 0] // 128
+        assert (ep[e0:e1, 0] % 128 == 0).all() and (pos < tu[k + 1] - tu[k]).all()
+        assert (us[tu[k] + pos] == A.indices[e0:e1]).all()
+    B = A.tolil()
+    B[9, :] = 1.0  # more distinct sources than any tile can stage
+    B = B.tocsr()
+    with pytest.raises(_lib.CnaError):
+        _graph.TilePlan(t(B.indptr.astype(np.int32)), t(B.indices.astype(np.int32)), t(B.data.astype(np.float32)), n)
