@@ -26,7 +26,9 @@
 #include <chrono>
 #include <cstdint>
 #include <cstdio>
+#include <condition_variable>
 #include <cstdlib>
+#include <functional>
 #include <limits>
 #include <mutex>
 #include <thread>
@@ -103,21 +105,72 @@ static inline int default_threads() {
     return t > 64 ? 64 : t;
 }
 
-template <typename F>
-static void parallel_for(int64_t n, int n_threads, F fn) {
-    if (n_threads <= 1 || n < 2) {
-        fn(0, n);
-        return;
+// A small persistent pool: the workers are created once per process and parked on a condition variable
+// (spawning 15 threads costs more than a tenth of the whole draw).  run(n, fn) executes fn(worker) for
+// worker = 0 .. n-1, worker 0 on the calling thread, and returns when all are done.
+class Pool {
+  public:
+    static Pool &get() {
+        // never destroyed: the parked workers outlive main(), and destroying a condition variable with
+        // waiters blocks process exit
+        static Pool *p = new Pool();
+        return *p;
     }
-    std::vector<std::thread> pool;
-    int64_t per = (n + n_threads - 1) / n_threads;
-    for (int t = 0; t < n_threads; ++t) {
-        int64_t a = t * per, b = std::min(n, a + per);
-        if (a >= b) break;
-        pool.emplace_back([=] { fn(a, b); });
+    template <typename F>
+    void run(int n, F fn) {
+        if (n <= 1) {
+            fn(0);
+            return;
+        }
+        std::lock_guard<std::mutex> serial(run_mutex_);
+        grow(n - 1);
+        std::function<void(int)> job = fn;
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            job_ = &job;
+            active_ = n - 1;
+            remaining_ = n - 1;
+            ++generation_;
+        }
+        cv_.notify_all();
+        fn(0);
+        std::unique_lock<std::mutex> lk(m_);
+        done_.wait(lk, [&] { return remaining_ == 0; });
+        job_ = nullptr;
     }
-    for (auto &th : pool) th.join();
-}
+
+  private:
+    void grow(int n) {
+        while (int(threads_.size()) < n) {
+            const int id = int(threads_.size());
+            threads_.emplace_back([this, id] {
+                uint64_t seen = 0;
+                for (;;) {
+                    std::function<void(int)> *job;
+                    {
+                        std::unique_lock<std::mutex> lk(m_);
+                        cv_.wait(lk, [&] { return generation_ != seen; });
+                        seen = generation_;
+                        if (id >= active_) continue;
+                        job = job_;
+                    }
+                    (*job)(id + 1);
+                    std::lock_guard<std::mutex> lk(m_);
+                    if (--remaining_ == 0) done_.notify_one();
+                }
+            });
+            threads_.back().detach();
+        }
+    }
+    std::mutex m_, run_mutex_;
+    std::condition_variable cv_, done_;
+    std::vector<std::thread> threads_;
+    std::function<void(int)> *job_ = nullptr;
+    uint64_t generation_ = 0;
+    int active_ = 0, remaining_ = 0;
+};
+
+static inline void cpu_relax() { _mm_pause(); }
 
 // argsort of n <= 256 keys by counting: rank_i = #{j : key_j < key_i}.  Branch-free and SIMD-friendly,
 // ~3x faster than std::sort on the 50-element columns of a 4-batch design.  `key` is padded with
@@ -172,6 +225,199 @@ static void small_argsort(double *key, int n, int32_t *order, std::vector<std::p
 }  // namespace hostperm
 }  // namespace cna
 
+namespace cna {
+namespace hostperm {
+
+// Work that follows the deviates: task t may start once the first `need[t]` deviates are in place
+// (the argsort of one batch block needs exactly the deviates of that block).
+struct PostTasks {
+    int64_t count = 0;
+    std::function<int64_t(int64_t)> need;         // deviates task t depends on
+    std::function<void(int64_t, int)> run;        // (task, worker)
+};
+
+// The draw as ONE pass over the stream, pipelined behind the state recurrence:
+//   * the calling thread generates the MT19937 blocks (the only inherently serial part) and publishes
+//     how many are ready;
+//   * the workers claim chunks of attempts in stream order.  For its chunk a worker tempers, converts and
+//     tests every attempt, keeps the accepted ones (r2, x1, x2) in a thread-local buffer, waits for the
+//     chunk before it to publish its cumulative number of accepted pairs (a short wait: chunks are claimed
+//     in order and publish before their expensive part), publishes its own, and then runs the log / sqrt
+//     transform into the output positions that number fixes;
+//   * when the chunks are exhausted the workers go on to the post tasks (per-column argsorts), each of
+//     which waits only for the deviates it reads.
+// Every attempt consumes exactly four words, accepted or not, so attempt j sits at words [4j, 4j + 4)
+// of the stream that starts at key[pos]; accepted attempt number p fills out[first + 2p] = f*x2 and
+// out[first + 2p + 1] = f*x1 (legacy_gauss returns the cached second deviate on the next call).
+static int randn_pipeline(uint32_t *key, int *pos, int *has_gauss, double *gauss, int64_t count, double *out,
+                          int n_threads, const PostTasks *post) {
+    const double t_begin = now_ms();
+    int64_t first = 0;
+    if (count > 0 && *has_gauss) {  // legacy_gauss: the cached deviate goes out first
+        out[first++] = *gauss;
+        *has_gauss = 0;
+        *gauss = 0.0;
+    }
+    const int64_t n_pairs = count > first ? (count - first + 1) / 2 : 0;
+    const bool odd = ((count - first) & 1) != 0;
+    const int pos0 = *pos;
+    static std::mutex ws_mutex;
+    static std::vector<uint32_t> raw;  // [the caller's key][block 0][block 1]...: untempered, each a candidate final state
+    std::lock_guard<std::mutex> ws_lock(ws_mutex);
+
+    constexpr int64_t kChunk = 2048;  // attempts per chunk (8192 words, ~13 blocks)
+    struct Accepted {
+        double r2, x1, x2;
+        int32_t j;  // attempt index inside the chunk
+    };
+    std::atomic<int64_t> blocks_ready{0}, next_chunk{0}, next_task{0}, deviates_done{0}, j_stop{-1};
+    std::atomic<int> failed{0};
+    double last_second = 0.0;
+    int64_t n_blocks = 0, chunks_total = 0;
+    std::vector<std::atomic<int64_t>> cum;   // cum[c] = accepted pairs before chunk c (-1 = not yet known)
+    std::vector<std::atomic<int8_t>> chunk_done;
+    double t_serial = 0.0;
+
+    auto words_available = [&](int64_t blocks) { return int64_t(kN - pos0) + blocks * kN; };
+
+    for (int round = 0; n_pairs > 0; ++round) {
+        // expected attempts = pairs / (pi/4); 0.4 % + 256 of slack covers > 6 sigma, else one more round
+        const int64_t want_att = int64_t(double(n_pairs) * (1.2732395447351628 * (1.004 + 0.01 * round))) + 256;
+        const int64_t need_blocks = std::max<int64_t>(0, (4 * want_att - (kN - pos0) + kN - 1) / kN);
+        if (raw.size() < size_t(need_blocks + 1) * kN) {
+            std::vector<uint32_t> bigger(size_t(need_blocks + 1) * kN);
+            std::copy(raw.begin(), raw.begin() + std::min(raw.size(), size_t(n_blocks + 1) * kN), bigger.begin());
+            raw.swap(bigger);
+        }
+        if (n_blocks == 0) std::copy(key, key + kN, raw.begin());
+        const int64_t n_att = words_available(need_blocks) / 4;
+        const int64_t n_chunks = (n_att + kChunk - 1) / kChunk;
+        // a later round re-runs everything over the longer stream (it practically never happens)
+        cum = std::vector<std::atomic<int64_t>>(size_t(n_chunks) + 1);
+        chunk_done = std::vector<std::atomic<int8_t>>(size_t(n_chunks));
+        for (auto &c : cum) c.store(-1, std::memory_order_relaxed);
+        for (auto &c : chunk_done) c.store(0, std::memory_order_relaxed);
+        cum[0].store(0, std::memory_order_relaxed);
+        next_chunk.store(0);
+        blocks_ready.store(n_blocks);
+        deviates_done.store(first);
+        chunks_total = n_chunks;
+        const uint32_t *stream = raw.data() + pos0;
+
+        auto recurrence = [&]() {
+            const double t0 = now_ms();
+            for (; n_blocks < need_blocks; ++n_blocks) {
+                mt_next_block(raw.data() + size_t(n_blocks) * kN, raw.data() + size_t(n_blocks + 1) * kN);
+                if ((n_blocks & 7) == 7) blocks_ready.store(n_blocks + 1, std::memory_order_release);
+            }
+            blocks_ready.store(n_blocks, std::memory_order_release);
+            t_serial += now_ms() - t0;
+        };
+        auto chunk_loop = [&]() {
+            std::vector<Accepted> acc(static_cast<size_t>(kChunk));
+            for (;;) {
+                const int64_t c = next_chunk.fetch_add(1, std::memory_order_relaxed);
+                if (c >= n_chunks) break;
+                const int64_t j0 = c * kChunk, j1 = std::min(n_att, j0 + kChunk);
+                while (words_available(blocks_ready.load(std::memory_order_acquire)) < 4 * j1) cpu_relax();
+                int64_t na = 0;
+                for (int64_t j = j0; j < j1; ++j) {
+                    double x1, x2;
+                    const double r2 = polar_attempt(stream + 4 * j, x1, x2);
+                    if (r2 >= 1.0 || r2 == 0.0) continue;
+                    acc[size_t(na++)] = {r2, x1, x2, int32_t(j - j0)};
+                }
+                int64_t p0;
+                while ((p0 = cum[size_t(c)].load(std::memory_order_acquire)) < 0) cpu_relax();
+                cum[size_t(c) + 1].store(p0 + na, std::memory_order_release);
+                for (int64_t i = 0; i < na && p0 + i < n_pairs; ++i) {
+                    const Accepted &e = acc[size_t(i)];
+                    const int64_t p = p0 + i;
+                    const double f = sqrt(-2.0 * log(e.r2) / e.r2);
+                    out[first + 2 * p] = f * e.x2;
+                    if (p == n_pairs - 1) {
+                        j_stop.store(j0 + e.j, std::memory_order_relaxed);
+                        if (odd) last_second = f * e.x1;
+                        else out[first + 2 * p + 1] = f * e.x1;
+                    } else {
+                        out[first + 2 * p + 1] = f * e.x1;
+                    }
+                }
+                chunk_done[size_t(c)].store(1, std::memory_order_release);
+            }
+        };
+        // The post tasks run inside the same parallel region, after the chunks.  Task t waits until every
+        // chunk that holds one of its deviates is done; if the round turns out to be short of attempts
+        // (practically never) the tasks are abandoned and the next round starts over.
+        auto task_loop = [&](int w) {
+            if (!post || post->count == 0) return;
+            int64_t mark = 0;  // chunks [0, mark) are known to be done
+            for (;;) {
+                const int64_t t = next_task.fetch_add(1, std::memory_order_relaxed);
+                if (t >= post->count) break;
+                const int64_t need = std::min(post->need(t), count);  // deviates [0, need) must be in place
+                for (;;) {
+                    if (failed.load(std::memory_order_relaxed)) return;
+                    while (mark < n_chunks && chunk_done[size_t(mark)].load(std::memory_order_acquire)) ++mark;
+                    if (mark >= n_chunks) {
+                        if (cum[size_t(n_chunks)].load(std::memory_order_acquire) < n_pairs) {
+                            failed.store(1);
+                            return;
+                        }
+                        break;
+                    }
+                    // chunks [0, mark) done: pairs [0, cum[mark]) are in place
+                    const int64_t pairs_done = std::min(cum[size_t(mark)].load(std::memory_order_acquire), n_pairs);
+                    if (first + 2 * pairs_done >= need) break;
+                    cpu_relax();
+                }
+                post->run(t, w);
+            }
+        };
+        next_task.store(0);
+        failed.store(0);
+        Pool::get().run(n_threads, [&](int w) {
+            if (w == 0) recurrence();
+            chunk_loop();
+            task_loop(w);
+        });
+        if (cum[size_t(n_chunks)].load() >= n_pairs) break;
+    }
+    if (n_pairs > 0) {
+        if (odd) {
+            *gauss = last_second;
+            *has_gauss = 1;
+        }
+        // state after the last consumed word (numpy regenerates lazily: pos may be left at 624)
+        const int64_t consumed = 4 * (j_stop.load() + 1);
+        if (consumed <= kN - pos0) {
+            *pos = pos0 + int(consumed);  // still inside the caller's block: key unchanged
+        } else {
+            const int64_t c = consumed - (kN - pos0);
+            const int64_t blk = (c - 1) / kN;  // new block that holds the last consumed word
+            std::copy(raw.begin() + size_t(blk + 1) * kN, raw.begin() + size_t(blk + 2) * kN, key);
+            *pos = int(c - blk * kN);
+        }
+    } else if (post && post->count > 0) {  // every deviate came out of the cache: nothing to wait for
+        next_task.store(0);
+        Pool::get().run(n_threads, [&](int w) {
+            for (;;) {
+                const int64_t t = next_task.fetch_add(1, std::memory_order_relaxed);
+                if (t >= post->count) break;
+                post->run(t, w);
+            }
+        });
+    }
+    (void)chunks_total;
+    if (timing_on())
+        fprintf(stderr, "[cna timing] host draw: %lld deviates%s, state recurrence %.2f ms (overlapped), total %.2f ms (%d threads)\n",
+                (long long)count, post ? " + argsorts" : "", t_serial, now_ms() - t_begin, n_threads);
+    return CNA_OK;
+}
+
+}  // namespace hostperm
+}  // namespace cna
+
 using namespace cna;
 using namespace cna::hostperm;
 
@@ -183,115 +429,14 @@ int cna_host_randn(uint32_t *key, int *pos, int *has_gauss, double *gauss, int64
                 "cna_host_randn: bad arguments");
     if (count == 0) return CNA_OK;
     if (n_threads <= 0) n_threads = default_threads();
-    const double t_begin = now_ms();
-    int64_t first = 0;
-    if (*has_gauss) {  // legacy_gauss: the cached deviate goes out first
-        out[first++] = *gauss;
-        *has_gauss = 0;
-        *gauss = 0.0;
-    }
-    // Pair p (the p-th ACCEPTED attempt) fills out[first + 2p] = f*x2 and out[first + 2p + 1] = f*x1;
-    // if the count is odd the very last f*x1 stays cached in the state.
-    const int64_t n_pairs = (count - first + 1) / 2;
-    if (n_pairs == 0) return CNA_OK;
-    const bool odd = ((count - first) & 1) != 0;
-
-    // The only serial part is the state recurrence.  Every attempt consumes exactly four words,
-    // accepted or not, so attempt j sits at words [4j, 4j+4) of the stream that starts at
-    // key[pos]: all blocks that can be needed are generated first (kept untempered: each is a
-    // candidate final state), then tempering, conversion, the acceptance test, the compaction and the
-    // log/sqrt transform run on all threads.
-    static std::mutex ws_mutex;
-    static std::vector<uint32_t> raw;      // [block -1 = the caller's key][block 0][block 1]...
-    static std::vector<int64_t> chunk_acc;
-    std::lock_guard<std::mutex> ws_lock(ws_mutex);
-    const int pos0 = *pos;
-    int64_t n_blocks = 0;                  // new blocks generated so far
-    int64_t j_stop = -1;                   // index of the attempt that completes pair n_pairs-1
-    int64_t n_att = 0, n_chunks = 0, per_chunk = 0;
-    double t_serial = 0.0;
-    for (int round = 0;; ++round) {
-        // expected attempts = pairs / (pi/4); 0.4 % + 256 of slack covers > 6 sigma, else loop again
-        const int64_t want_att = int64_t(double(n_pairs) * (1.2732395447351628 * (1.004 + 0.01 * round))) + 256;
-        const int64_t want_words = 4 * want_att;
-        const int64_t need_blocks = std::max<int64_t>(0, (want_words - (kN - pos0) + kN - 1) / kN);
-        const double t0 = now_ms();
-        if (raw.size() < size_t(need_blocks + 1) * kN) raw.resize(size_t(need_blocks + 1) * kN);
-        if (n_blocks == 0) std::copy(key, key + kN, raw.begin());
-        for (; n_blocks < need_blocks; ++n_blocks)
-            mt_next_block(raw.data() + size_t(n_blocks) * kN, raw.data() + size_t(n_blocks + 1) * kN);
-        t_serial += now_ms() - t0;
-        const uint32_t *stream = raw.data() + pos0;   // word i of the stream
-        n_att = ((kN - pos0) + n_blocks * kN) / 4;
-        per_chunk = std::max<int64_t>(4096, (n_att + 8 * n_threads - 1) / (8 * n_threads));
-        n_chunks = (n_att + per_chunk - 1) / per_chunk;
-        chunk_acc.assign(size_t(n_chunks) + 1, 0);
-        parallel_for(n_chunks, n_threads, [&](int64_t ca, int64_t cb) {  // pass 1: acceptances per chunk
-            for (int64_t c = ca; c < cb; ++c) {
-                const int64_t j0 = c * per_chunk, j1 = std::min(n_att, j0 + per_chunk);
-                int64_t acc = 0;
-                for (int64_t j = j0; j < j1; ++j) {
-                    double x1, x2;
-                    double r2 = polar_attempt(stream + 4 * j, x1, x2);
-                    acc += !(r2 >= 1.0 || r2 == 0.0);
-                }
-                chunk_acc[size_t(c) + 1] = acc;
-            }
-        });
-        for (int64_t c = 0; c < n_chunks; ++c) chunk_acc[size_t(c) + 1] += chunk_acc[size_t(c)];
-        if (chunk_acc[size_t(n_chunks)] >= n_pairs) break;
-    }
-    const uint32_t *stream = raw.data() + pos0;
-    double last_second = 0.0;
-    std::vector<int64_t> stops(size_t(n_chunks), -1);
-    parallel_for(n_chunks, n_threads, [&](int64_t ca, int64_t cb) {  // pass 2: compaction + transform
-        for (int64_t c = ca; c < cb; ++c) {
-            int64_t p = chunk_acc[size_t(c)];
-            if (p >= n_pairs) break;
-            const int64_t j0 = c * per_chunk, j1 = std::min(n_att, j0 + per_chunk);
-            for (int64_t j = j0; j < j1 && p < n_pairs; ++j) {
-                double x1, x2;
-                double r2 = polar_attempt(stream + 4 * j, x1, x2);
-                if (r2 >= 1.0 || r2 == 0.0) continue;
-                double f = sqrt(-2.0 * log(r2) / r2);
-                out[first + 2 * p] = f * x2;
-                if (p == n_pairs - 1) {
-                    stops[size_t(c)] = j;
-                    if (odd) last_second = f * x1;
-                    else out[first + 2 * p + 1] = f * x1;
-                } else {
-                    out[first + 2 * p + 1] = f * x1;
-                }
-                ++p;
-            }
-        }
-    });
-    for (int64_t c = 0; c < n_chunks; ++c)
-        if (stops[size_t(c)] >= 0) j_stop = stops[size_t(c)];
-    if (odd) {
-        *gauss = last_second;
-        *has_gauss = 1;
-    }
-    // state after the last consumed word (numpy regenerates lazily: pos may be left at 624)
-    const int64_t consumed = 4 * (j_stop + 1);
-    if (consumed <= kN - pos0) {
-        *pos = pos0 + int(consumed);  // still inside the caller's block: key unchanged
-    } else {
-        const int64_t c = consumed - (kN - pos0);
-        const int64_t blk = (c - 1) / kN;  // new block that holds the last consumed word
-        std::copy(raw.begin() + size_t(blk + 1) * kN, raw.begin() + size_t(blk + 2) * kN, key);
-        *pos = int(c - blk * kN);
-    }
-    if (timing_on())
-        fprintf(stderr, "[cna timing] host_randn: %lld deviates, state recurrence %.2f ms (serial), the rest %.2f ms (%d threads)\n",
-                (long long)count, t_serial, now_ms() - t_begin - t_serial, n_threads);
-    return CNA_OK;
+    return randn_pipeline(key, pos, has_gauss, gauss, count, out, n_threads, nullptr);
 }
 
 int cna_host_perm_blocks(uint32_t *key, int *pos, int *has_gauss, double *gauss, int n_blocks,
                          const int32_t *block_off, const int32_t *src_pos, int64_t num, int32_t *out,
                          int64_t ld_out, int n_threads) {
-    CNA_REQUIRE(n_blocks >= 0 && block_off && out && num >= 0, "cna_host_perm_blocks: bad arguments");
+    CNA_REQUIRE(n_blocks >= 0 && block_off && out && num >= 0 && key && pos && has_gauss && gauss,
+                "cna_host_perm_blocks: bad arguments");
     if (n_threads <= 0) n_threads = default_threads();
     const int64_t total_rows = block_off[n_blocks];
     CNA_REQUIRE(ld_out >= total_rows, "cna_host_perm_blocks: ld_out too small");
@@ -302,47 +447,48 @@ int cna_host_perm_blocks(uint32_t *key, int *pos, int *has_gauss, double *gauss,
     static std::vector<double> z;
     std::lock_guard<std::mutex> z_lock(z_mutex);
     if (z.size() < nz) z.resize(nz);
-    int rc = cna_host_randn(key, pos, has_gauss, gauss, total_rows * num, z.data(), n_threads);
-    if (rc != CNA_OK) return rc;
     // argsort(axis=0) per column of each block; ties have probability zero, so any comparison sort
     // gives numpy's answer.  Result rows are permutations k, columns are positions.
     // Columns are walked in tiles of 16 so that every cache line of the row-major block is read once
-    // (a single column is a stride-`num` walk: one cache and TLB miss per element).
-    const double t_sort = now_ms();
+    // (a single column is a stride-`num` walk: one cache and TLB miss per element).  Task = (block,
+    // tile), blocks first: the argsorts of a batch start as soon as its deviates are in place.
     constexpr int kTile = 16;
     const int64_t n_tiles = (num + kTile - 1) / kTile;
-    parallel_for(n_tiles, n_threads, [&](int64_t ta, int64_t tb) {
-        std::vector<std::pair<double, int32_t>> scratch;
+    struct Scratch {
+        std::vector<std::pair<double, int32_t>> pairs;
         std::vector<double> keys;
         std::vector<int32_t> order;
-        for (int64_t tile = ta; tile < tb; ++tile) {
-            const int64_t k0 = tile * kTile;
-            const int w = int(std::min<int64_t>(kTile, num - k0));
-            for (int blk = 0; blk < n_blocks; ++blk) {
-                const int32_t r0 = block_off[blk], rows = block_off[blk + 1] - r0;
-                const size_t stride = size_t(rows) + 4;  // room for the +inf padding of the rank sort
-                keys.resize(stride * kTile);
-                order.resize(size_t(rows));
-                const double *zb = z.data() + size_t(r0) * size_t(num) + k0;  // block is [rows x num]
-                for (int32_t t = 0; t < rows; ++t) {
-                    const double *zr = zb + size_t(t) * size_t(num);
-                    for (int c = 0; c < w; ++c) keys[size_t(c) * stride + t] = zr[c];
-                }
-                for (int c = 0; c < w; ++c) {
-                    small_argsort(keys.data() + size_t(c) * stride, rows, order.data(), scratch);
-                    int32_t *o = out + (k0 + c) * ld_out;
-                    if (src_pos) {  // _stats.py:14-16: bix[bi[t], k] = bi[argsort[t]]
-                        for (int32_t t = 0; t < rows; ++t) o[src_pos[r0 + t]] = src_pos[r0 + order[size_t(t)]];
-                    } else {        // raw order of this block
-                        for (int32_t t = 0; t < rows; ++t) o[r0 + t] = order[size_t(t)];
-                    }
-                }
+    };
+    std::vector<Scratch> scratch(size_t(n_threads) + 1);
+    PostTasks post;
+    post.count = int64_t(n_blocks) * n_tiles;
+    post.need = [&](int64_t t) { return int64_t(block_off[t / n_tiles + 1]) * num; };
+    post.run = [&](int64_t t, int w) {
+        Scratch &sc = scratch[size_t(w)];
+        const int blk = int(t / n_tiles);
+        const int64_t k0 = (t % n_tiles) * kTile;
+        const int wdt = int(std::min<int64_t>(kTile, num - k0));
+        const int32_t r0 = block_off[blk], rows = block_off[blk + 1] - r0;
+        if (rows == 0) return;
+        const size_t stride = size_t(rows) + 4;  // room for the +inf padding of the rank sort
+        sc.keys.resize(stride * kTile);
+        sc.order.resize(size_t(rows));
+        const double *zb = z.data() + size_t(r0) * size_t(num) + k0;  // block is [rows x num]
+        for (int32_t tt = 0; tt < rows; ++tt) {
+            const double *zr = zb + size_t(tt) * size_t(num);
+            for (int c = 0; c < wdt; ++c) sc.keys[size_t(c) * stride + tt] = zr[c];
+        }
+        for (int c = 0; c < wdt; ++c) {
+            small_argsort(sc.keys.data() + size_t(c) * stride, rows, sc.order.data(), sc.pairs);
+            int32_t *o = out + (k0 + c) * ld_out;
+            if (src_pos) {  // _stats.py:14-16: bix[bi[t], k] = bi[argsort[t]]
+                for (int32_t tt = 0; tt < rows; ++tt) o[src_pos[r0 + tt]] = src_pos[r0 + sc.order[size_t(tt)]];
+            } else {        // raw order of this block
+                for (int32_t tt = 0; tt < rows; ++tt) o[r0 + tt] = sc.order[size_t(tt)];
             }
         }
-    });
-    if (timing_on())
-        fprintf(stderr, "[cna timing] host_perm_blocks: argsort + scatter %.2f ms (%d threads)\n", now_ms() - t_sort, n_threads);
-    return CNA_OK;
+    };
+    return randn_pipeline(key, pos, has_gauss, gauss, total_rows * num, z.data(), n_threads, &post);
 }
 
 // Asynchronous form: the draw runs on a library-owned thread (no Python thread, hence no waiting for
