@@ -88,6 +88,8 @@ _SIGNATURES = {
     "cna_fdr_thresholds": [_VP, _INT, _VP, _VP, _VP, _VP],
     "cna_absmax": [_VP, _VP, _I64, _VP, _VP],
     "cna_cell_fdr": [_VP, _VP, _I64, _VP, _VP, _INT, _VP, _VP, _VP],
+    "cna_cell_fdr_dev": [_VP, _VP, _I64, _VP, _VP, _INT, _VP, _VP, _VP, _VP],
+    "cna_fdr_table": [_VP, _VP, _VP, _INT, _INT, _VP, _VP, _VP],
     "cna_knn_bruteforce": [_VP, _I64, _INT, _INT, _VP, _VP, _VP],
     "cna_bfs_expand": [_VP, _VP, _VP, _INT, _INT, _INT, _VP, _VP, _VP, _VP, _VP],
     "cna_bfs_keys": [_VP, _INT, _VP, _VP, _VP],
@@ -410,6 +412,22 @@ def cell_fdr(ncorr, row_valid, thresholds, prefix_min_fdr, coef, fdr):
                                _ptr(thresholds, torch.float64, "thresholds"),
                                _ptr(prefix_min_fdr, torch.float64, "prefix_min_fdr"), thresholds.numel(),
                                _ptr(coef, torch.float64, "coef"), _ptr(fdr, torch.float64, "fdr"), _stream())
+
+
+def cell_fdr_dev(ncorr, row_valid, thresholds, prefix_min_fdr, count, coef, fdr):
+    _call("cna_cell_fdr_dev", _ptr(ncorr, torch.float64, "ncorr"),
+          _ptr(row_valid, torch.uint8, "row_valid", allow_none=True), ncorr.numel(),
+          _ptr(thresholds, torch.float64, "thresholds"), _ptr(prefix_min_fdr, torch.float64, "prefix_min_fdr"),
+          thresholds.numel(), _ptr(count, torch.int32, "count"), _ptr(coef, torch.float64, "coef"),
+          _ptr(fdr, torch.float64, "fdr"), _stream())
+
+
+def fdr_table(null_hist, rank_hist, count, n_null, fdr, prefix_min_fdr):
+    """fdr / running-min-fdr per threshold from the device-resident histograms (int64 null histogram
+    summed over the nulls, int32 observed rank histogram)."""
+    _call("cna_fdr_table", _ptr(null_hist, torch.int64, "null_hist"), _ptr(rank_hist, torch.int32, "rank_hist"),
+          _ptr(count, torch.int32, "count"), fdr.numel(), int(n_null), _ptr(fdr, torch.float64, "fdr"),
+          _ptr(prefix_min_fdr, torch.float64, "prefix_min_fdr"), _stream())
 
 
 def bfs_expand(indptr, indices, frontier, pos_base, next_level, level, first_parent, nxt, next_count):

@@ -267,9 +267,11 @@ __global__ void obs_hist_kernel(const double *__restrict__ ncorr, const uint8_t 
 
 __global__ void cell_fdr_kernel(const double *__restrict__ ncorr, const uint8_t *__restrict__ valid,
                                 int64_t n, const double *__restrict__ thr,
-                                const double *__restrict__ pmin, int n_thr, double *coef, double *fdr) {
+                                const double *__restrict__ pmin, int n_thr_cap, const int32_t *__restrict__ n_thr_dev,
+                                double *coef, double *fdr) {
     extern __shared__ double sm[];
-    double *t = sm, *p = sm + n_thr;
+    double *t = sm, *p = sm + n_thr_cap;
+    const int n_thr = n_thr_dev ? min(__ldg(n_thr_dev), n_thr_cap) : n_thr_cap;
     for (int i = threadIdx.x; i < n_thr; i += blockDim.x) {
         t[i] = thr[i];
         p[i] = pmin[i];
@@ -379,18 +381,24 @@ int cna_obs_hist(const double *ncorr, const uint8_t *row_valid, int64_t n_rows, 
                             stream);
 }
 
-int cna_cell_fdr(const double *ncorr, const uint8_t *row_valid, int64_t n_rows,
-                 const double *thresholds, const double *prefix_min_fdr, int n_thr, double *coef,
-                 double *fdr, void *stream) {
+int cna_cell_fdr_dev(const double *ncorr, const uint8_t *row_valid, int64_t n_rows,
+                     const double *thresholds, const double *prefix_min_fdr, int n_thr, const int32_t *n_thr_dev,
+                     double *coef, double *fdr, void *stream) {
     CNA_REQUIRE(n_thr > 0 && n_thr <= 2048, "cna_cell_fdr: 1..2048 thresholds supported");
     if (n_rows <= 0) return CNA_OK;
     int64_t blocks = (n_rows + 255) / 256;
     unsigned grid = unsigned(blocks < 1184 ? blocks : 1184);
     size_t smem = 2 * sizeof(double) * n_thr;
     cell_fdr_kernel<<<grid, 256, smem, as_stream(stream)>>>(ncorr, row_valid, n_rows, thresholds,
-                                                          prefix_min_fdr, n_thr, coef, fdr);
+                                                          prefix_min_fdr, n_thr, n_thr_dev, coef, fdr);
     CNA_LAUNCHED("cell_fdr_kernel");
     return CNA_OK;
+}
+
+int cna_cell_fdr(const double *ncorr, const uint8_t *row_valid, int64_t n_rows,
+                 const double *thresholds, const double *prefix_min_fdr, int n_thr, double *coef,
+                 double *fdr, void *stream) {
+    return cna_cell_fdr_dev(ncorr, row_valid, n_rows, thresholds, prefix_min_fdr, n_thr, nullptr, coef, fdr, stream);
 }
 
 }  // extern "C"

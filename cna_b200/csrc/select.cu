@@ -192,6 +192,39 @@ __global__ void fdr_thresholds_kernel(const double *__restrict__ maxabs, int cap
     if (threadIdx.x == 0) n_thresholds[0] = T;
 }
 
+// _stats.py:57-59, :79-80 and _association.py:234 on the device, from the histograms the null GEMM and
+// cna_obs_hist left there: tails = reverse cumulative sums, fdr_i = (sum_k tails[k, i]) / ranks_i / n_null
+// (the same two float64 divisions numpy performs), pmin = running minimum of fdr that skips NaN
+// (np.fmin.accumulate; Series.min() in the per-cell lookup).  One block; T <= cap <= 1024.
+__global__ void __launch_bounds__(1024)
+fdr_table_kernel(const unsigned long long *__restrict__ null_hist, const unsigned int *__restrict__ rank_hist,
+                 const int *__restrict__ count, int cap, double n_null, double *__restrict__ fdr,
+                 double *__restrict__ pmin) {
+    __shared__ unsigned long long tn[1024], tr[1024];
+    __shared__ double f[1024];
+    const int T = min(count[0], cap), i = threadIdx.x;
+    tn[i] = i < T ? null_hist[i] : 0ull;
+    tr[i] = i < T ? (unsigned long long)rank_hist[i] : 0ull;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {  // suffix sums (Hillis-Steele)
+        const unsigned long long a = i + o < 1024 ? tn[i + o] : 0ull, b = i + o < 1024 ? tr[i + o] : 0ull;
+        __syncthreads();
+        tn[i] += a;
+        tr[i] += b;
+        __syncthreads();
+    }
+    f[i] = i < T ? __ddiv_rn(__ddiv_rn(double((long long)tn[i]), double((long long)tr[i])), n_null) : nan("");
+    __syncthreads();
+    if (i < cap) fdr[i] = i < T ? f[i] : 0.0;
+    if (i == 0) {  // running fmin, 300 steps
+        double m = nan("");
+        for (int k = 0; k < cap; ++k) {
+            if (k < T) m = fmin(m, f[k]);  // fmin ignores a NaN operand
+            pmin[k] = k < T ? m : 0.0;
+        }
+    }
+}
+
 }  // namespace cna
 
 using namespace cna;
@@ -222,6 +255,17 @@ int cna_median_f64(const double *v, const uint8_t *valid, int64_t n, double *out
     select_finish_kernel<<<grid, 512, 0, s>>>(v, valid, n, st, out);
     CNA_LAUNCHED("select_pass_kernel");
     count_launch(kSelPasses);
+    return CNA_OK;
+}
+
+int cna_fdr_table(const uint64_t *null_hist, const uint32_t *rank_hist, const int32_t *n_thresholds, int cap,
+                  int n_null, double *fdr, double *prefix_min_fdr, void *stream) {
+    CNA_REQUIRE(null_hist && rank_hist && n_thresholds && fdr && prefix_min_fdr && cap >= 1 && cap <= 1024 && n_null > 0,
+                "cna_fdr_table: bad arguments");
+    fdr_table_kernel<<<1, 1024, 0, as_stream(stream)>>>(reinterpret_cast<const unsigned long long *>(null_hist),
+                                                        rank_hist, n_thresholds, cap, double(n_null), fdr,
+                                                        prefix_min_fdr);
+    CNA_LAUNCHED("fdr_table_kernel");
     return CNA_OK;
 }
 

@@ -85,15 +85,15 @@ class _Readback:
 
     def __init__(self, slot, tensors):
         self.views = []
-        total = sum(t.numel() * t.element_size() for t in tensors)
-        buf = _pinned(slot, (max(total, 1),), torch.uint8)
+        sizes = [(t.numel() * t.element_size() + 15) // 16 * 16 for t in tensors]  # every view 16-byte aligned
+        buf = _pinned(slot, (max(sum(sizes), 16),), torch.uint8)
         off = 0
-        for t in tensors:
+        for t, size in zip(tensors, sizes):
             nbytes = t.numel() * t.element_size()
             host = buf[off:off + nbytes].view(t.dtype).reshape(t.shape)
             host.copy_(t, non_blocking=True)
             self.views.append(host)
-            off += nbytes
+            off += size
         self.event = torch.cuda.Event()
         self.event.record()
 
@@ -155,7 +155,13 @@ def _f_sf(f, dfn, dfd):
     evaluated in row chunks on a small thread pool (same function, same bits)."""
     global _POOL
     if f.shape[0] < 2048:
-        return st.f.sf(f, dfn, dfd)
+        # st.f.sf(f, dfn, dfd) without scipy.stats' argument machinery: same special function, same bits
+        from scipy.special import fdtrc
+        dfn, dfd = np.broadcast_arrays(np.asarray(dfn, dtype=np.float64), np.asarray(dfd, dtype=np.float64))
+        with np.errstate(all="ignore"):
+            p = fdtrc(dfn, dfd, f)
+            p = np.where(f <= 0, np.where(np.isnan(f), np.nan, 1.0), p)
+            return np.where((dfd > 0) & (dfn > 0), p, np.nan)
     if _POOL is None:
         from concurrent.futures import ThreadPoolExecutor
         import os
@@ -216,18 +222,15 @@ class _Columns:
         if self.gather:
             self.coef = _to_host_owned(self._full(coef), self.side)
 
-    def start_fdr(self, fdrs):
-        """``fdrs`` = the threshold/FDR table, or None (local_test=False: the reference writes the
-        coefficients and then crashes looking up FDRs at :235; here the FDR column is simply not
-        written)."""
-        if fdrs is None:
-            return
+    def start_fdr(self, thr_d, pmin_d, count_d):
+        """Per-cell FDR (:234-237) from the device-resident threshold table and running minimum of the FDR
+        (``cna_fdr_table``): queued right behind the null GEMM, no host round trip.  (With
+        local_test=False the reference writes the coefficients and then crashes looking up FDRs at :235;
+        here the FDR column is simply not written.)"""
         res = self.res
-        thr = fdrs.threshold.to_numpy()
-        pmin = np.fmin.accumulate(fdrs.fdr.to_numpy())  # Series.min() skips NaN (:234)
         coef_d = torch.empty_like(res.ncorr)
         fdr_d = torch.empty_like(res.ncorr)
-        _lib.cell_fdr(res.ncorr, res.valid, _to_dev(thr), _to_dev(pmin), coef_d, fdr_d)
+        _lib.cell_fdr_dev(res.ncorr, res.valid, thr_d, pmin_d, count_d, coef_d, fdr_d)
         if self.gather:
             self.fdr = _to_host_owned(self._full(fdr_d), self.side)
 
@@ -317,7 +320,13 @@ def _association(res, perms, Nnull=1000, local_test=True, show_progress=False, c
             if comm is not None:  # counts over all shards
                 comm.all_reduce(hist)
                 comm.all_reduce(obs)
-            back = _Readback("phase_b", [hist, obs, thr_d, count_d])
+            # the FDR table (_stats.py:79-80) and the per-cell FDR column follow on the device
+            fdr_d = torch.empty(THRESHOLD_CAP, dtype=torch.float64, device=dev)
+            pmin_d = torch.empty(THRESHOLD_CAP, dtype=torch.float64, device=dev)
+            _lib.fdr_table(hist, obs[0], count_d, Kl, fdr_d, pmin_d)
+            back = _Readback("phase_b", [hist, obs, thr_d, count_d, fdr_d])
+            if columns is not None:
+                columns.start_fdr(thr_d, pmin_d, count_d)
         mark("null kernels launched")
         return perm_d, C_d, W_d, back
 
@@ -379,14 +388,16 @@ def _association(res, perms, Nnull=1000, local_test=True, show_progress=False, c
 
     def fdr_table(back):
         """:105-118 from the histograms (and the thresholds the device derived from max |ncorr|)."""
-        hist_h, obs_h, thr_h, count_h = back.get()
+        hist_h, obs_h, thr_h, count_h, fdr_h = back.get()
         T = int(count_h[0])
         if T >= THRESHOLD_CAP:
             raise _lib.CnaError(f"more than {THRESHOLD_CAP - 1} FDR thresholds")
         thresholds = thr_h[:T].copy()
-        fdr_vals = _stats.fdr_from_counts(hist_h[:T], obs_h[0, :T], n_null=Kl)  # _stats.py:64-83
+        fdr_vals = fdr_h[:T].copy()  # _stats.py:64-83 (cna_fdr_table; == _stats.fdr_from_counts(hist, obs[0], Kl))
         num_detected = _stats.tails_from_hist(obs_h[1, :T].astype(np.int64))  # :105-108
-        fdrs = pd.DataFrame({"threshold": thresholds, "fdr": fdr_vals, "num_detected": num_detected})
+        # the DataFrame is part of the full result surface only
+        fdrs = (pd.DataFrame({"threshold": thresholds, "fdr": fdr_vals, "num_detected": num_detected})
+                if want_null_table else True)
         t5 = t10 = None
         if not np.nanmin(fdr_vals) > 0.05:  # :111-114 (Series.min skips NaN; first row with fdr <= 0.05)
             t5 = thresholds[np.nonzero(fdr_vals <= 0.05)[0][0]]
@@ -417,14 +428,12 @@ def _association(res, perms, Nnull=1000, local_test=True, show_progress=False, c
         b = phase_b(tabs)
     U, svs, res.G = _nam.svd_of_gram(Gh.copy(), res.svd_top)
     res.U, res.svs = U, svs
-    o = observed_test(U)
     if b is None:
         b = phase_b(tabs)
     perm_d, C_d, W_d, back_b = b
-    sse_d = launch_pc_regressions(U, perm_d, C_d, W_d)
+    sse_d = launch_pc_regressions(U, perm_d, C_d, W_d)  # the device works on these while the host ...
+    o = observed_test(U)                                 # ... tests the observed phenotype
     fdrs, fdr_5p_t, fdr_10p_t = fdr_table(back_b) if local_test else (None, None, None)
-    if columns is not None:
-        columns.start_fdr(fdrs)
     pfinal, nullminps, nullr2s = global_pvalue(o.p, sse_d)
 
     return Namespace(p=pfinal, nullminps=nullminps, k=o.k, ncorrs=None, fdrs=fdrs,
@@ -454,6 +463,21 @@ def association(data, y, sid_name, batches=None, covs=None, donorids=None, ks=No
     codes = _graph.sample_codes(data, sid_name)
     if len(codes[0]) > 1024:
         raise ValueError(f"cna_b200 supports at most 1024 samples (data.obs['{sid_name}'] has {len(codes[0])})")
+    # The diffusion needs nothing but the graph and the sample codes.  With the graph resident it is queued
+    # first, and the input checks, the design algebra and the permutation draw run on the host while the
+    # device works (an exception below simply abandons the queued kernels: nothing has been written to
+    # data.obs).  A host graph is uploaded and reordered first (~10 ms): there the draw is started before.
+    user_batches = batches
+
+    def launch_nam():
+        print("computing NAM", file=out)
+        st = _nam._nam_device(data, sid_name, nsteps=nsteps, show_progress=show_progress, codes=codes,
+                              qc_batches=user_batches)
+        mark("diffusion launched")
+        return st
+
+    resident = isinstance(getattr(data, "graph", None), _graph.DeviceGraph)
+    stn = launch_nam() if resident else None
     batches, filter_samples = check_inputs(data, y, sid_name, batches, covs, donorids,
                                            allow_low_sample_size, present=codes[0])
     mark("check_inputs done")
@@ -484,16 +508,14 @@ def association(data, y, sid_name, batches=None, covs=None, donorids=None, ks=No
     comm = getattr(data, "comm", None)
     if comm is not None and return_full:
         raise NotImplementedError("return_full=True is not supported on a cell-axis shard")
-    # the permutation draws only need the sample-level inputs: start them before any GPU work
+    # the permutation draw only needs the sample-level inputs: it runs on the host's threads from here on
     perms = (_stats.PermutationDraw(y_std, perm_batches, donor_f, Nnull)
              if comm is None or comm.rank == 0 else None)
     mark("permutation draw started")
     try:
-        # ---- the diffusion, QC and residualisation: queued back to back, no host round trip ----
-        print("computing NAM", file=out)
-        stn = _nam._nam_device(data, sid_name, nsteps=nsteps, show_progress=show_progress, codes=codes,
-                               qc_batches=batches)
-        mark("diffusion launched")
+        if stn is None:
+            stn = launch_nam()
+        # ---- QC and residualisation: queued behind the diffusion, no host round trip ----
         _nam._qc_device(stn, batches, show_progress=show_progress)
         colmap = stn.labels.get_indexer(sids)  # NAM.reindex(y.index)[filter_samples], :178-181
         res = _nam.resid_nam_device(stn, colmap, covs_f, batches_f, y_std, ridges=ridges,

@@ -159,15 +159,22 @@ class DeviceGraph:
         self.n_total = A.shape[0]
         if len(A.indices) >= 2 ** 31:
             raise ValueError("graphs with >= 2^31 stored edges are not supported")
-        indptr = _to_dev(A.indptr, torch.int32)
-        indices = _to_dev(A.indices, torch.int32)
         data = A.data if A.data.dtype in (np.float32, np.float64) else A.data.astype(np.float64)
-        # the edge weights (2/3 of the bytes) are not needed by the ordering: they travel on a side
-        # stream while the breadth-first sweeps run (truly asynchronous when the host buffer is pinned)
-        main, side = torch.cuda.current_stream(), _upload_stream(indptr.device)
-        with torch.cuda.stream(side):
-            data = _to_dev(data)
-        data.record_stream(main)
+        if shard is not None and shard[0].world > 1:
+            # Each rank ingests only its own block of the caller's rows (1 / world of the host -> device
+            # traffic); the blocks are then all-gathered over NVLink so that every rank can compute the
+            # same cell order and cut its shard of the reordered graph.
+            indptr, indices, data = self._gather_blocks(A, data, shard[0])
+            main = side = torch.cuda.current_stream() if indptr.is_cuda else None
+        else:
+            indptr = _to_dev(A.indptr, torch.int32)
+            indices = _to_dev(A.indices, torch.int32)
+            # the edge weights (2/3 of the bytes) are not needed by the ordering: they travel on a side
+            # stream while the breadth-first sweeps run (truly asynchronous when the host buffer is pinned)
+            main, side = torch.cuda.current_stream(), _upload_stream(indptr.device)
+            with torch.cuda.stream(side):
+                data = _to_dev(data)
+            data.record_stream(main)
         self.order = self.inv = None
         mark("graph: indices queued for upload")
         if (want_reorder(self.n_total) if reorder is None else reorder) and self.n_total > 1:
@@ -179,10 +186,12 @@ class DeviceGraph:
                 new_indptr = torch.zeros(self.n_total + 1, dtype=torch.int32, device=indptr.device)
                 new_indptr[1:] = torch.cumsum(deg, 0)
                 new_indices, new_data = torch.empty_like(indices), torch.empty_like(data)
-                main.wait_stream(side)
+                if main is not side:
+                    main.wait_stream(side)
                 _lib.permute_csr(indptr, indices, data, self.order, self.inv, new_indptr, new_indices, new_data)
                 indptr, indices, data = new_indptr, new_indices, new_data
-        main.wait_stream(side)
+        if main is not side:
+            main.wait_stream(side)
         self.halo_ids = None
         if shard is None:
             self.comm, self.row0, self.rows_per = None, 0, self.n_total
@@ -198,6 +207,25 @@ class DeviceGraph:
         self.nnz = int(indices.numel())
         self.indptr, self.indices, self.data = indptr, indices, data
         self._scaled = {}
+
+    @staticmethod
+    def _gather_blocks(A, data, comm):
+        """Upload rows [o0, o1) of the host CSR (this rank's block of the caller's row order) and
+        all-gather the blocks: returns the full (indptr, indices, data) on this rank's device."""
+        n_total = A.shape[0]
+        rows_per = (n_total + comm.world - 1) // comm.world
+        o0 = min(comm.rank * rows_per, n_total)
+        o1 = min(o0 + rows_per, n_total)
+        e0, e1 = int(A.indptr[o0]), int(A.indptr[o1])
+        deg = np.zeros(rows_per, dtype=np.int32)
+        deg[: o1 - o0] = np.diff(A.indptr[o0:o1 + 1])
+        deg_all = comm.all_gather_rows(_to_dev(deg))[:n_total]
+        indptr = torch.zeros(n_total + 1, dtype=torch.int32, device=deg_all.device)
+        indptr[1:] = torch.cumsum(deg_all, 0)
+        indices = torch.cat(comm.all_gather_padded(_to_dev(A.indices[e0:e1], torch.int32)))
+        data = torch.cat(comm.all_gather_padded(_to_dev(data[e0:e1])))
+        mark("graph: blocks gathered")
+        return indptr, indices, data
 
     def _plan_halo(self, indices, row1):
         """kNN halo of this shard, gathered once: the sorted remote row ids its edges reference

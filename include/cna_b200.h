@@ -306,6 +306,19 @@ int cna_cell_fdr(const double *ncorr, const uint8_t *row_valid, int64_t n_rows,
                  const double *thresholds, const double *prefix_min_fdr, int n_thr, double *coef,
                  double *fdr, void *stream);
 
+/* cna_cell_fdr with the number of thresholds read from device memory (n_thr = capacity of the tables). */
+int cna_cell_fdr_dev(const double *ncorr, const uint8_t *row_valid, int64_t n_rows,
+                     const double *thresholds, const double *prefix_min_fdr, int n_thr, const int32_t *n_thr_dev,
+                     double *coef, double *fdr, void *stream);
+
+/* The FDR table on the device: fdr[i] = (reverse cumulative sum of null_hist)[i] / (reverse cumulative sum
+ * of rank_hist)[i] / n_null for i < n_thresholds[0] (the float64 operations of _stats.py:79-80 applied to
+ * the histogram summed over the nulls), prefix_min_fdr = its running minimum skipping NaN (what the
+ * per-cell lookup of _association.py:234 needs).  With it the whole chain null GEMM -> FDR table -> per-cell
+ * FDR column runs without the host.  cap <= 1024.  replaces: _stats.py:57-59, :79-80, _association.py:234. */
+int cna_fdr_table(const uint64_t *null_hist, const uint32_t *rank_hist, const int32_t *n_thresholds, int cap,
+                  int n_null, double *fdr, double *prefix_min_fdr, void *stream);
+
 /* ------------------------------------------------------------------------------------------
  * locality-restoring cell order (no reference counterpart: a property of the HBM layout)
  * ------------------------------------------------------------------------------------------ */

@@ -38,6 +38,24 @@ def _entry(rank, world, port, fn, args):
         dist.destroy_process_group()
 
 
+def _spawn_nccl(fn, world, *args):
+    port = _free_port()
+    mp.spawn(_entry_nccl, args=(world, port, fn, args), nprocs=world, join=True)
+
+
+def _entry_nccl(rank, world, port, fn, args):
+    """One rank per GPU over NCCL: the configuration bench.py --gpus N runs (all_to_all_single halo
+    exchange, NCCL all-reduces / all-gathers)."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        fn(rank, world, *args)
+    finally:
+        dist.destroy_process_group()
+
+
 def test_shard_bounds_and_slicing():
     from cna_b200.sharded import shard_bounds, slice_csr
     for n, w in [(10, 2), (11, 2), (7, 8), (1_000_000, 8), (5, 1)]:
@@ -97,10 +115,10 @@ def test_sharded_median_world2():
     _spawn(_median_checks, 2)
 
 
-def _sharded_vs_single(rank, world, spec, reorder=False):
+def _sharded_vs_single(rank, world, spec, reorder=False, own_gpu=False):
     import cna_b200 as cna
     from cna_b200.sharded import shard_to_device
-    torch.cuda.set_device(0)
+    torch.cuda.set_device(rank if own_gpu else 0)
     if reorder:  # shards of the Cuthill-McKee ordered graph: small halo, results in the caller's order
         os.environ["CNA_B200_REORDER"] = "1"
     g = cases.load_demo_graph()
@@ -161,3 +179,52 @@ def _sharded_auto_stop(rank, world):
 @pytest.mark.gpu
 def test_sharded_nam_auto_stop_and_qc():
     _spawn(_sharded_auto_stop, 2)
+
+
+def _nccl_halo_and_large(rank, world):
+    """NCCL path at a size where the graph is stored reordered and shards have a real halo: the
+    all_to_all_single exchange itself (against rows fetched directly), then whole association() against the
+    single-GPU result: exact p and kept cells, identical coefficients."""
+    import cna_b200 as cna
+    from cna_b200 import synth
+    from cna_b200.sharded import shard_to_device
+    data, meta = synth.make_dataset(200_000, 60, 15, seed=1)
+    kw = dict(y=meta.case, sid_name="id", batches=meta.batch, covs=meta[["age"]], nsteps=3, Nnull=500, seed=2)
+    sh = shard_to_device(data)
+    g = sh.graph
+    assert g.comm.backend == "nccl" and g.order is not None and g.halo_ids.numel() > 0
+    # the exchange: every rank's extended state must end with the owners' rows
+    ld = 64
+    full = torch.arange(g.n_total * ld, dtype=torch.float32, device="cuda").reshape(g.n_total, ld)
+    ext = torch.zeros((g.rows_per + g.halo_ids.numel(), ld), dtype=torch.float32, device="cuda")
+    ext[: g.n] = full[g.row0: g.row0 + g.n]
+    g.exchange_halo(ext)
+    assert torch.equal(ext[g.rows_per:], full[g.halo_ids])
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        p_sh = cna.tl.association(sh, **kw)
+        c_sh, f_sh = data.obs["coef"].to_numpy().copy(), data.obs["coef_fdr"].to_numpy().copy()
+        p_e2e = cna.tl.association(shard_to_device(data, resident=False), **kw)  # one-shot shards (bench e2e)
+        c_e2e = data.obs["coef"].to_numpy().copy()
+        p_1 = cna.tl.association(cna.tl.to_device(data), **kw)
+        c_1, f_1 = data.obs["coef"].to_numpy(), data.obs["coef_fdr"].to_numpy()
+    assert p_sh == p_1 == p_e2e
+    np.testing.assert_array_equal(np.isnan(c_sh), np.isnan(c_1))
+    np.testing.assert_allclose(c_sh, c_1, rtol=1e-12, atol=1e-15)
+    np.testing.assert_allclose(c_e2e, c_1, rtol=1e-6, atol=1e-9)  # another cell order: column sums differ in the last bits
+    np.testing.assert_allclose(f_sh, f_1, rtol=1e-9)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (NCCL, one rank per GPU)")
+def test_nccl_two_gpus_halo_exchange_and_association():
+    _spawn_nccl(_nccl_halo_and_large, 2)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (NCCL, one rank per GPU)")
+def test_nccl_two_gpus_golden_case():
+    spec = dict(cases.DEMO_CASES["case_male_batch"])
+    spec.pop("np_seed", None)
+    spec.setdefault("seed", 0)
+    _spawn_nccl(_sharded_vs_single, 2, spec, True, True)
