@@ -25,9 +25,7 @@ than the 126 MB L2, so no explicit L2 flush is needed between iterations.
 import argparse
 import json
 import os
-import subprocess
 import sys
-import tempfile
 import time
 import warnings
 
@@ -42,6 +40,8 @@ CONFIGS = {
     "A": (10_000, 50, 15, 3, 1000),
     "B": (100_000, 100, 15, 3, 1000),
     "C": (1_000_000, 200, 30, 3, 10_000),
+    "E": (10_000_000, 500, 30, 4, 10_000),
+    "T": (200_000, 60, 15, 4, 500),  # smoke test of the row-block (config E) path at a size that takes seconds
 }
 METRIC = "cells/sec through nam()+association(), 1M cells/200 samples/10k perms"
 # CPU sample: same samples / k / steps, cells and permutations scaled down by the same factor
@@ -59,6 +59,8 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="C", choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-full", action="store_true",
+                    help="also run the CPU oracle once on the SAME full-size AnnData (same-config baseline + result check; minutes)")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
 
@@ -109,6 +111,27 @@ def time_cpu_arm(data, kw, steps, warmup):
     return times
 
 
+def oracle_full(data, kw):
+    """The CPU oracle (reference cost structure) once on the very AnnData the GPU arm ran on: a same-config
+    baseline and the result fingerprint the GPU `check` block is compared with."""
+    from oracle import cna_oracle as orc
+    d = type(data)(data.obs[["id"]].copy(), data.obsp["connectivities"])
+    t0 = time.perf_counter()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        res = orc.association(d, faithful=True, return_full=True, **kw)
+    dt = time.perf_counter() - t0
+    coef, fdr = d.obs["coef"].to_numpy(), d.obs["coef_fdr"].to_numpy()
+    check = {
+        "p": float(res.p), "k": int(res.k), "n_kept": int(res.kept.sum()),
+        "n_fdr05": int((fdr <= 0.05).sum()), "n_fdr10": int((fdr <= 0.10).sum()),
+        "fdr_5p_t": None if res.fdr_5p_t is None else float(res.fdr_5p_t),
+        "fdr_10p_t": None if res.fdr_10p_t is None else float(res.fdr_10p_t),
+        "svs": [float(v) for v in res.namresid_svs.to_numpy()[:4]], "sum_abs_coef": float(np.nansum(np.abs(coef))),
+    }
+    return dt, check
+
+
 def run_reference(args):
     """--impl reference: the CPU implementation of the path on this box's host cores."""
     rank = int(os.environ.get("RANK", "0"))
@@ -127,6 +150,9 @@ def run_reference(args):
         "cpu_baseline": {"value": value, "unit": "cells/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        # the CPU arm runs a 1 / sample_scale sample of the workload (cells and permutations): its cells/s is
+        # an upper bound for the full-size CPU run (profiles/r02_oracle_C.json has that one: same-config)
+        "sample_scale": CONFIGS[args.config][0] // n_cells, "same_config": CONFIGS[args.config][0] == n_cells,
     }
     print(json.dumps(line))
 
@@ -135,56 +161,59 @@ def run_reference(args):
 # GPU arm
 # ---------------------------------------------------------------------------------------------
 class ClockSampler:
-    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed region, in-process through NVML (a thread that
+    wakes every 20 ms; starting an `nvidia-smi -lms` child instead costs ~100 ms of driver-wide locking
+    at start-up, which showed up as +4 ms per step on a 2-GPU run whose timed region is only 0.1 s)."""
+    BAD = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, index):
         self.index = index
-        self.proc = None
-        self.path = None
+        self.sm, self.reasons, self.max_mhz = [], set(), None
+        self.stop = None
+        self.thread = None
 
     def __enter__(self):
         try:
-            fd, self.path = tempfile.mkstemp(suffix=".csv")
-            os.close(fd)
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100",
-                 "-i", str(self.index)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+            import threading
+
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES when it lists indices
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = self.index
+            if vis and all(v.strip().isdigit() for v in vis.split(",")):
+                phys = int(vis.split(",")[self.index])
+            h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            self.stop = threading.Event()
+
+            def loop():
+                while not self.stop.is_set():
+                    try:
+                        self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                        mask = int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                        for name, bit in self.BAD.items():
+                            if mask & bit:
+                                self.reasons.add(name)
+                    except Exception:
+                        pass
+                    self.stop.wait(0.02)
+
+            self.thread = threading.Thread(target=loop, daemon=True)
+            self.thread.start()
         except Exception:
-            self.proc = None
+            self.thread = None
         return self
 
     def __exit__(self, *exc):
-        if self.proc is not None:
-            self.proc.terminate()
-            try:
-                self.proc.wait(timeout=5)
-            except Exception:
-                self.proc.kill()
+        if self.thread is not None:
+            self.stop.set()
+            self.thread.join(timeout=2)
 
     def summary(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        if not self.path or not os.path.exists(self.path):
-            return out
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in open(self.path):
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, val in zip(names, f[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        os.unlink(self.path)
-        if sm:
-            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons),
-                       samples=len(sm))
+        out = {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+        if self.sm:
+            out.update(sm_mhz=float(np.median(self.sm)), samples=len(self.sm), source="nvml")
         return out
 
 
@@ -300,10 +329,22 @@ def run_ours(args):
 
     N, S, k, s_steps, K = CONFIGS[args.config]
     t0 = time.perf_counter()
-    data, meta = synth.make_dataset(N, S, k, seed=0)
+    comm = None
+    if world > 1:
+        from cna_b200.sharded import Comm
+        comm = Comm()
+    # the kNN search of the generator is split over the ranks; at config E every rank also keeps only its
+    # own block of rows of the graph on the host (10M x 10M, 4e8 stored edges)
+    blocks = args.config in ("E", "T") and world > 1
+    data, meta = synth.make_dataset(N, S, k, seed=0, dim=6 if N >= 1_000_000 else None, comm=comm, row_block=blocks)
     gen_s = time.perf_counter() - t0
     A = data.obsp["connectivities"]
     nnz = int(A.nnz)
+    host_graph_bytes = A.data.nbytes + A.indices.nbytes + A.indptr.nbytes
+    if blocks:
+        t = torch.tensor([nnz, host_graph_bytes], dtype=torch.int64, device="cuda")
+        dist.all_reduce(t)
+        nnz, host_graph_bytes = int(t[0].item()), int(t[1].item())
     kw = dict(y=meta.case, sid_name="id", batches=meta.batch, covs=meta[["age"]], nsteps=s_steps, Nnull=K, seed=0)
     n = S
     Kl = min(1000, K)
@@ -362,7 +403,7 @@ def run_ours(args):
             undo()
             check_e2e = check_block(data.obs)
             check["e2e_agrees"] = checks_agree(check_e2e, check)
-            h2d = (A.data.nbytes + A.indices.nbytes + A.indptr.nbytes) + 4 * N * world
+            h2d = host_graph_bytes + 4 * N * world  # summed over the ranks (each uploads its block of rows)
             d2h = 2 * 8 * N + 8 * n * n + 8 * K * 5
             e2e = {"value": N * args.steps / (ms_e2e * 1e-3), "unit": "cells/s", "ms_per_step": ms_e2e / args.steps,
                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)}
@@ -370,7 +411,7 @@ def run_ours(args):
     if rank != 0:
         dist.destroy_process_group()
         return
-    if world > 1:  # the same call on one GPU (outside every timed region): the shards must reproduce it
+    if world > 1 and not blocks:  # the same call on one GPU (outside every timed region): the shards must reproduce it
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
             cna.tl.association(cna.tl.to_device(data), **kw)
@@ -402,11 +443,17 @@ def run_ours(args):
         "clocks": clk.summary(), "e2e": e2e, "gpu_launches": launches / args.steps, "check": check,
         "roofline": primary, "rooflines": roofs,
     }
-    if not args.no_cpu_baseline and world == 1:
+    if not args.no_cpu_baseline and world == 1 and args.config not in ("E", "T"):
         cdata, ckw, sample = make_cpu_sample(args.config)
         t = time_cpu_arm(cdata, ckw, 1, 0)
         line["cpu_baseline"] = {"value": len(cdata.obs) / t[0], "unit": "cells/s", "cores": cpu_threads(),
                                 "kind": "port", "sample": sample, "seconds": t[0]}
+    if args.cpu_full and world == 1:
+        secs, ocheck = oracle_full(data, kw)
+        line["cpu_baseline_full"] = {"value": N / secs, "unit": "cells/s", "seconds": secs, "cores": cpu_threads(),
+                                     "kind": "port", "same_config": True,
+                                     "sample": workload_name(args.config) + ", the same AnnData as the GPU arm",
+                                     "check": ocheck, "gpu_check_agrees": checks_agree(check, ocheck)}
     os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()

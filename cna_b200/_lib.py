@@ -91,6 +91,7 @@ _SIGNATURES = {
     "cna_cell_fdr_dev": [_VP, _VP, _I64, _VP, _VP, _INT, _VP, _VP, _VP, _VP],
     "cna_fdr_table": [_VP, _VP, _VP, _INT, _INT, _VP, _VP, _VP],
     "cna_knn_bruteforce": [_VP, _I64, _INT, _INT, _VP, _VP, _VP],
+    "cna_knn_bruteforce_range": [_VP, _I64, _INT, _INT, _I64, _I64, _VP, _VP, _VP],
     "cna_bfs_expand": [_VP, _VP, _VP, _INT, _INT, _INT, _VP, _VP, _VP, _VP, _VP],
     "cna_bfs_keys": [_VP, _INT, _VP, _VP, _VP],
     "cna_bfs_place": [_VP, _INT, _VP, _VP, _VP],
@@ -619,18 +620,19 @@ class HostPermJob:
             pass
 
 
-def knn_bruteforce(points, k):
-    """points: [n, dim] float32 CUDA tensor.  Returns (idx int64 [n, k], dist2 float32 [n, k])."""
+def knn_bruteforce(points, k, queries=None):
+    """points: [n, dim] float32 CUDA tensor.  Returns (idx int64 [nq, k], dist2 float32 [nq, k]) for the
+    queries ``queries`` = (q0, q1) (default: all points)."""
     n, dim = points.shape
+    q0, q1 = (0, n) if queries is None else queries
     pad = next(d for d in (4, 8, 16, 32) if d >= dim) if dim <= 32 else None
     if pad is None:
         raise CnaError("knn_bruteforce: at most 32 dimensions")
     if pad != dim:
         points = torch.nn.functional.pad(points, (0, pad - dim))
     points = points.contiguous()
-    idx = torch.empty((n, k), dtype=torch.int32, device=points.device)
-    d2 = torch.empty((n, k), dtype=torch.float32, device=points.device)
-    _call("cna_knn_bruteforce", _ptr(points, torch.float32, "points"), n, pad, int(k),
-                                     _ptr(idx, torch.int32, "idx"), _ptr(d2, torch.float32, "dist2"),
-                                     _stream())
+    idx = torch.empty((q1 - q0, k), dtype=torch.int32, device=points.device)
+    d2 = torch.empty((q1 - q0, k), dtype=torch.float32, device=points.device)
+    _call("cna_knn_bruteforce_range", _ptr(points, torch.float32, "points"), n, pad, int(k), int(q0), int(q1 - q0),
+          _ptr(idx, torch.int32, "idx"), _ptr(d2, torch.float32, "dist2"), _stream())
     return idx.long(), d2

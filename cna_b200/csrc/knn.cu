@@ -10,13 +10,14 @@ constexpr int kKnnMaxK = 64;
 
 template <int DIM>
 __global__ void __launch_bounds__(128)
-knn_kernel(const float *__restrict__ pts, int64_t n, int k, int32_t *__restrict__ idx,
+knn_kernel(const float *__restrict__ pts, int64_t n, int k, int64_t q0, int64_t nq, int32_t *__restrict__ idx,
            float *__restrict__ dist2) {
     constexpr int kKnnTile = kKnnTileFloats / DIM;
     __shared__ float tile[kKnnTile * DIM];
-    int64_t qi = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int64_t ql = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;  // query index inside [q0, q0 + nq)
+    const int64_t qi = q0 + ql;
     float q[DIM];
-    bool live = qi < n;
+    bool live = ql < nq;
 #pragma unroll
     for (int d = 0; d < DIM; ++d) q[d] = live ? pts[qi * DIM + d] : 0.f;
     float bd[kKnnMaxK];
@@ -54,8 +55,8 @@ knn_kernel(const float *__restrict__ pts, int64_t n, int k, int32_t *__restrict_
     }
     if (live)
         for (int t = 0; t < k; ++t) {
-            idx[qi * k + t] = bi[t];
-            dist2[qi * k + t] = bd[t];
+            idx[ql * k + t] = bi[t];
+            dist2[ql * k + t] = bd[t];
         }
 }
 
@@ -63,18 +64,25 @@ knn_kernel(const float *__restrict__ pts, int64_t n, int k, int32_t *__restrict_
 
 using namespace cna;
 
-extern "C" int cna_knn_bruteforce(const float *points, int64_t n, int dim, int k, int32_t *idx,
-                                  float *dist2, void *stream) {
+extern "C" int cna_knn_bruteforce_range(const float *points, int64_t n, int dim, int k, int64_t q0, int64_t nq,
+                                        int32_t *idx, float *dist2, void *stream) {
     CNA_REQUIRE(n > 0 && k > 0 && k <= kKnnMaxK && k < n, "cna_knn_bruteforce: need 0 < k <= 64, k < n");
-    unsigned grid = unsigned((n + 127) / 128);
+    CNA_REQUIRE(q0 >= 0 && nq >= 0 && q0 + nq <= n, "cna_knn_bruteforce: bad query range");
+    if (nq == 0) return CNA_OK;
+    unsigned grid = unsigned((nq + 127) / 128);
     cudaStream_t st = as_stream(stream);
     switch (dim) {
-        case 4: knn_kernel<4><<<grid, 128, 0, st>>>(points, n, k, idx, dist2); break;
-        case 8: knn_kernel<8><<<grid, 128, 0, st>>>(points, n, k, idx, dist2); break;
-        case 16: knn_kernel<16><<<grid, 128, 0, st>>>(points, n, k, idx, dist2); break;
-        case 32: knn_kernel<32><<<grid, 128, 0, st>>>(points, n, k, idx, dist2); break;
+        case 4: knn_kernel<4><<<grid, 128, 0, st>>>(points, n, k, q0, nq, idx, dist2); break;
+        case 8: knn_kernel<8><<<grid, 128, 0, st>>>(points, n, k, q0, nq, idx, dist2); break;
+        case 16: knn_kernel<16><<<grid, 128, 0, st>>>(points, n, k, q0, nq, idx, dist2); break;
+        case 32: knn_kernel<32><<<grid, 128, 0, st>>>(points, n, k, q0, nq, idx, dist2); break;
         default: return set_error(CNA_ERR_INVALID, "cna_knn_bruteforce: dim must be 4, 8, 16 or 32 (pad with zeros), got %d", dim);
     }
     CNA_LAUNCHED("knn_kernel");
     return CNA_OK;
+}
+
+extern "C" int cna_knn_bruteforce(const float *points, int64_t n, int dim, int k, int32_t *idx,
+                                  float *dist2, void *stream) {
+    return cna_knn_bruteforce_range(points, n, dim, k, 0, n, idx, dist2, stream);
 }

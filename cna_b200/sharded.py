@@ -107,7 +107,7 @@ class ShardedData:
         self._host = data
         self.comm = comm or Comm()
         A = get_connectivity(data)
-        n_total = A.shape[0]
+        n_total = A.shape[1]  # the host object may hold only this rank's block of rows (rows x N)
         r0, r1, rows_per = shard_bounds(n_total, self.comm.world, self.comm.rank)
         self.graph = DeviceGraph(A, shard=(self.comm, r0, r1, rows_per), resident=resident)
         self.obsp = getattr(data, "obsp", None)

@@ -43,18 +43,33 @@ def _knn_cpu(points, k):
     return idx[:, 1:].astype(np.int64), dist[:, 1:].astype(np.float64)
 
 
-def _knn_gpu(points, k):
+def _knn_gpu(points, k, comm=None):
+    """Exact kNN on the GPU; with a ``comm`` (cna_b200.sharded.Comm) every rank searches its own block
+    of queries and the blocks are all-gathered (brute force is O(N^2): 10M points take ~6 min on one
+    B200, ~45 s split over eight)."""
     from . import _lib
     pts = torch.as_tensor(points, dtype=torch.float32, device="cuda").contiguous()
-    idx, d2 = _lib.knn_bruteforce(pts, k - 1)
+    if comm is None or comm.world == 1:
+        idx, d2 = _lib.knn_bruteforce(pts, k - 1)
+        return idx, d2.double().sqrt_()
+    n = pts.shape[0]
+    per = (n + comm.world - 1) // comm.world
+    q0, q1 = min(comm.rank * per, n), min((comm.rank + 1) * per, n)
+    idx, d2 = _lib.knn_bruteforce(pts, k - 1, queries=(q0, q1))
+    pad_i = torch.zeros((per, k - 1), dtype=torch.int32, device=pts.device)
+    pad_d = torch.zeros((per, k - 1), dtype=torch.float32, device=pts.device)
+    pad_i[: q1 - q0], pad_d[: q1 - q0] = idx.to(torch.int32), d2
+    idx = comm.all_gather_rows(pad_i)[:n].long()
+    d2 = comm.all_gather_rows(pad_d)[:n]
     return idx, d2.double().sqrt_()
 
 
-def fuzzy_simplicial_set(idx, dist, n_iter=64):
+def fuzzy_simplicial_set(idx, dist, n_iter=64, rows=None):
     """UMAP's smooth-kNN-distance weights, symmetrised by probabilistic t-conorm.
 
     idx/dist: [N, k-1] neighbour indices / distances (self excluded), torch tensors (any device) or
-    numpy arrays.  Returns scipy CSR float64 with sorted indices."""
+    numpy arrays.  Returns scipy CSR float64 with sorted indices; with ``rows`` = (r0, r1) only that
+    block of rows, as an (r1 - r0) x N matrix (what one rank of a sharded run ingests)."""
     idx = torch.as_tensor(idx)
     dist = torch.as_tensor(dist, dtype=torch.float64, device=idx.device)
     idx = idx.long()
@@ -82,19 +97,26 @@ def fuzzy_simplicial_set(idx, dist, n_iter=64):
     s1 = torch.zeros(len(ukey), dtype=torch.float64, device=idx.device).index_add_(0, inv, val)
     s2 = torch.zeros(len(ukey), dtype=torch.float64, device=idx.device).index_add_(0, inv, val * val)
     w = s1 - (s1 * s1 - s2) / 2  # p + q - p.q for mutual pairs, p otherwise
-    rows = (ukey // N).cpu().numpy()
+    r0, r1 = (0, N) if rows is None else rows
+    if rows is not None:  # keys are sorted by row: the block is one slice
+        e0, e1 = torch.searchsorted(ukey, torch.tensor([r0 * N, r1 * N], device=ukey.device)).tolist()
+        ukey, w = ukey[e0:e1], w[e0:e1]
+    row = (ukey // N - r0).cpu().numpy()
     cols = (ukey % N).cpu().numpy().astype(np.int32)
-    indptr = np.zeros(N + 1, dtype=np.int64)
-    np.cumsum(np.bincount(rows, minlength=N), out=indptr[1:])
-    return sp.csr_matrix((w.cpu().numpy(), cols, indptr.astype(np.int32)), shape=(N, N))
+    indptr = np.zeros(r1 - r0 + 1, dtype=np.int64)
+    np.cumsum(np.bincount(row, minlength=r1 - r0), out=indptr[1:])
+    return sp.csr_matrix((w.cpu().numpy(), cols, indptr.astype(np.int32)), shape=(r1 - r0, N))
 
 
 def make_dataset(n_cells=10000, n_samples=50, k=15, dim=None, seed=0, n_clusters=12, n_batches=4,
-                 ragged=False, knn="auto", device=None):
+                 ragged=False, knn="auto", device=None, comm=None, row_block=False):
     """Returns (AnnDataLike, sample_meta DataFrame with columns case / batch / age).
 
     Cells are stored sample-contiguous like the reference's demo; ``ragged`` draws unequal cells
-    per sample.  ``obs`` has the column ``id`` (sample id per cell)."""
+    per sample.  ``obs`` has the column ``id`` (sample id per cell).  With a ``comm`` the kNN search is
+    split over the ranks (every rank ends with the same data); ``row_block=True`` then keeps only this
+    rank's block of rows of the graph on the host (``.obsp['connectivities']`` is (rows of the block) x
+    N, ``.row_block`` = (r0, r1)): what ``cna_b200.sharded.shard_to_device`` needs and nothing more."""
     rng = np.random.default_rng(seed)
     if dim is None:
         dim = 20 if n_cells <= 200_000 else 6
@@ -119,14 +141,19 @@ def make_dataset(n_cells=10000, n_samples=50, k=15, dim=None, seed=0, n_clusters
 
     use_gpu = torch.cuda.is_available() if knn == "auto" else knn == "gpu"
     if use_gpu and n_cells >= 50_000:
-        idx, dist = _knn_gpu(points, k)
+        idx, dist = _knn_gpu(points, k, comm=comm)
     else:
         idx, dist = _knn_cpu(points, k)
         if device is None and torch.cuda.is_available():
             device = "cuda"
         idx = torch.as_tensor(idx, device=device or "cpu")
         dist = torch.as_tensor(dist, device=device or "cpu")
-    A = fuzzy_simplicial_set(idx, dist)
+    block = None
+    if row_block and comm is not None and comm.world > 1:
+        per = (n_cells + comm.world - 1) // comm.world
+        block = (min(comm.rank * per, n_cells), min((comm.rank + 1) * per, n_cells))
+    A = fuzzy_simplicial_set(idx, dist, rows=block)
+    del idx, dist
 
     index = (pd.Index([f"c{i}" for i in range(n_cells)]) if n_cells <= 200_000
              else pd.RangeIndex(n_cells))
@@ -136,4 +163,7 @@ def make_dataset(n_cells=10000, n_samples=50, k=15, dim=None, seed=0, n_clusters
         "batch": np.tile(np.arange(n_batches), n_samples // n_batches + 1)[:n_samples],
         "age": np.random.default_rng(seed + 1).normal(0, 1, n_samples),
     }, index=pd.Index(np.arange(n_samples), name="id"))
-    return AnnDataLike(obs, A), meta
+    data = AnnDataLike(obs, A)
+    if block is not None:
+        data.row_block = block
+    return data, meta

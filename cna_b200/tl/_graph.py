@@ -154,9 +154,10 @@ class DeviceGraph:
         if not sp.issparse(A):
             raise TypeError("connectivities must be a scipy sparse matrix")
         A = A.tocsr()
-        if A.shape[0] != A.shape[1]:
+        block_only = shard is not None and shard[0].world > 1 and A.shape[0] != A.shape[1]
+        if A.shape[0] != A.shape[1] and not block_only:
             raise ValueError("connectivities must be square")
-        self.n_total = A.shape[0]
+        self.n_total = A.shape[1]  # a rank of a sharded run may hold only its block of rows (rows x N)
         if len(A.indices) >= 2 ** 31:
             raise ValueError("graphs with >= 2^31 stored edges are not supported")
         data = A.data if A.data.dtype in (np.float32, np.float64) else A.data.astype(np.float64)
@@ -212,10 +213,14 @@ class DeviceGraph:
     def _gather_blocks(A, data, comm):
         """Upload rows [o0, o1) of the host CSR (this rank's block of the caller's row order) and
         all-gather the blocks: returns the full (indptr, indices, data) on this rank's device."""
-        n_total = A.shape[0]
+        n_total = A.shape[1]
         rows_per = (n_total + comm.world - 1) // comm.world
         o0 = min(comm.rank * rows_per, n_total)
         o1 = min(o0 + rows_per, n_total)
+        if A.shape[0] != n_total:  # the host holds this rank's block only
+            if A.shape[0] != o1 - o0:
+                raise ValueError(f"rank {comm.rank} expects rows [{o0}, {o1}) of the graph, got {A.shape[0]} rows")
+            o0, o1 = 0, A.shape[0]
         e0, e1 = int(A.indptr[o0]), int(A.indptr[o1])
         deg = np.zeros(rows_per, dtype=np.int32)
         deg[: o1 - o0] = np.diff(A.indptr[o0:o1 + 1])

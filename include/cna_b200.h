@@ -382,6 +382,10 @@ int cna_host_perm_wait(void *handle);
  * k <= 64.  idx [n x k] int32 ascending by distance, dist2 [n x k] squared distances. */
 int cna_knn_bruteforce(const float *points, int64_t n, int dim, int k, int32_t *idx, float *dist2,
                        void *stream);
+/* The same search for the queries [q0, q0 + nq) only (idx / dist2 are [nq x k]): lets the ranks of a
+ * multi-GPU run split the queries of one data set between them. */
+int cna_knn_bruteforce_range(const float *points, int64_t n, int dim, int k, int64_t q0, int64_t nq,
+                             int32_t *idx, float *dist2, void *stream);
 
 #ifdef __cplusplus
 }
