@@ -287,6 +287,7 @@ def rooflines(prof, steps, N, S, n, nnz, K, Kl, s_steps, peaks):
         "cna_gram_tc": ("tensor", 2.0 * n * n * N, "Gram X^T X (tcgen05, fp16 hi/lo split, fp64 flush)"),
         "cna_null_hist": ("tensor", 2.0 * N * n * Kl, "null GEMM + threshold histogram (CUDA cores)"),
         "cna_null_hist_tc": ("tensor", 2.0 * N * n * Kl, "null GEMM + threshold histogram (tcgen05, fp16 hi/lo split)"),
+        "cna_null_hist_tc_dev": ("tensor", 2.0 * N * n * Kl, "null GEMM + threshold histogram (tcgen05, fp16 hi/lo split; thresholds read from device memory)"),
         "cna_perm_stats": (None, None, "permutation engine (fp64)"),
     }
     total = sum(ms for _, ms in prof.values()) or 1.0

@@ -379,6 +379,18 @@ def graph_of(data):
     return DeviceGraph(get_connectivity(data), resident=False)  # one-shot: built for this call only
 
 
+def _fingerprint(raw):
+    """Cheap content fingerprint of a column buffer: a strided sample of 4096 values (microseconds; a full
+    pass over a million ids would cost 0.5 ms of every resident call).  It catches a re-assigned column
+    that landed on a reused address and any bulk in-place edit; a handful of ids edited in place between
+    two calls on the same resident handle can escape it — call ``to_device`` again after such an edit."""
+    step = max(1, raw.shape[0] // 4096)
+    sample = raw[::step]
+    if raw.dtype.kind in "iubf":
+        return hash(sample.tobytes())
+    return hash(tuple(sample.tolist()))
+
+
 def sample_codes(data, sid_name):
     """Column order of ``pd.get_dummies(data.obs[sid_name])`` (``_nam.py:51``): the categories of a
     categorical column, otherwise the sorted unique values.  Returns (labels Index, int32 codes
@@ -387,8 +399,10 @@ def sample_codes(data, sid_name):
     sid = data.obs[sid_name]
     categorical = isinstance(sid.dtype, pd.CategoricalDtype)
     raw = sid.cat.codes.to_numpy() if categorical else sid.to_numpy()
-    # cache key for resident data: same column buffer => same codes (obs is shared with the host object)
-    key = (sid_name, raw.__array_interface__["data"][0], raw.shape[0], str(raw.dtype))
+    # cache key for resident data: same column buffer and same content fingerprint => same codes (obs is
+    # shared with the host object; an in-place edit keeps the buffer, a re-added column may reuse its address)
+    key = (sid_name, raw.__array_interface__["data"][0], raw.shape[0], str(raw.dtype), _fingerprint(raw),
+           hash(tuple(sid.cat.categories)) if categorical else None)
     if cache is not None and key in cache:
         return cache[key]
     if categorical:
