@@ -35,7 +35,7 @@ def load():
                 "Run `python -m cna_b200.build` on a machine with nvcc 12.9.") from exc
     lib = ctypes.CDLL(LIB_PATH)
     _declare(lib)
-    if lib.cna_abi_version() != 3:
+    if lib.cna_abi_version() != 4:
         raise ImportError("cna_b200: ABI version mismatch between _lib.py and libcna_b200.so")
     _lib = lib
     return lib
@@ -102,13 +102,14 @@ _SIGNATURES = {
     "cna_host_perm_wait": [_VP],
     "cna_split_f16": [_VP, _I64, _I64, _INT, _INT, _VP, _VP, _I64, _I64, _VP],
     "cna_gram_tc": [_VP, _VP, _I64, _I64, _INT, _VP, _VP, _I64, _VP],
+    "cna_sym_eig_top": [_VP, _I64, _INT, _INT, _VP, _VP, _VP, _VP, _I64, _VP],
     "cna_right_multiply_tc": [_VP, _VP, _I64, _I64, _INT, _VP, _VP, _I64, _INT, _VP, _I64, _VP],
     "cna_null_hist_tc": [_VP, _VP, _I64, _I64, _INT, _VP, _VP, _I64, _INT, _VP, _INT, _DBL, _VP, _VP],
     "cna_null_hist_tc_dev": [_VP, _VP, _I64, _I64, _INT, _VP, _VP, _I64, _INT, _VP, _INT, _VP, _DBL, _VP, _VP],
 }
 EXPORTS = sorted(list(_SIGNATURES) + ["cna_abi_version", "cna_last_error", "cna_launch_count",
                                       "cna_gram_tc_workspace", "cna_host_perm_blocks_async",
-                                      "cna_median_workspace"])
+                                      "cna_median_workspace", "cna_sym_eig_workspace", "cna_tc_max_ctas"])
 
 
 
@@ -123,6 +124,10 @@ def _declare(lib):
     lib.cna_gram_tc_workspace.argtypes = [ctypes.c_int]
     lib.cna_median_workspace.restype = ctypes.c_int64
     lib.cna_median_workspace.argtypes = []
+    lib.cna_tc_max_ctas.restype = ctypes.c_int
+    lib.cna_tc_max_ctas.argtypes = [ctypes.c_int]
+    lib.cna_sym_eig_workspace.restype = ctypes.c_int64
+    lib.cna_sym_eig_workspace.argtypes = [ctypes.c_int, ctypes.c_int]
     lib.cna_host_perm_blocks_async.restype = ctypes.c_void_p
     lib.cna_host_perm_blocks_async.argtypes = _SIGNATURES["cna_host_perm_blocks"]
     for name, args in _SIGNATURES.items():
@@ -504,6 +509,29 @@ def gram_tc(xp, n, out):
         ws = _GRAM_WS[key] = torch.empty(need, dtype=torch.uint8, device=xp.t.device)
     _call("cna_gram_tc", _ptr(xp.hi, torch.float16, "xh"), _ptr(xp.lo, torch.float16, "xl"), xp.ld, xp.rows,
           int(n), _ptr(out, torch.float64, "gram"), ws.data_ptr(), need, _stream())
+
+
+def tc_max_ctas(cap):
+    """Cap the grid of the persistent tensor-core kernels (0 = one CTA per SM); returns the previous cap."""
+    return int(load().cna_tc_max_ctas(int(cap)))
+
+
+_EIG_WS = {}
+
+
+def sym_eig_top(G, k, w_out, ut_out, de_out=None):
+    """Leading k eigenpairs of the symmetric [n x n] fp64 device matrix G: w_out[k] descending,
+    ut_out[k x n] (row c = eigenvector of the c-th largest eigenvalue).  One launch, no host round trip."""
+    n = int(G.shape[0])
+    need = int(load().cna_sym_eig_workspace(n, int(k)))
+    key = (G.device, need)
+    ws = _EIG_WS.get(key)
+    if ws is None:
+        _EIG_WS.clear()
+        ws = _EIG_WS[key] = torch.empty(need, dtype=torch.uint8, device=G.device)
+    _call("cna_sym_eig_top", _ptr(G, torch.float64, "G"), int(G.stride(0)), n, int(k),
+          _ptr(w_out, torch.float64, "w_out"), _ptr(ut_out, torch.float64, "ut_out"),
+          _ptr(de_out, torch.float64, "de_out", allow_none=True), ws.data_ptr(), need, _stream())
 
 
 def right_multiply_tc(xp, n, btp, n_out, out):

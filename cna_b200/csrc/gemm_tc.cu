@@ -27,6 +27,8 @@
 //     accumulation truncates, and an unflushed sum over 10^4 steps would bias the diagonal by more
 //     than the 1e-5 budget.  Partial Grams live in a per-CTA fp64 scratch (no atomics; the final
 //     reduction is deterministic).
+#include <atomic>
+
 #include <cuda.h>
 #include <cuda_fp16.h>
 
@@ -712,6 +714,8 @@ static int make_map(CUtensorMap *map, const void *base, int64_t cols, int64_t ro
     return CNA_OK;
 }
 
+static std::atomic<int> g_cta_cap{0};
+
 static int xb_tc_launch(Epi epi, const void *xh, const void *xl, int64_t ld16, int64_t n_rows, int n, const void *bh,
                         const void *bl, int64_t ld16_b, int n_out, XbTcArgs a, cudaStream_t st) {
     CNA_REQUIRE(n_rows > 0 && n_rows < (int64_t(1) << 31) && n > 0 && n_out > 0, "xb_tc: bad shape");
@@ -730,7 +734,10 @@ static int xb_tc_launch(Epi epi, const void *xh, const void *xl, int64_t ld16, i
     size_t smem = size_t(kStages) * kStageBytes + 1024 + 256 + size_t(kXbEpiWarps) * kQueue * 4 +
                   (epi == Epi::HIST ? (sizeof(double) + sizeof(uint32_t) + 2 * sizeof(float)) * (a.n_edges + 2) : 0);
     int64_t tiles = (n_rows + kBM - 1) / kBM;
-    unsigned grid = unsigned(tiles < num_sms() ? tiles : num_sms());
+    int ctas = num_sms();
+    const int cap = g_cta_cap.load(std::memory_order_relaxed);
+    if (cap > 0 && cap < ctas) ctas = cap;  // the caller keeps SMs free for a kernel on another stream
+    unsigned grid = unsigned(tiles < ctas ? tiles : ctas);
     if (epi == Epi::HIST) {
         CNA_CUDA(cudaFuncSetAttribute(xb_tc_kernel<Epi::HIST>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
         xb_tc_kernel<Epi::HIST><<<grid, kXbThreads, smem, st>>>(tm_ah, tm_al, tm_bh, tm_bl, a);
@@ -841,3 +848,7 @@ int cna_gram_tc(const void *xh, const void *xl, int64_t ld16, int64_t n_rows, in
 }
 
 }  // extern "C"
+
+extern "C" int cna_tc_max_ctas(int cap) {
+    return tc::g_cta_cap.exchange(cap < 0 ? 0 : cap, std::memory_order_relaxed);
+}

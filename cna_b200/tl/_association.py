@@ -105,13 +105,23 @@ class _Readback:
 _SIDE = {}
 
 
-def _side_stream(dev):
-    """One side stream per device for the copies of the per-cell result columns (they overlap the
-    kernels queued after the pass that produced them)."""
-    key = (dev.type, dev.index)
+def _side_stream(dev, tag="copy"):
+    """Side streams per device: "copy" for the copies of the per-cell result columns (they overlap the
+    kernels queued after the pass that produced them), "eig" for the single-CTA eigensolver."""
+    key = (dev.type, dev.index, tag)
     if key not in _SIDE:
         _SIDE[key] = torch.cuda.Stream(device=dev)
     return _SIDE[key]
+
+
+_SMS = {}
+
+
+def _sm_count(dev):
+    key = (dev.type, dev.index)
+    if key not in _SMS:
+        _SMS[key] = torch.cuda.get_device_properties(dev).multi_processor_count
+    return _SMS[key]
 
 
 def _to_host_owned(t, stream=None):
@@ -279,6 +289,21 @@ def _association(res, perms, Nnull=1000, local_test=True, show_progress=False, c
     # ---- phase A ----
     def phase_a():
         G_d = _nam.gram_device(res.x, n, comm=comm, planes=res.planes)
+        # the leading max(ks) eigenpairs of the Gram follow on the device (one launch); only the full result
+        # surface (and n > 512) decomposes the Gram with LAPACK on the host
+        eig = None
+        if res.svd_top is not None and res.svd_top < n <= _nam.DEVICE_EIG_MAX_N:
+            # one CTA, ~1 ms: on a side stream, beside the null GEMM (which leaves it an SM, phase B)
+            w_d = torch.empty(res.svd_top, dtype=torch.float64, device=dev)
+            ut_d = torch.empty((res.svd_top, n), dtype=torch.float64, device=dev)
+            gram_done = torch.cuda.Event()
+            gram_done.record()
+            side = _side_stream(dev, "eig")
+            with torch.cuda.stream(side):
+                side.wait_event(gram_done)
+                _lib.sym_eig_top(G_d, res.svd_top, w_d, ut_d)
+                back_e = _Readback("eig", [w_d, ut_d])
+            eig = (w_d, ut_d, back_e, G_d)  # (G_d stays referenced until the side stream is done with it)
         mx = torch.zeros(1, dtype=torch.float64, device=dev)
         tabs = None
         if local_test:
@@ -291,10 +316,10 @@ def _association(res, perms, Nnull=1000, local_test=True, show_progress=False, c
             _lib.fdr_thresholds(mx, thr_d, edges_d, count_d)  # :101-102, _stats.py:51
             tabs = (thr_d, edges_d, count_d)
         med = res.ridge_median if res.ridge_median is not None else torch.zeros(2, dtype=torch.float64, device=dev)
-        return _Readback("phase_a", [G_d, med, mx]), tabs
+        return _Readback("phase_a", [G_d, med, mx] if eig is None else [med, mx]), tabs, eig
 
     # ---- phase B ----
-    def phase_b(tabs):
+    def phase_b(tabs, eig_running=False):
         # permutations: indices from the host RNG (bit-exact), everything else on the device
         if perms is not None:
             perm_d = perms.result_device(dev)
@@ -315,7 +340,12 @@ def _association(res, perms, Nnull=1000, local_test=True, show_progress=False, c
             # (cells x n) . (n x Kl) on the tensor cores with the histogram epilogue straight out of TMEM
             ytp = _lib.Planes(Kl, n, dev, zero=True)
             _lib.perm_stats(y_d, perm_d[:Kl], C_d, W_d, None, None, None, None, None, Kl, planes=ytp)
-            _lib.null_hist_tc_dev(res.planes, n, ytp, Kl, edges_d, count_d, hist)
+            cap = _lib.tc_max_ctas(_sm_count(dev) - 1) if eig_running else None  # an SM for the eigensolver
+            try:
+                _lib.null_hist_tc_dev(res.planes, n, ytp, Kl, edges_d, count_d, hist)
+            finally:
+                if cap is not None:
+                    _lib.tc_max_ctas(cap)
             _lib.obs_hist_dev(res.ncorr, res.valid, edges_d, thr_d, count_d, obs[0], obs[1])
             if comm is not None:  # counts over all shards
                 comm.all_reduce(hist)
@@ -330,12 +360,13 @@ def _association(res, perms, Nnull=1000, local_test=True, show_progress=False, c
         mark("null kernels launched")
         return perm_d, C_d, W_d, back
 
-    def launch_pc_regressions(U, perm_d, C_d, W_d):
+    def launch_pc_regressions(U, perm_d, C_d, W_d, eig=None):
         """PC regressions of every permuted phenotype (:84) -> SSEs and, unless the full table of null
-        p-values is wanted on the host, the F survival function + min over ks on the device."""
+        p-values is wanted on the host, the F survival function + min over ks on the device.  ``eig``:
+        the device-resident eigenpairs (U^T never left the GPU)."""
         ssered_d = torch.empty(Nnull, dtype=torch.float64, device=dev)
         ssefull_d = torch.full((Nnull, len(ks_dev)), float("nan"), dtype=torch.float64, device=dev)
-        Ut_d = _to_dev(np.ascontiguousarray(U[:, :kmax].T))
+        Ut_d = eig[1][:kmax] if eig is not None else _to_dev(np.ascontiguousarray(U[:, :kmax].T))
         ks_d = _to_dev(ks_dev.astype(np.int32))
         _lib.perm_stats(y_d, perm_d, C_d, W_d, Ut_d, ks_d, ssered_d, ssefull_d, None, 0)
         if want_null_table:
@@ -406,32 +437,46 @@ def _association(res, perms, Nnull=1000, local_test=True, show_progress=False, c
         mark("fdr table done")
         return fdrs, t5, t10
 
-    back_a, tabs = phase_a()
+    back_a, tabs, eig = phase_a()
     if columns is not None:
         columns.start_coef()
     # phase B needs the permutation indices: queued now when the draw has already finished (or when this
     # rank only receives them), otherwise as soon as the Gram is here if the draw has finished by then,
     # otherwise after the decomposition
-    b = phase_b(tabs) if (perms is None or perms.done()) else None
+    b = phase_b(tabs, eig is not None) if (perms is None or perms.done()) else None
     while True:
-        Gh, med_h, mx_h = back_a.get()
-        mark("gram on host")
-        if res.settle(float(med_h[0])):
+        got = back_a.get()
+        mark("gram on host" if eig is None else "ridge median on host")
+        if res.settle(float(got[-2][0])):
             break
         # the first ridge did not bring the median batch kurtosis down to 6 (_nam.py:154): the walk has
         # now been finished ridge by ridge and everything queued on the speculative NAM is repeated
-        back_a, tabs = phase_a()
+        back_a, tabs, eig = phase_a()
         if columns is not None:
             columns.start_coef()
-        b = phase_b(tabs) if b is not None else None
+        b = phase_b(tabs, eig is not None) if b is not None else None
     if b is None and perms.done():
-        b = phase_b(tabs)
-    U, svs, res.G = _nam.svd_of_gram(Gh.copy(), res.svd_top)
+        b = phase_b(tabs, eig is not None)
+    if eig is None:
+        U, svs, res.G = _nam.svd_of_gram(got[0].copy(), res.svd_top)
+        if b is None:
+            b = phase_b(tabs)
+        perm_d, C_d, W_d, back_b = b
+        sse_d = launch_pc_regressions(U, perm_d, C_d, W_d)  # the device works on these while the host ...
+    else:
+        if b is None:
+            b = phase_b(tabs, True)
+        perm_d, C_d, W_d, back_b = b
+        # the PC regressions are queued behind the null GEMM and wait (on the device) for the eigenvectors
+        torch.cuda.current_stream().wait_event(eig[2].event)
+        sse_d = launch_pc_regressions(None, perm_d, C_d, W_d, eig)
+        w_h, ut_h = eig[2].get()
+        mark("eigenpairs on host")
+        # same shapes as svd_of_gram: trailing columns / values are zero and are never read
+        U, svs = np.zeros((n, n)), np.zeros(n)
+        U[:, :res.svd_top] = ut_h.T
+        svs[:res.svd_top] = np.maximum(w_h, 0.0)
     res.U, res.svs = U, svs
-    if b is None:
-        b = phase_b(tabs)
-    perm_d, C_d, W_d, back_b = b
-    sse_d = launch_pc_regressions(U, perm_d, C_d, W_d)  # the device works on these while the host ...
     o = observed_test(U)                                 # ... tests the observed phenotype
     fdrs, fdr_5p_t, fdr_10p_t = fdr_table(back_b) if local_test else (None, None, None)
     pfinal, nullminps, nullr2s = global_pvalue(o.p, sse_d)

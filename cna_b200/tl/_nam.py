@@ -4,6 +4,7 @@ Mirrors ``src/cna/tools/_nam.py`` of the reference (same public names, arguments
 return types) with the arithmetic running on the GPU through the C-ABI in ``include/cna_b200.h``.
 The device state is CELLS x SAMPLES (the transpose of the reference's DataFrames) in fp32.
 """
+import os
 from argparse import Namespace
 
 import numpy as np
@@ -357,6 +358,11 @@ TC_GRAM_MAX_N = 512  # four 128-row output tiles in groups of <= 512 TMEM column
 def planes_of(x, n):
     """fp16 hi/lo operand planes of the fp32 matrix x[:, :n] (tensor-core operand format)."""
     return _lib.split_f16(x, n)
+
+
+DEVICE_EIG_MAX_N = 512  # cna_sym_eig_top's limit; CNA_B200_HOST_EIG=1 forces the LAPACK route (cross-check)
+if os.environ.get("CNA_B200_HOST_EIG"):
+    DEVICE_EIG_MAX_N = 0
 
 
 def gram_device(x, n, comm=None, planes=None):

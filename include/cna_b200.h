@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define CNA_B200_ABI_VERSION 3
+#define CNA_B200_ABI_VERSION 4
 
 /* bit pattern (a signalling NaN) of vector entries cna_median_f64 ignores: padding of gathered shards */
 #define CNA_MEDIAN_SKIP_BITS 0x7FF4DEADBEEF0001ull
@@ -241,6 +241,25 @@ int cna_split_f16(const float *src, int64_t ld_src, int64_t src_rows, int src_co
 int64_t cna_gram_tc_workspace(int n);
 int cna_gram_tc(const void *xh, const void *xl, int64_t ld16, int64_t n_rows, int n, double *gram,
                 void *workspace, int64_t workspace_bytes, void *stream);
+
+/* Cap on the number of CTAs of the persistent tensor-core kernels (cna_null_hist_tc*, cna_right_multiply_tc):
+ * they launch one CTA per SM; a caller that runs a single-CTA kernel (cna_sym_eig_top) on another stream at the
+ * same time leaves it an SM by passing (SM count - 1).  0 = no cap.  Returns the previous cap.  Process-wide.
+ * replaces: nothing in the reference (scheduling only). */
+int cna_tc_max_ctas(int cap);
+
+/* Leading k eigenpairs of the symmetric n x n matrix (G + G^T) / 2 (the Gram), n <= 512, entirely on the
+ * device in one launch: Householder tridiagonalisation, multisection on Sturm counts, inverse iteration
+ * (dstein's clustering rule) and back-transformation, all fp64.  w_out[k]: eigenvalues, descending;
+ * ut_out[k x n]: row c = unit eigenvector of the c-th largest eigenvalue (sign arbitrary — the association
+ * test only forms projectors U_k U_k^T); de_out: optional [2 n + 4], diagonal and off-diagonal of the
+ * tridiagonal form, then the SM clocks spent in the four phases (diagnostics).  `workspace`: cna_sym_eig_workspace(n, k) bytes, contents irrelevant on entry.
+ * replaces: _nam.py:105 `U, svs, UT = np.linalg.svd(NAM.dot(NAM.T))` for the columns the association
+ * test reads (_association.py:35-42 `U[:, :k]`, k <= max(ks)); the full decomposition of
+ * return_full=True stays with LAPACK on the host. */
+int64_t cna_sym_eig_workspace(int n, int k);
+int cna_sym_eig_top(const double *G, int64_t ldg, int n, int k, double *w_out, double *ut_out, double *de_out,
+                    void *workspace, int64_t workspace_bytes, void *stream);
 
 /* Same contract as cna_right_multiply: out = X . B, with B given TRANSPOSED as fp16 planes
  * bt [n_out x ld16_b] (row j = column j of B).  replaces: _nam.py:106. */

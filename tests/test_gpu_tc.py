@@ -136,3 +136,54 @@ def test_null_hist_tc(lib, N, n, Kl):
     rank_hist = h2[0] + 1
     np.testing.assert_allclose(_stats.fdr_from_counts(h2.sum(0), rank_hist, n_null=Kl),
                                _stats.fdr_from_counts(h2, rank_hist), rtol=1e-12)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,k,kind", [(200, 16, "gram"), (50, 4, "gram"), (500, 40, "gram"), (216, 17, "gram"),
+                                      (230, 10, "gram"), (129, 129 - 1, "gram"), (120, 12, "clustered"),
+                                      (37, 5, "lowrank"), (3, 2, "gram"), (2, 1, "gram"), (300, 150, "gram")])
+def test_sym_eig_top_vs_lapack(lib, n, k, kind):
+    """cna_sym_eig_top (device Householder + multisection + inverse iteration) against numpy's eigh:
+    eigenvalues to 1e-12 of the largest, projectors onto every leading subspace that is separated from
+    the rest to 1e-9, unit orthogonal vectors, small residual.  Replaces _nam.py:105 for the columns
+    _association.py:35-42 reads."""
+    import torch
+    rng = np.random.default_rng(n * 1000 + k)
+    if kind == "gram":
+        X = rng.normal(size=(20 * n, n)) * np.linspace(3.0, 1.0, n)
+        G = X.T @ X
+    elif kind == "lowrank":  # rank 10 < n: trailing eigenvalues are zero up to rounding
+        X = rng.normal(size=(10, n))
+        G = X.T @ X
+    else:  # near-multiple leading eigenvalues: the re-orthogonalisation inside clusters
+        Q, _ = np.linalg.qr(rng.normal(size=(n, n)))
+        ev = np.linspace(1.0, 2.0, n)
+        ev[-3:] = [5.0, 5.0 + 1e-9, 5.0 + 2e-9]
+        ev[-6:-3] = [4.0, 4.0 + 1e-13, 4.0 + 3e-13]
+        G = (Q * ev) @ Q.T
+    G = G + 1e-9 * rng.normal(size=(n, n)) * np.abs(G).max() * 1e-7  # not exactly symmetric, like the device Gram
+    Gs = (G + G.T) / 2
+    G_d = torch.as_tensor(G, device="cuda")
+    w_d = torch.empty(k, dtype=torch.float64, device="cuda")
+    ut_d = torch.empty((k, n), dtype=torch.float64, device="cuda")
+    de_d = torch.empty(2 * n + 4, dtype=torch.float64, device="cuda")
+    lib.sym_eig_top(G_d, k, w_d, ut_d, de_d)
+    torch.cuda.synchronize()
+    w, Ut, de = w_d.cpu().numpy(), ut_d.cpu().numpy(), de_d.cpu().numpy()
+    w0, U0 = np.linalg.eigh(Gs)
+    w0, U0 = w0[::-1], U0[:, ::-1]
+    scale = abs(w0[0])
+    # the tridiagonal form has the same spectrum
+    import scipy.linalg as sl
+    if n > 1:
+        wt = sl.eigvalsh_tridiagonal(de[:n], de[n:2 * n - 1])[::-1]
+        np.testing.assert_allclose(wt, w0, rtol=0, atol=1e-12 * scale)
+    np.testing.assert_allclose(w, w0[:k], rtol=0, atol=1e-12 * scale)
+    np.testing.assert_allclose(Ut @ Ut.T, np.eye(k), rtol=0, atol=1e-10)
+    resid = Gs @ Ut.T - Ut.T * w
+    assert np.abs(resid).max() <= 1e-10 * scale
+    for j in range(1, k + 1):  # every leading subspace with a gap behind it
+        gap = (w0[j - 1] - w0[j]) / scale if j < n else 1.0
+        if gap > 1e-6:
+            P, P0 = Ut[:j].T @ Ut[:j], U0[:, :j] @ U0[:, :j].T
+            assert np.abs(P - P0).max() <= 1e-9 / gap * 1e-3 + 1e-11, (j, gap)
