@@ -109,7 +109,8 @@ _SIGNATURES = {
 }
 EXPORTS = sorted(list(_SIGNATURES) + ["cna_abi_version", "cna_last_error", "cna_launch_count",
                                       "cna_gram_tc_workspace", "cna_host_perm_blocks_async",
-                                      "cna_median_workspace", "cna_sym_eig_workspace", "cna_tc_max_ctas"])
+                                      "cna_median_workspace", "cna_sym_eig_workspace", "cna_tc_max_ctas",
+                                      "cna_perm_draw_workspace", "cna_perm_draw_device"])
 
 
 
@@ -124,6 +125,11 @@ def _declare(lib):
     lib.cna_gram_tc_workspace.argtypes = [ctypes.c_int]
     lib.cna_median_workspace.restype = ctypes.c_int64
     lib.cna_median_workspace.argtypes = []
+    lib.cna_perm_draw_workspace.restype = ctypes.c_int64
+    lib.cna_perm_draw_workspace.argtypes = [ctypes.c_int64, ctypes.c_int64, ctypes.c_int]
+    lib.cna_perm_draw_device.restype = ctypes.c_int
+    lib.cna_perm_draw_device.argtypes = [_VP, _INT, _INT, _DBL, _INT, _VP, _VP, _I64, _VP, _I64, _VP, _VP, _VP,
+                                         _VP, _I64, _VP]
     lib.cna_tc_max_ctas.restype = ctypes.c_int
     lib.cna_tc_max_ctas.argtypes = [ctypes.c_int]
     lib.cna_sym_eig_workspace.restype = ctypes.c_int64
@@ -646,6 +652,104 @@ class HostPermJob:
                 self.result()
         except Exception:
             pass
+
+
+_DRAW_WS = {}
+_DRAW_STREAM = {}
+_DRAW_RING = {}
+
+
+class DevicePermJob:
+    """``host_perm_blocks`` on the GPU (``cna_perm_draw_device``), queued on a side stream of its own so that
+    it runs beside whatever the caller launches next.  Same contract as ``HostPermJob``: numpy's global
+    generator must not be touched between construction and ``result()`` / ``finish()``, which writes the
+    advanced state back.  ``finish()`` returns False when the draw has to be repeated with the host engine
+    (an argsort within rounding of a tie, or a stream that was too short: probability ~1e-6 per call); the
+    generator is then left in its state from before the draw."""
+
+    _turn = 0
+
+    def __init__(self, block_off, src_pos, num, device):
+        import numpy as np
+        kind, key, pos, has_gauss, gauss = np.random.get_state()
+        if kind != "MT19937":
+            raise CnaError(f"numpy's global generator is {kind}, expected MT19937")
+        self.before = (kind, key, pos, has_gauss, gauss)
+        self.block_off = np.ascontiguousarray(block_off, dtype=np.int32)
+        key = np.ascontiguousarray(key, dtype=np.uint32)
+        n, nb = int(self.block_off[-1]), len(self.block_off) - 1
+        self.count, self.first = n * int(num), 1 if has_gauss else 0
+        dev = torch.device(device)
+        need = int(load().cna_perm_draw_workspace(n, int(num), nb))
+        ws = _DRAW_WS.get((dev, need))
+        if ws is None:
+            _DRAW_WS.clear()
+            ws = _DRAW_WS[(dev, need)] = torch.empty(need, dtype=torch.uint8, device=dev)
+        # Output buffers come from a ring of two per shape, allocated once: the draw runs on a stream of its
+        # own, so nothing here may be ordered by (or wait for) the caller's stream.  A buffer is reused two
+        # draws later, when the call that consumed it has long returned.
+        ring = _DRAW_RING.setdefault((dev, int(num), n), [])
+        if len(ring) < 2:
+            ring.append((torch.empty((int(num), n), dtype=torch.int32, device=dev),
+                         torch.empty(650, dtype=torch.int32, device=dev),  # state (626) | pad | tail (4 f64) | flag
+                         torch.empty(650, dtype=torch.int32, pin_memory=True)))
+            torch.cuda.current_stream(dev).synchronize()  # first use only: the allocations are settled
+        self.out, self.small, self.host = ring[DevicePermJob._turn % 2] if len(ring) == 2 else ring[0]
+        DevicePermJob._turn += 1
+        src = None if src_pos is None else np.ascontiguousarray(src_pos, dtype=np.int32)
+        self._keep = (ws, key, src)
+        side = _DRAW_STREAM.get(dev)
+        if side is None:
+            side = _DRAW_STREAM[dev] = torch.cuda.Stream(device=dev)
+        with torch.cuda.stream(side):
+            base = self.small.data_ptr()
+            rc = load().cna_perm_draw_device(key.ctypes.data, int(pos), int(has_gauss), float(gauss), nb,
+                                             self.block_off.ctypes.data, None if src is None else src.ctypes.data,
+                                             int(num), self.out.data_ptr(), n, base, base + 640 * 4, base + 648 * 4,
+                                             ws.data_ptr(), need, side.cuda_stream)
+            if rc != 0:
+                raise CnaError(f"cna_perm_draw_device failed ({rc}): {load().cna_last_error().decode()}")
+            self.host.copy_(self.small, non_blocking=True)
+            self.event = torch.cuda.Event()
+            self.event.record()
+        self.finished = None
+
+    def done(self):
+        return True  # queued: whatever consumes the permutations waits on the device
+
+    def result_tensor_device(self):
+        """The [num x n] int32 index matrix on the device; the current stream waits for the draw."""
+        torch.cuda.current_stream(self.out.device).wait_event(self.event)
+        return self.out
+
+    def finish(self):
+        """Waits for the draw, hands numpy's generator its advanced state; False = repeat on the host."""
+        import math
+
+        import numpy as np
+        if self.finished is not None:
+            return self.finished
+        self.event.synchronize()
+        h = self.host.numpy()
+        state = h[:626].view(np.uint32)
+        tail = h[640:648].view(np.float64)
+        ok = bool(state[625]) and int(h[648]) == 0
+        if ok:
+            has_gauss, gauss = 0, 0.0
+            if (self.count - self.first) % 2 == 1:  # legacy_gauss caches the second deviate of the last pair
+                r2, x1 = float(tail[1]), float(tail[2])
+                has_gauss, gauss = 1, math.sqrt(-2.0 * math.log(r2) / r2) * x1
+            np.random.set_state(("MT19937", state[:624].copy(), int(state[624]), has_gauss, gauss))
+        else:
+            np.random.set_state(self.before)
+        self.finished = ok
+        return ok
+
+    def result(self):
+        ok = self.finish()
+        if not ok:
+            raise CnaError("device permutation draw must be repeated on the host")
+        return self.out.cpu().numpy()
 
 
 def knn_bruteforce(points, k, queries=None):

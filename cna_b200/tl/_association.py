@@ -258,7 +258,7 @@ class _Columns:
         mark("obs written")
 
 
-def _association(res, perms, Nnull=1000, local_test=True, show_progress=False, columns=None):
+def _association(res, perms, Nnull=1000, local_test=True, show_progress=False, columns=None, host_draw=True):
     """``_nam.py:163`` (Gram + SVD of the residualised NAM) and ``_association.py:10-129`` after
     seeding / permutation drawing (done by the caller so that they overlap with the NAM kernels).
     ``res`` carries the device-resident residualised NAM (``res.planes`` / ``res.x``), M, r, the
@@ -325,7 +325,7 @@ def _association(res, perms, Nnull=1000, local_test=True, show_progress=False, c
             perm_d = perms.result_device(dev)
         else:  # a shard other than rank 0: the indices are drawn once, by rank 0
             perm_d = torch.empty((Nnull, n), dtype=torch.int32, device=dev)
-        if comm is not None:
+        if comm is not None and host_draw:
             comm.broadcast(perm_d, src=0)
         mark("permutations uploaded")
         C_d = _to_dev(res.C) if r else None
@@ -443,7 +443,9 @@ def _association(res, perms, Nnull=1000, local_test=True, show_progress=False, c
     # phase B needs the permutation indices: queued now when the draw has already finished (or when this
     # rank only receives them), otherwise as soon as the Gram is here if the draw has finished by then,
     # otherwise after the decomposition
-    b = phase_b(tabs, eig is not None) if (perms is None or perms.done()) else None
+    # (with the eigensolver on the device the host has nothing to do for the Gram: it waits for the draw
+    # right here and queues phase B behind phase A without a gap)
+    b = phase_b(tabs, eig is not None) if (perms is None or perms.done() or eig is not None) else None
     while True:
         got = back_a.get()
         mark("gram on host" if eig is None else "ridge median on host")
@@ -496,7 +498,7 @@ def association(data, y, sid_name, batches=None, covs=None, donorids=None, ks=No
     Limits (checked before any device work): at most 1024 samples in ``data.obs[sid_name]`` and at
     most 1024 selected samples."""
     out = select_output(show_progress)
-    bad = set(kwargs) - {"Nnull", "force_permute_all", "local_test", "seed"}
+    bad = set(kwargs) - {"Nnull", "force_permute_all", "local_test", "seed", "_host_draw"}
     if bad:  # the reference forwards **kwargs to _association(), which rejects anything else
         raise TypeError(f"_association() got an unexpected keyword argument '{sorted(bad)[0]}'")
     mark("association() entered")
@@ -555,9 +557,14 @@ def association(data, y, sid_name, batches=None, covs=None, donorids=None, ks=No
     comm = getattr(data, "comm", None)
     if comm is not None and return_full:
         raise NotImplementedError("return_full=True is not supported on a cell-axis shard")
-    # the permutation draw only needs the sample-level inputs: it runs on the host's threads from here on
-    perms = (_stats.PermutationDraw(y_std, perm_batches, donor_f, Nnull)
-             if comm is None or comm.rank == 0 else None)
+    # the permutation draw only needs the sample-level inputs.  Device engine (default): queued on a side
+    # stream, every rank of a sharded run draws the same matrix itself; host engine: rank 0 draws on the
+    # host's threads and broadcasts
+    dev = _graph.device()
+    host_draw = kwargs.get("_host_draw", False) or not _stats._device_draw_enabled()
+    perms = (_stats.PermutationDraw(y_std, perm_batches, donor_f, Nnull, device=dev,
+                                    engine="host" if host_draw else "device")
+             if (not host_draw or comm is None or comm.rank == 0) else None)
     mark("permutation draw started")
     try:
         if stn is None:
@@ -576,10 +583,26 @@ def association(data, y, sid_name, batches=None, covs=None, donorids=None, ks=No
         # every rank of a sharded run ends with the full columns in its copy of data.obs
         columns = _Columns(data, key_added, stn, res, gather=True)
         core = _association(res, perms, Nnull=Nnull, local_test=local_test, show_progress=show_progress,
-                            columns=columns)
-    finally:
+                            columns=columns, host_draw=host_draw)
+    except BaseException:
         if perms is not None:
-            perms.cancel()  # joins the draw and hands numpy's generator its advanced state back
+            try:
+                perms.cancel()  # joins the draw and hands numpy's generator its advanced state back
+            except _stats.RedoWithHostDraw:
+                pass
+        raise
+    if perms is not None:
+        try:
+            perms.cancel()
+        except _stats.RedoWithHostDraw:
+            # the device draw could not certify one of its argsorts (~1e-6 per call): nothing has been written
+            # to data.obs yet and the generator is back in its state from before the draw — once more with
+            # the host engine
+            return association(data, y, sid_name, batches=user_batches, covs=covs, donorids=donorids, ks=ks,
+                               key_added=key_added, max_frac_pcs=max_frac_pcs, nsteps=nsteps,
+                               show_progress=show_progress, allow_low_sample_size=allow_low_sample_size,
+                               return_full=return_full, ridges=ridges,
+                               **{**{k: v for k, v in kwargs.items() if k != "seed"}, "_host_draw": True})
     columns.write()
     svs = res.svs
     LAST.__dict__.clear()

@@ -1,10 +1,12 @@
 """Permutation generators and empirical-FDR bookkeeping — host side.
 
-Mirrors ``src/cna/tools/_stats.py`` of the reference.  Permutation *indices* are drawn on the host
-with exactly the reference's sequence of legacy numpy RNG calls (``np.random.randn`` +
-``np.argsort(axis=0)``), because the legacy MT19937 / polar-Gaussian stream cannot be reproduced by a
-device generator and the permutations must be bit-identical.  The gather ``Y[bix]`` and everything
-after it happen on the device (``cna_perm_stats``).
+Mirrors ``src/cna/tools/_stats.py`` of the reference.  Permutation *indices* follow exactly the
+reference's sequence of legacy numpy RNG calls (``np.random.randn`` + ``np.argsort(axis=0)``): the legacy
+MT19937 / polar-Gaussian stream is restated natively, on the device (``cna_perm_draw_device``, the default
+engine of ``association``) and on the host (``cna_host_perm_blocks``), and leaves numpy's global generator
+in the state the reference's calls would have left it in.  The functions ``*_indices`` keep the literal
+numpy call sequence as the in-repo cross-check.  The gather ``Y[bix]`` and everything after it happen on
+the device (``cna_perm_stats``).
 """
 import numpy as np
 
@@ -56,16 +58,32 @@ def _batch_blocks(B):
     return off, np.concatenate(batchind)
 
 
-class PermutationDraw:
-    """Asynchronous ``conditional_permutation_matrix`` / ``grouplevel_permutation_matrix``: the
-    draws run on a thread owned by the native library while the caller drives the GPU.  numpy's
-    global generator must not be used until ``result()`` has returned (it is advanced there exactly
-    as the reference's calls would have advanced it)."""
+class RedoWithHostDraw(Exception):
+    """The device draw could not certify an argsort (two keys within rounding of a tie) or ran out of
+    stream: the call is repeated with the host engine.  numpy's generator is back in its prior state."""
 
-    def __init__(self, y_std, batches, donorids, num):
+
+def _device_draw_enabled():
+    import os
+
+    import torch
+    return torch.cuda.is_available() and not os.environ.get("CNA_B200_HOST_DRAW")
+
+
+class PermutationDraw:
+    """Asynchronous ``conditional_permutation_matrix`` / ``grouplevel_permutation_matrix``.  Default engine:
+    the device draw (``cna_perm_draw_device``), queued on a side stream beside the NAM kernels — no host
+    threads, and on a cell-axis shard every rank draws the same matrix itself.  ``engine="host"`` (or
+    ``CNA_B200_HOST_DRAW=1``): the native host engine on a library-owned thread.  numpy's global generator
+    must not be used until ``result()`` / ``cancel()`` has returned (it is advanced there exactly as the
+    reference's calls would have advanced it)."""
+
+    def __init__(self, y_std, batches, donorids, num, device=None, engine=None):
         from .. import _lib
         self._map = None
         self._fail = False
+        self._dev = None
+        use_device = device is not None and (engine == "device" or (engine is None and _device_draw_enabled()))
         if donorids is not None:  # _stats.py:20-32
             G, Y = np.asarray(donorids), np.asarray(y_std)
             Gu = np.unique(G)
@@ -76,21 +94,31 @@ class PermutationDraw:
                 self._fail, self._job = True, None
                 return
             self._map = (rep, Gind)
-            self._job = _lib.HostPermJob(np.array([0, len(rep)], dtype=np.int32), None, num)
+            off, pos = np.array([0, len(rep)], dtype=np.int32), None
         else:  # _stats.py:4-18
             off, pos = _batch_blocks(batches)
+        if use_device:
+            self._dev = self._job = _lib.DevicePermJob(off, pos, num, device)
+        else:
             self._job = _lib.HostPermJob(off, pos, num)
 
     def done(self):
         return self._job is None or self._job.done()
 
     def cancel(self):
-        if self._job is not None:
+        """Joins the draw and hands numpy's generator its advanced state back.  Raises RedoWithHostDraw when
+        the device engine asks for a repeat."""
+        if self._dev is not None:
+            if not self._dev.finish():
+                raise RedoWithHostDraw()
+        elif self._job is not None:
             self._job.result()
 
     def result(self):
         if self._fail:
             raise TypeError("'NoneType' object is not subscriptable")  # what the reference dies with
+        if self._dev is not None and not self._dev.finish():
+            raise RedoWithHostDraw()
         out = self._job.result()
         if self._map is not None:
             rep, Gind = self._map
@@ -98,9 +126,18 @@ class PermutationDraw:
         return out
 
     def result_device(self, device):
-        """The index matrix as an int32 device tensor (asynchronous copy out of pinned memory)."""
-        if self._map is not None or self._fail:
-            import torch
+        """The index matrix as an int32 device tensor (asynchronous)."""
+        import torch
+        if self._fail:
+            raise TypeError("'NoneType' object is not subscriptable")
+        if self._dev is not None:
+            out = self._dev.result_tensor_device()
+            if self._map is not None:
+                rep, Gind = self._map
+                rep_t = torch.as_tensor(rep.astype(np.int32), device=out.device)
+                out = rep_t[out.long()][:, torch.as_tensor(Gind, device=out.device)].contiguous()
+            return out
+        if self._map is not None:
             return torch.from_numpy(self.result()).to(device, non_blocking=True)
         return self._job.result_tensor().to(device, non_blocking=True)
 

@@ -384,6 +384,25 @@ int cna_host_perm_blocks(uint32_t *key, int *pos, int *has_gauss, double *gauss,
                          const int32_t *block_off, const int32_t *src_pos, int64_t num, int32_t *out,
                          int64_t ld_out, int n_threads);
 
+/* cna_host_perm_blocks on the device (perm_dev.cu): the MT19937 recurrence in one CTA, every attempt of the
+ * polar rejection loop tested in parallel, accepted pairs numbered by a scan, per-column argsort by counting.
+ * key_host / pos / has_gauss / gauss: numpy's legacy state BEFORE the draw; block_off_host [n_blocks + 1],
+ * src_pos_host [n] or NULL: HOST tables as in cna_host_perm_blocks (packed into a page-locked staging
+ * buffer of the library and sent in one asynchronous copy: the call never waits for the stream).
+ * out: device int32 [num x ld_out].  state_out (device, 626 uint32): key after the draw, pos, 1 if the
+ * stream was long enough; tail (device, 4 doubles): attempt index, r2 and x1 of the last accepted pair
+ * (an odd count leaves f * x1 cached in numpy's state: the caller finishes it with the host libm, so the
+ * state is bit-exact); ambiguous (device int): 1 when two keys of a column are closer than 1e-14
+ * relative, i.e. when the last place of log() could decide an argsort — the caller then repeats the draw
+ * with cna_host_perm_blocks.  Integer stream, acceptance tests and uniforms are exact; permutations are
+ * exact unless `ambiguous`.  workspace: cna_perm_draw_workspace(n, num, n_blocks) bytes.
+ * replaces: _stats.py:11-16 and :31 (`np.argsort(np.random.randn(rows, num), axis=0)`). */
+int64_t cna_perm_draw_workspace(int64_t n, int64_t num, int n_blocks);
+int cna_perm_draw_device(const uint32_t *key_host, int pos, int has_gauss, double gauss, int n_blocks,
+                         const int32_t *block_off_host, const int32_t *src_pos_host, int64_t num, int32_t *out,
+                         int64_t ld_out, uint32_t *state_out, double *tail, int *ambiguous, void *workspace,
+                         int64_t workspace_bytes, void *stream);
+
 /* Asynchronous form of cna_host_perm_blocks: the draw runs on a thread owned by the library and
  * every buffer (including the four state words) must stay alive until cna_host_perm_wait, which
  * joins the thread, frees the handle and returns the status.  cna_host_perm_done polls (1 = finished). */

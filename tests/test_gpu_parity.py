@@ -4,6 +4,7 @@ seeded inputs.  Integer / index outputs must be exact; floating-point outputs wi
 north-star tolerance of 1e-5 relative (the device state is fp32, the reference fp64).
 """
 import os
+import warnings
 
 import numpy as np
 import pandas as pd
@@ -679,3 +680,65 @@ def test_config_B_vs_oracle(cna):
         edge = np.abs(np.abs(np.nan_to_num(d_cpu.obs["coef"].to_numpy())) - thr) < 1e-5 * max(thr, 1e-3)
         assert ((a <= level) == (b <= level))[~edge].all()
         assert (b <= level).sum() > 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,nb,num,pre", [(200, 4, 2000, 0), (50, 1, 333, 1), (333, 7, 257, 0), (12, 12, 40, 3),
+                                          (201, 3, 1001, 0), (7, 1, 1, 0), (64, 2, 10000, 1)])
+def test_device_permutation_draw_is_bit_exact(cna, n, nb, num, pre):
+    """cna_perm_draw_device against the reference's numpy call sequence (_stats.py:8-16 and :20-32): the
+    same index matrices bit for bit and the same generator state left behind (key, position, cached
+    deviate), for even / odd deviate counts and a cached deviate pending on entry."""
+    import torch
+    from cna_b200.tl import _stats
+    rng = np.random.default_rng(n + nb)
+    B = rng.integers(0, nb, n)
+    B[:nb] = np.arange(nb)
+    y = rng.normal(size=n)
+    np.random.seed(n)
+    np.random.randn(pre)
+    want, after_w, state_w = _stats.conditional_permutation_indices(B, num), np.random.randn(5), np.random.get_state()
+    np.random.seed(n)
+    np.random.randn(pre)
+    draw = _stats.PermutationDraw(y, B, None, num, device=torch.device("cuda", 0), engine="device")
+    got_d = draw.result_device(torch.device("cuda", 0))
+    torch.cuda.synchronize()
+    got = draw.result()
+    after_g, state_g = np.random.randn(5), np.random.get_state()
+    assert got.dtype == np.int32 and got.shape == (num, n)
+    np.testing.assert_array_equal(got, want.T)
+    np.testing.assert_array_equal(got_d.cpu().numpy(), want.T)
+    np.testing.assert_array_equal(after_g, after_w)
+    np.testing.assert_array_equal(state_g[1], state_w[1])
+    assert state_g[2:] == state_w[2:]
+    # donor-level permutations (_stats.py:20-32)
+    G = np.arange(n) // 2
+    Y = (G % 3 == 0).astype(float)
+    np.random.seed(n + 1)
+    want, after_w = _stats.grouplevel_permutation_indices(G, Y, num), np.random.randn(3)
+    np.random.seed(n + 1)
+    draw = _stats.PermutationDraw(Y, None, G, num, device=torch.device("cuda", 0), engine="device")
+    got = draw.result_device(torch.device("cuda", 0)).cpu().numpy()
+    draw.cancel()
+    np.testing.assert_array_equal(got, want.T)
+    np.testing.assert_array_equal(np.random.randn(3), after_w)
+
+
+@pytest.mark.gpu
+def test_device_draw_and_host_draw_give_the_same_association(cna):
+    """The whole call with the device engine (default) and with the host engine: identical p, k, kept set
+    and per-cell columns, and the same generator state afterwards."""
+    spec = dict(y="case", covs=["male"], batches="batch", seed=3, Nnull=500, nsteps=3)
+    out = []
+    for host in (False, True):
+        d, kw = cases.build_demo_case(cases.load_demo_graph(), spec)
+        if host:
+            kw["_host_draw"] = True
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            p = cna.tl.association(d, **kw)
+        out.append((p, d.obs["coef"].to_numpy().copy(), d.obs["coef_fdr"].to_numpy().copy(), np.random.randn(3)))
+    assert out[0][0] == out[1][0]
+    np.testing.assert_array_equal(out[0][1], out[1][1])
+    np.testing.assert_array_equal(out[0][2], out[1][2])
+    np.testing.assert_array_equal(out[0][3], out[1][3])
