@@ -395,8 +395,20 @@ def run_ours(args):
             p_value = step_dev()
         prof = _lib.profile_stop()
         check = check_block(data.obs)
+        # standalone cna.tl.nam() (NAM + QC, _nam.py:179) on the resident graph; the samples x cells DataFrame it
+        # returns is 1.6 GB at config C and is copied to the host inside this number
+        nam_ms = None
+        if world == 1 and args.config in ("A", "B", "C"):
+            nam_call = lambda: cna.tl.nam(handle, "id", batches=meta.batch, nsteps=s_steps)  # noqa: E731
+            nam_call()
+            nam_ms = timed(nam_call, 3) / 3
         e2e = None
         if not args.no_e2e:
+            # the same call on the caller's own (pageable) scipy buffers: what a user gets without registering
+            # the CSR arrays as pinned memory first (fewer steps: the number is for the record, not the headline)
+            pg_steps = max(3, args.steps // 4)
+            step_e2e()
+            ms_pageable = timed(step_e2e, pg_steps) / pg_steps
             undo = pin_graph(A)
             for _ in range(min(args.warmup, 2)):
                 step_e2e()
@@ -407,7 +419,10 @@ def run_ours(args):
             h2d = host_graph_bytes + 4 * N * world  # summed over the ranks (each uploads its block of rows)
             d2h = 2 * 8 * N + 8 * n * n + 8 * K * 5
             e2e = {"value": N * args.steps / (ms_e2e * 1e-3), "unit": "cells/s", "ms_per_step": ms_e2e / args.steps,
-                   "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)}
+                   "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                   "input_memory": "scipy CSR buffers registered as pinned host memory (cudaHostRegister) outside the timed region",
+                   "pageable": {"value": N / (ms_pageable * 1e-3), "unit": "cells/s", "ms_per_step": ms_pageable,
+                                "steps": pg_steps, "input_memory": "the caller's pageable scipy CSR buffers as they are"}}
 
     if rank != 0:
         dist.destroy_process_group()
@@ -442,6 +457,7 @@ def run_ours(args):
                    "parallelism": f"cell-axis shards x{world}" if world > 1 else "single GPU",
                    "p_value": p_value, "datagen_s": round(gen_s, 1)},
         "clocks": clk.summary(), "e2e": e2e, "gpu_launches": launches / args.steps, "check": check,
+        "nam_standalone_ms": nam_ms,
         "roofline": primary, "rooflines": roofs,
     }
     if not args.no_cpu_baseline and world == 1 and args.config not in ("E", "T"):

@@ -757,9 +757,9 @@ def knn_bruteforce(points, k, queries=None):
     queries ``queries`` = (q0, q1) (default: all points)."""
     n, dim = points.shape
     q0, q1 = (0, n) if queries is None else queries
-    pad = next(d for d in (4, 8, 16, 32) if d >= dim) if dim <= 32 else None
+    pad = next(d for d in (4, 8, 16, 32, 64) if d >= dim) if dim <= 64 else None
     if pad is None:
-        raise CnaError("knn_bruteforce: at most 32 dimensions")
+        raise CnaError("knn_bruteforce: at most 64 dimensions")
     if pad != dim:
         points = torch.nn.functional.pad(points, (0, pad - dim))
     points = points.contiguous()

@@ -1,5 +1,5 @@
-// Exact brute-force kNN used only by the synthetic-data generator (cna_b200/synth.py) to build
-// benchmark-sized kNN graphs on the GPU box; it is not part of the timed path.  One thread per
+// Exact brute-force kNN behind cna_b200.pp.neighbors (the graph scanpy.pp.neighbors would build, read by the
+// reference at _nam.py:12-19) and the synthetic-data generator; it is not part of the timed path.  One thread per
 // query, candidate tiles broadcast from shared memory, a sorted top-k list per thread.
 #include "common.cuh"
 
@@ -76,7 +76,8 @@ extern "C" int cna_knn_bruteforce_range(const float *points, int64_t n, int dim,
         case 8: knn_kernel<8><<<grid, 128, 0, st>>>(points, n, k, q0, nq, idx, dist2); break;
         case 16: knn_kernel<16><<<grid, 128, 0, st>>>(points, n, k, q0, nq, idx, dist2); break;
         case 32: knn_kernel<32><<<grid, 128, 0, st>>>(points, n, k, q0, nq, idx, dist2); break;
-        default: return set_error(CNA_ERR_INVALID, "cna_knn_bruteforce: dim must be 4, 8, 16 or 32 (pad with zeros), got %d", dim);
+        case 64: knn_kernel<64><<<grid, 128, 0, st>>>(points, n, k, q0, nq, idx, dist2); break;
+        default: return set_error(CNA_ERR_INVALID, "cna_knn_bruteforce: dim must be 4, 8, 16, 32 or 64 (pad with zeros), got %d", dim);
     }
     CNA_LAUNCHED("knn_kernel");
     return CNA_OK;

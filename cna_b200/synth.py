@@ -64,48 +64,7 @@ def _knn_gpu(points, k, comm=None):
     return idx, d2.double().sqrt_()
 
 
-def fuzzy_simplicial_set(idx, dist, n_iter=64, rows=None):
-    """UMAP's smooth-kNN-distance weights, symmetrised by probabilistic t-conorm.
-
-    idx/dist: [N, k-1] neighbour indices / distances (self excluded), torch tensors (any device) or
-    numpy arrays.  Returns scipy CSR float64 with sorted indices; with ``rows`` = (r0, r1) only that
-    block of rows, as an (r1 - r0) x N matrix (what one rank of a sharded run ingests)."""
-    idx = torch.as_tensor(idx)
-    dist = torch.as_tensor(dist, dtype=torch.float64, device=idx.device)
-    idx = idx.long()
-    N, km1 = idx.shape
-    target = math.log2(km1 + 1)
-    rho = dist[:, :1]
-    gap = (dist - rho).clamp_(min=0)
-    lo = torch.zeros(N, 1, dtype=torch.float64, device=idx.device)
-    hi = torch.full((N, 1), float("inf"), dtype=torch.float64, device=idx.device)
-    mid = torch.ones(N, 1, dtype=torch.float64, device=idx.device)
-    for _ in range(n_iter):
-        psum = torch.exp(-gap / mid).sum(dim=1, keepdim=True)
-        too_big = psum > target
-        hi = torch.where(too_big, mid, hi)
-        lo = torch.where(too_big, lo, mid)
-        mid = torch.where(torch.isinf(hi), mid * 2, (lo + hi) / 2)
-    p = torch.exp(-gap / mid).reshape(-1)
-    i = torch.arange(N, device=idx.device).repeat_interleave(km1)
-    j = idx.reshape(-1)
-    key = torch.cat([i * N + j, j * N + i])
-    val = torch.cat([p, p])
-    key, order = torch.sort(key)
-    val = val[order]
-    ukey, inv = torch.unique_consecutive(key, return_inverse=True)
-    s1 = torch.zeros(len(ukey), dtype=torch.float64, device=idx.device).index_add_(0, inv, val)
-    s2 = torch.zeros(len(ukey), dtype=torch.float64, device=idx.device).index_add_(0, inv, val * val)
-    w = s1 - (s1 * s1 - s2) / 2  # p + q - p.q for mutual pairs, p otherwise
-    r0, r1 = (0, N) if rows is None else rows
-    if rows is not None:  # keys are sorted by row: the block is one slice
-        e0, e1 = torch.searchsorted(ukey, torch.tensor([r0 * N, r1 * N], device=ukey.device)).tolist()
-        ukey, w = ukey[e0:e1], w[e0:e1]
-    row = (ukey // N - r0).cpu().numpy()
-    cols = (ukey % N).cpu().numpy().astype(np.int32)
-    indptr = np.zeros(r1 - r0 + 1, dtype=np.int64)
-    np.cumsum(np.bincount(row, minlength=r1 - r0), out=indptr[1:])
-    return sp.csr_matrix((w.cpu().numpy(), cols, indptr.astype(np.int32)), shape=(r1 - r0, N))
+from .pp._neighbors import fuzzy_simplicial_set  # noqa: E402,F401  (the product implementation)
 
 
 def make_dataset(n_cells=10000, n_samples=50, k=15, dim=None, seed=0, n_clusters=12, n_batches=4,

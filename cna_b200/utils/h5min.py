@@ -18,8 +18,10 @@ _SIG = b"\x89HDF\r\n\x1a\n"
 
 class H5File:
     def __init__(self, path):
+        # memory-mapped: a row-block read of a multi-GB file touches only the pages it needs
+        import mmap
         with open(path, "rb") as fh:
-            self.buf = fh.read()
+            self.buf = mmap.mmap(fh.fileno(), 0, access=mmap.ACCESS_READ)
         if self.buf[:8] != _SIG:
             raise ValueError("not an HDF5 file")
         ver = self.buf[8]
@@ -56,7 +58,7 @@ class H5File:
             raise ValueError("bad local heap")
         data_addr = struct.unpack_from("<Q", self.buf, heap_addr + 24)[0]
         start = data_addr + off
-        stop = self.buf.index(b"\x00", start)
+        stop = self.buf.find(b"\x00", start)
         return self.buf[start:stop].decode()
 
     def _group_walk(self, tree, heap, out):
@@ -186,3 +188,39 @@ class H5File:
                 out[sel] = block[tuple(slice(0, s.stop - s.start) for s in sel)]
             return out
         raise NotImplementedError(f"layout class {cls}")
+
+    def dataset_info(self, path):
+        """(shape, dtype, file offset or None) of a dataset; the offset is set for contiguous layouts."""
+        hdr = self.resolve(path) if isinstance(path, str) else path
+        shape = dtype = offset = None
+        for mtype, body, _ in self._messages(hdr):
+            if mtype == 0x01:
+                ver, rank, flags = struct.unpack_from("<BBB", self.buf, body)
+                off = body + (8 if ver == 1 else 4)
+                shape = struct.unpack_from(f"<{rank}Q", self.buf, off) if rank else ()
+            elif mtype == 0x03:
+                dtype = self._dtype(self.buf, body)
+            elif mtype == 0x08:
+                ver, cls = struct.unpack_from("<BB", self.buf, body)
+                if ver == 3 and cls == 1:
+                    offset = struct.unpack_from("<Q", self.buf, body + 2)[0]
+            elif mtype == 0x0B:
+                raise NotImplementedError("filter pipeline (compressed dataset)")
+        if shape is None or dtype is None:
+            raise ValueError("not a dataset")
+        return shape, dtype, offset
+
+    def read_slice(self, path, start, stop, out=None):
+        """Elements [start, stop) of a 1-D dataset, straight out of the mapped file for contiguous layouts
+        (copied into ``out`` when given: e.g. a page-locked buffer)."""
+        shape, dtype, offset = self.dataset_info(path)
+        if len(shape) != 1:
+            raise ValueError("read_slice: 1-D datasets only")
+        if offset is None:  # chunked / compact: whole read, then slice
+            arr = self.read(path)[start:stop]
+        else:
+            arr = np.frombuffer(self.buf, dtype=dtype, count=stop - start, offset=offset + start * dtype.itemsize)
+        if out is None:
+            return np.array(arr)
+        out[...] = arr
+        return out

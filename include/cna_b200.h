@@ -413,11 +413,13 @@ int cna_host_perm_done(void *handle);
 int cna_host_perm_wait(void *handle);
 
 /* ------------------------------------------------------------------------------------------
- * utilities used by the data generator (not on the timed path)
+ * kNN graph construction (cna_b200.pp.neighbors and the data generator; not on the timed path)
  * ------------------------------------------------------------------------------------------ */
 
-/* Exact brute-force k nearest neighbours (self excluded) of fp32 points [n x dim], dim <= 32,
- * k <= 64.  idx [n x k] int32 ascending by distance, dist2 [n x k] squared distances. */
+/* Exact brute-force k nearest neighbours (self excluded) of fp32 points [n x dim], dim in {4, 8, 16, 32, 64}
+ * (pad with zeros), k <= 64: candidates stream through shared memory in tiles, nothing N x N is formed.
+ * idx [n x k] int32 ascending by distance, dist2 [n x k] squared distances.
+ * replaces: the kNN search of scanpy.pp.neighbors that produces the graph read at _nam.py:12-19. */
 int cna_knn_bruteforce(const float *points, int64_t n, int dim, int k, int32_t *idx, float *dist2,
                        void *stream);
 /* The same search for the queries [q0, q0 + nq) only (idx / dist2 are [nq x k]): lets the ranks of a

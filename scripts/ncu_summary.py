@@ -43,6 +43,9 @@ KEYS = [
 ]
 
 
+PREFIXES = ("sm__pipe_tensor", "sm__inst_executed_pipe_tensor", "sm__inst_executed_pipe_uniform", "smsp__pipe_tensor")
+
+
 def summarise(path):
     raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
@@ -55,6 +58,10 @@ def summarise(path):
             if key in d:
                 u, v = d[key]
                 out.append(f"   {label:42s} {v} {u}")
+        for key in sorted(d):  # every tensor-pipe counter the report holds (the names differ between ncu versions)
+            if key.startswith(PREFIXES) and key not in dict(KEYS):
+                u, v = d[key]
+                out.append(f"   {key:42s} {v} {u}")
     return "\n".join(out)
 
 

@@ -7,6 +7,7 @@ never copied).  Writes, next to this script:
 
   demo_graph.npz      the kNN graph + obs columns of the reference's bundled ``demo/data.h5ad``
                       (data fixture, read with cna_b200.utils.h5min — no h5py/anndata here)
+  demo_knn.npz        the kNN distances stored in the same file
   demo_cases.npz/json reference outputs for the demo analyses listed in SURVEY.md section 8(c)
   synth_cases.npz/json reference outputs on small synthetic inputs that exercise the edge cases
                       (ragged samples, NaN phenotype, extra / shuffled sample ids, donors, ...)
@@ -39,6 +40,12 @@ def export_demo_graph():
     for col in ("id", "case", "male", "batch"):
         out["obs_" + col] = f.read("obs/" + col)
     np.savez_compressed(os.path.join(HERE, "demo_graph.npz"), **out)
+    # the kNN distances scanpy stored next to the graph (14 per row): what the stored connectivities were built
+    # from — pins cna_b200.pp.fuzzy_simplicial_set
+    d = "uns/neighbors/distances/"
+    np.savez_compressed(os.path.join(HERE, "demo_knn.npz"), data=f.read(d + "data"),
+                        indices=f.read(d + "indices"), indptr=f.read(d + "indptr"),
+                        n_neighbors=f.read("uns/neighbors/params/n_neighbors"))
     return out
 
 
