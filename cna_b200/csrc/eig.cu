@@ -116,47 +116,51 @@ __global__ void __launch_bounds__(kThreads, 1) sym_eig_top_kernel(Args a) {
     extern __shared__ double sm[];
     const int n = a.n, k = a.k;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int HB = (n + 15) >> 4, NB = (n + 31) >> 5;  // 16-row half-blocks, 32-column blocks
+    // Storage is padded to np = the next multiple of 16 (zero rows / entries): every 16-row unit of the sweep is
+    // complete, and the padding stays exactly zero through every update.
+    const int np = (n + 15) & ~15;
+    const int HB = np >> 4, NB = (np + 31) >> 5;  // 16-row half-blocks, 32-column blocks
     // ---- shared-memory carve-up ----
-    double *v = sm;                 // [n] pending reflector
-    double *w = v + n;              // [n] pending update vector
-    double *vn = w + n;             // [n] reflector under construction (ping-pong with v)
-    double *raw = vn + n;           // [n] column j of the updated matrix, unscaled
-    double *e2 = raw + n;           // [n] squares of the scaled off-diagonal
-    double *dS = e2 + n;            // [n] diagonal of T
-    double *eS = dS + n;            // [n] off-diagonal of T (n - 1 used)
-    double *tauS = eS + n;          // [n]
-    double *redA = tauS + n;        // [kWarps]
+    double *v = sm;                 // [np] pending reflector
+    double *w = v + np;             // [np] pending update vector
+    double *vn = w + np;            // [np] reflector under construction (ping-pong with v)
+    double *raw = vn + np;          // [np] column j of the updated matrix, unscaled
+    double *e2 = raw + np;          // [np] squares of the scaled off-diagonal
+    double *dS = e2 + np;           // [np] diagonal of T
+    double *eS = dS + np;           // [np] off-diagonal of T (n - 1 used)
+    double *tauS = eS + np;         // [np]
+    double *redA = tauS + np;       // [kWarps]
     double *redB = redA + kWarps;   // [kWarps]
     double *lamS = redB + kWarps;   // [k] eigenvalues (ascending)
     double *loS = lamS + k;         // [k]
     double *hiS = loS + k;          // [k]
-    int *group = reinterpret_cast<int *>(hiS + k);   // [k <= 512] first member of the cluster of an eigenvalue
-    double *scratch = reinterpret_cast<double *>(group + 512);
-    double *rowpart = scratch;                       // [NB x n] row sums per column block
-    double *colpart = rowpart + size_t(NB) * n;      // [HB x n] column sums per half-block
-    double *A = SMEM ? colpart + size_t(HB) * n : a.packed;  // packed lower triangle, row-major
+    int *group = reinterpret_cast<int *>(hiS + k);   // [k] first member of the cluster of an eigenvalue
+    double *scratch = reinterpret_cast<double *>(group + ((k + 1) & ~1));
+    double *rowpart = scratch;                       // [NB x np] row sums per column block
+    double *colpart = rowpart + size_t(NB) * np;     // [HB x np] column sums per half-block
+    double *A = SMEM ? colpart + size_t(HB) * np : a.packed;  // packed lower triangle of the padded matrix, row-major
     double *red = redA;
 
     const long long clk0 = clock64();
     // ---- load (G + G^T) / 2 into the packed lower triangle ----
-    for (int i = warp; i < n; i += kWarps)
+    for (int i = warp; i < np; i += kWarps)
         for (int l = lane; l <= i; l += 32)
-            A[tri(i) + l] = 0.5 * (a.G[int64_t(i) * a.ldg + l] + a.G[int64_t(l) * a.ldg + i]);
+            A[tri(i) + l] = i < n ? 0.5 * (a.G[int64_t(i) * a.ldg + l] + a.G[int64_t(l) * a.ldg + i]) : 0.0;
+    for (int i = tid; i < 4 * np; i += kThreads) v[i] = 0.0;  // v, w, vn, raw
     __syncthreads();
 
     // ---- 1. Householder tridiagonalisation (LAPACK dsytd2 'L' arithmetic, update fused with the next product) ----
-    // Thread i owns element i of every vector (n <= kThreads), so only three barriers separate the phases
-    // of a step: column + norm | sweep | dot.  The pending reflector v has v[j] = 1 at its first index j and
-    // the matching w[j] is carried in a register by every thread (w_first).
+    // Thread i owns element i of every vector (np <= kThreads), so four barriers separate the phases of a
+    // step: column + norm | reflector | sweep | dot.  The pending reflector v has v[j] = 1 at its first index j
+    // and the matching w[j] is carried in a register by every thread (w_first).
     bool pending = false;
     double w_first = 0.0;
     for (int j = 0; j + 2 < n; ++j) {
         const int s = j + 1, hb0 = s >> 4, bl0 = s >> 5;
-        // column j with the pending update applied -> raw[j .. n-1]; sum of squares below the sub-diagonal
+        // column j with the pending update applied -> raw[j .. np-1]; sum of squares below the sub-diagonal
         {
             double sq = 0.0;
-            if (tid >= j && tid < n) {
+            if (tid >= j && tid < np) {
                 double x = A[tri(tid) + j];
                 if (pending) {
                     x = fma(-v[tid], w_first, x);
@@ -179,66 +183,85 @@ __global__ void __launch_bounds__(kThreads, 1) sym_eig_top_kernel(Args a) {
             scale = 1.0 / (alpha - beta);
         }
         double vn_own = 0.0;  // element tid of the new reflector
-        if (tid >= s && tid < n) {
+        if (tid >= s && tid < np) {
             vn_own = (tid == s) ? 1.0 : raw[tid] * scale;
             vn[tid] = vn_own;
-            a.refl[size_t(j) * n + tid] = vn_own;  // kept for the back-transformation
+            if (tid < n) a.refl[size_t(j) * n + tid] = vn_own;  // kept for the back-transformation
         }
         if (tid == 0) {
             dS[j] = diag;
             eS[j] = beta;
             tauS[j] = t;
         }
-        // fused sweep over the trailing block rows / columns s .. n-1 in 16 x 32 units: apply the pending
-        // rank-2 update, accumulate p = A22 . vn (row part per row, column part per lane).  The new reflector
-        // is rebuilt from raw[] and the scale on the fly, so no barrier is needed after writing vn[].
+        __syncthreads();
+        // fused sweep over the trailing block rows / columns s .. np-1 in 16 x 32 units: apply the pending
+        // rank-2 update, accumulate p = A22 . vn (row part per row, column part per lane)
         {
             int rem = warp;
             for (int hb = hb0; hb < HB; ++hb) {
                 const int cnt = min((16 * hb + 15) >> 5, NB - 1) - bl0 + 1;
                 for (; rem < cnt; rem += kWarps) {
                     const int bl = bl0 + rem, l = 32 * bl + lane, i0 = 16 * hb;
-                    const bool lin = l >= s && l < n;
+                    const bool lin = l >= s && l < np;
                     const double vl = (lin && pending) ? v[l] : 0.0, wl = (lin && pending) ? w[l] : 0.0;
-                    const double nl = lin ? (l == s ? 1.0 : raw[l] * scale) : 0.0;
-                    // row r of the unit is i0 + r; this lane owns the elements of rows r_ok <= r < r_hi
-                    // (on or below the diagonal, inside the trailing block) and adds to its column sum from r_c
-                    const int r_lo = max(0, s - i0), r_hi = min(16, n - i0);  // uniform
-                    const int r_ok = lin ? max(l - i0, r_lo) : 16, r_c = lin ? max(l - i0 + 1, r_lo) : 16;
+                    const double nl = lin ? vn[l] : 0.0;
                     double *Ap = A + tri(i0) + l;  // element (i0 + r, l) at Ap[r * i0 + r (r + 1) / 2]
                     double x[16];
-#pragma unroll
-                    for (int r = 0; r < 16; ++r)  // all loads of the unit first
-                        x[r] = (r >= r_ok && r < r_hi) ? Ap[r * i0 + r * (r + 1) / 2] : 0.0;
                     double c0 = 0.0, c1 = 0.0;
+                    if (i0 >= 32 * bl + 32 && i0 >= s) {
+                        // every row of the unit lies strictly below every column and inside the trailing block:
+                        // no per-element predicates (lanes left of column s carry vl = wl = nl = 0: their stale
+                        // entries pass through unchanged and their sums are not stored)
 #pragma unroll
-                    for (int r = 0; r < 16; ++r) {
-                        if (r >= r_lo && r < r_hi) {  // uniform over the warp
+                        for (int r = 0; r < 16; ++r) x[r] = Ap[r * i0 + r * (r + 1) / 2];
+#pragma unroll
+                        for (int r = 0; r < 16; ++r) {
+                            const int i = i0 + r;
+                            if (pending) {
+                                x[r] = fma(-v[i], wl, x[r]);
+                                x[r] = fma(-w[i], vl, x[r]);
+                            }
+                            if (r & 1) c1 = fma(x[r], vn[i], c1);
+                            else c0 = fma(x[r], vn[i], c0);
+                        }
+                        if (pending) {
+#pragma unroll
+                            for (int r = 0; r < 16; ++r) Ap[r * i0 + r * (r + 1) / 2] = x[r];
+                        }
+                    } else {
+                        // a unit on the diagonal or on the upper edge of the trailing block: this lane owns the
+                        // elements of rows r >= r_ok (on or below the diagonal, inside the block) and adds to its
+                        // column sum from r_c
+                        const int r_lo = max(0, s - i0);  // uniform
+                        const int r_ok = lin ? max(l - i0, r_lo) : 16, r_c = lin ? max(l - i0 + 1, r_lo) : 16;
+#pragma unroll
+                        for (int r = 0; r < 16; ++r) x[r] = (r >= r_ok) ? Ap[r * i0 + r * (r + 1) / 2] : 0.0;
+#pragma unroll
+                        for (int r = 0; r < 16; ++r) {
                             const int i = i0 + r;
                             if (pending) {
                                 double y = fma(-v[i], wl, x[r]);
                                 y = fma(-w[i], vl, y);
                                 x[r] = (r >= r_ok) ? y : 0.0;
                             }
-                            const double ni = (i == s) ? 1.0 : raw[i] * scale;
                             const double xc = (r >= r_c) ? x[r] : 0.0;
-                            if (r & 1) c1 = fma(xc, ni, c1);
-                            else c0 = fma(xc, ni, c0);
+                            if (r & 1) c1 = fma(xc, vn[i], c1);
+                            else c0 = fma(xc, vn[i], c0);
                         }
-                    }
-                    if (pending) {
+                        if (pending) {
 #pragma unroll
-                        for (int r = 0; r < 16; ++r)
-                            if (r >= r_ok && r < r_hi) Ap[r * i0 + r * (r + 1) / 2] = x[r];
+                            for (int r = 0; r < 16; ++r)
+                                if (r >= r_ok) Ap[r * i0 + r * (r + 1) / 2] = x[r];
+                        }
                     }
 #pragma unroll
                     for (int r = 0; r < 16; ++r) x[r] *= nl;
                     bfly16(x, lane);
                     if (!(lane & 1)) {
-                        const int r = lane >> 1;
-                        if (r >= r_lo && r < r_hi) rowpart[bl * n + i0 + r] = x[0];
+                        const int i = i0 + (lane >> 1);
+                        if (i >= s) rowpart[bl * np + i] = x[0];
                     }
-                    if (lin) colpart[hb * n + l] = c0 + c1;
+                    if (lin) colpart[hb * np + l] = c0 + c1;
                 }
                 rem -= cnt;
             }
@@ -250,20 +273,20 @@ __global__ void __launch_bounds__(kThreads, 1) sym_eig_top_kernel(Args a) {
             const int l = (tid >= s && tid < n) ? tid : s;  // idle threads shadow the first entry
             double q0 = 0.0, q1 = 0.0, f0 = 0.0, f1 = 0.0;
             const int blmax = l >> 5;
-            for (int bl = bl0; bl <= blmax; ++bl) q0 += rowpart[bl * n + l];
-            f0 = rowpart[bl0 * n + s];
+            for (int bl = bl0; bl <= blmax; ++bl) q0 += rowpart[bl * np + l];
+            f0 = rowpart[bl0 * np + s];
             int hb = max(hb0, 2 * blmax);
             for (; hb + 1 < HB; hb += 2) {
-                q0 += colpart[hb * n + l];
-                q1 += colpart[(hb + 1) * n + l];
+                q0 += colpart[hb * np + l];
+                q1 += colpart[(hb + 1) * np + l];
             }
-            if (hb < HB) q0 += colpart[hb * n + l];
+            if (hb < HB) q0 += colpart[hb * np + l];
             hb = max(hb0, 2 * bl0);
             for (; hb + 1 < HB; hb += 2) {
-                f0 += colpart[hb * n + s];
-                f1 += colpart[(hb + 1) * n + s];
+                f0 += colpart[hb * np + s];
+                f1 += colpart[(hb + 1) * np + s];
             }
-            if (hb < HB) f0 += colpart[hb * n + s];
+            if (hb < HB) f0 += colpart[hb * np + s];
             p_own = (q0 + q1) * t;
             p_first = (f0 + f1) * t;
             double dot = (tid >= s && tid < n) ? p_own * vn_own : 0.0;
@@ -525,12 +548,12 @@ struct Layout {
     size_t matrix;    // packed lower triangle
 };
 static Layout layout(int n, int k) {
-    const int HB = (n + 15) / 16, NB = (n + 31) / 32;
+    const int np = (n + 15) & ~15, HB = np / 16, NB = (np + 31) / 32;
     Layout L;
-    L.fixed = sizeof(double) * (size_t(8) * n + 2 * kWarps + size_t(3) * k) + sizeof(int) * 512;
-    L.partial = sizeof(double) * size_t(HB + NB) * n;
+    L.fixed = sizeof(double) * (size_t(8) * np + 2 * kWarps + size_t(3) * k) + sizeof(int) * size_t((k + 1) & ~1);
+    L.partial = sizeof(double) * size_t(HB + NB) * np;
     if (L.partial < sizeof(int) * kThreads) L.partial = sizeof(int) * kThreads;  // the Sturm-count table lives there too
-    L.matrix = sizeof(double) * size_t(n) * (n + 1) / 2;
+    L.matrix = sizeof(double) * size_t(np) * (np + 1) / 2;
     return L;
 }
 
@@ -541,7 +564,8 @@ using namespace cna;
 
 extern "C" int64_t cna_sym_eig_workspace(int n, int k) {
     if (n < 1 || k < 1) return 0;
-    return int64_t(sizeof(double)) * (int64_t(n) * (n + 1) / 2 + int64_t(n) * n + int64_t(eig::kInvitArrays) * n * k);
+    const int64_t np = (n + 15) & ~15;
+    return int64_t(sizeof(double)) * (np * (np + 1) / 2 + int64_t(n) * n + int64_t(eig::kInvitArrays) * n * k);
 }
 
 extern "C" int cna_sym_eig_top(const double *G, int64_t ldg, int n, int k, double *w_out, double *ut_out,
@@ -556,7 +580,8 @@ extern "C" int cna_sym_eig_top(const double *G, int64_t ldg, int n, int k, doubl
     a.n = n;
     a.k = k;
     a.packed = static_cast<double *>(workspace);
-    a.refl = a.packed + size_t(n) * (n + 1) / 2;
+    const size_t np = size_t((n + 15) & ~15);
+    a.refl = a.packed + np * (np + 1) / 2;
     a.work = a.refl + size_t(n) * n;
     a.w_out = w_out;
     a.ut_out = ut_out;
