@@ -523,10 +523,8 @@ def association(data, y, sid_name, batches=None, covs=None, donorids=None, ks=No
         mark("diffusion launched")
         return st
 
-    # (on a cell-axis shard the device work is a fraction of the call and the draw is its critical path:
-    # there the draw goes first as well)
     resident = isinstance(getattr(data, "graph", None), _graph.DeviceGraph)
-    stn = launch_nam() if (resident and getattr(data, "comm", None) is None) else None
+    stn = launch_nam() if resident else None
     batches, filter_samples = check_inputs(data, y, sid_name, batches, covs, donorids,
                                            allow_low_sample_size, present=codes[0])
     mark("check_inputs done")

@@ -742,3 +742,61 @@ def test_device_draw_and_host_draw_give_the_same_association(cna):
     np.testing.assert_array_equal(out[0][1], out[1][1])
     np.testing.assert_array_equal(out[0][2], out[1][2])
     np.testing.assert_array_equal(out[0][3], out[1][3])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,r,kmax,K", [(700, 5, 56, 300), (1000, 3, 80, 200), (64, 0, 12, 500)])
+def test_perm_stats_many_samples_streams_the_pcs(cna, n, r, kmax, K):
+    """cna_perm_stats beyond the shared-memory staging limit (kmax * n doubles > 200 KB from n ~ 570 with
+    the default ks): the PC matrix is then read where it lies.  Against the reference's arithmetic
+    (_association.py:35-52) in numpy."""
+    import torch
+    from cna_b200 import _lib
+    rng = np.random.default_rng(n)
+    y = rng.normal(size=n)
+    perm = np.stack([rng.permutation(n) for _ in range(K)]).astype(np.int32)
+    U, _ = np.linalg.qr(rng.normal(size=(n, kmax)))
+    ks = np.unique(np.linspace(max(1, kmax // 4), kmax, 4).astype(np.int32))
+    if r:
+        C = rng.normal(size=(n, r))
+        C -= C.mean(axis=0)
+        W = np.linalg.solve(C.T @ C + 1e-3 * np.eye(r), C.T)
+        M = np.eye(n) - C @ W
+    else:
+        C = W = None
+        M = np.eye(n)
+    td = lambda a, dt=torch.float64: torch.as_tensor(np.ascontiguousarray(a), device="cuda", dtype=dt)  # noqa: E731
+    ssered = torch.empty(K, dtype=torch.float64, device="cuda")
+    ssefull = torch.full((K, len(ks)), float("nan"), dtype=torch.float64, device="cuda")
+    _lib.perm_stats(td(y), td(perm, torch.int32), td(C) if r else None, td(W) if r else None, td(U.T),
+                    td(ks, torch.int32), ssered, ssefull, None, 0)
+    z = M @ y[perm].T                      # n x K
+    z = z / z.std(axis=0, ddof=1)
+    want_red = (z * z).sum(axis=0)
+    want_full = np.stack([((z - U[:, :k] @ (U[:, :k].T @ z)) ** 2).sum(axis=0) for k in ks], axis=1)
+    np.testing.assert_allclose(ssered.cpu().numpy(), want_red, rtol=1e-12)
+    np.testing.assert_allclose(ssefull.cpu().numpy(), want_full, rtol=1e-9)
+
+
+@pytest.mark.gpu
+def test_ks_in_any_order_and_with_duplicates(cna):
+    """The reference accepts ks in any order (_association.py:25-61 loops over them as given); the device
+    kernels want them ascending and distinct, so the host sorts, de-duplicates and maps back: same p, k and
+    per-k statistics as the sorted call, and as the oracle."""
+    from oracle import cna_oracle as orc
+    spec = dict(y="case", covs=["male"], batches="batch", seed=2, Nnull=200, nsteps=3)
+    out = {}
+    for name, ks in (("sorted", [2, 4, 6, 8]), ("shuffled", [6, 2, 8, 4, 4, 2])):
+        d, kw = cases.build_demo_case(cases.load_demo_graph(), dict(spec, ks=ks))
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            out[name] = (cna.tl.association(d, return_full=True, **kw), d.obs["coef_fdr"].to_numpy().copy())
+    a, b = out["sorted"], out["shuffled"]
+    assert a[0].p == b[0].p and int(a[0].k) == int(b[0].k)
+    np.testing.assert_array_equal(a[0].nullminps, b[0].nullminps)
+    np.testing.assert_array_equal(a[1], b[1])
+    d, kw = cases.build_demo_case(cases.load_demo_graph(), dict(spec, ks=[6, 2, 8, 4, 4, 2]))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        want = orc.association(d, return_full=True, **kw)
+    assert b[0].p == want.p and int(b[0].k) == int(want.k)
