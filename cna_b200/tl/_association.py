@@ -95,7 +95,7 @@ class _Readback:
             self.views.append(host)
             off += size
         self.event = torch.cuda.Event()
-        self.event.record()
+        self.event.record(_lib.current_stream_object())
 
     def get(self):
         self.event.synchronize()
@@ -128,14 +128,14 @@ def _to_host_owned(t, stream=None):
     """Device tensor -> page-locked host tensor of its own, copied on ``stream`` (after everything
     queued so far on the current stream).  Returns (host tensor, event)."""
     buf = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
-    cur = torch.cuda.current_stream()
+    cur = _lib.current_stream_object()
     stream = stream or cur
     if stream is not cur:
         stream.wait_stream(cur)
     with torch.cuda.stream(stream):
         buf.copy_(t, non_blocking=True)
         ev = torch.cuda.Event()
-        ev.record()
+        ev.record(stream)
     t.record_stream(stream)
     return buf, ev
 
@@ -297,7 +297,7 @@ def _association(res, perms, Nnull=1000, local_test=True, show_progress=False, c
             w_d = torch.empty(res.svd_top, dtype=torch.float64, device=dev)
             ut_d = torch.empty((res.svd_top, n), dtype=torch.float64, device=dev)
             gram_done = torch.cuda.Event()
-            gram_done.record()
+            gram_done.record(_lib.current_stream_object())
             side = _side_stream(dev, "eig")
             with torch.cuda.stream(side):
                 side.wait_event(gram_done)
@@ -470,7 +470,7 @@ def _association(res, perms, Nnull=1000, local_test=True, show_progress=False, c
             b = phase_b(tabs, True)
         perm_d, C_d, W_d, back_b = b
         # the PC regressions are queued behind the null GEMM and wait (on the device) for the eigenvectors
-        torch.cuda.current_stream().wait_event(eig[2].event)
+        _lib.current_stream_object().wait_event(eig[2].event)
         sse_d = launch_pc_regressions(None, perm_d, C_d, W_d, eig)
         w_h, ut_h = eig[2].get()
         mark("eigenpairs on host")

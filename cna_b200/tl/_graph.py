@@ -27,17 +27,28 @@ def get_connectivity(data):
     raise KeyError("no kNN graph found: expected data.obsp['connectivities']")
 
 
+_HAVE_CUDA = None
+
+
 def device():
-    if not torch.cuda.is_available():
+    global _HAVE_CUDA
+    if _HAVE_CUDA is None:
+        _HAVE_CUDA = bool(torch.cuda.is_available())
+        if _HAVE_CUDA:
+            torch.cuda.init()
+    if not _HAVE_CUDA:
         raise RuntimeError("cna_b200 needs a CUDA device (B200, sm_100a); there is no CPU path")
-    return torch.device("cuda", torch.cuda.current_device())
+    return torch.device("cuda", torch._C._cuda_getDevice())
 
 
 def _to_dev(arr, dtype=None):
     arr = np.ascontiguousarray(arr)
-    with warnings.catch_warnings():  # read-only numpy views (pandas CoW, mmap) are only read from
-        warnings.simplefilter("ignore", UserWarning)
+    if arr.flags.writeable:
         t = torch.from_numpy(arr)
+    else:
+        with warnings.catch_warnings():  # read-only numpy views (pandas CoW, mmap) are only read from
+            warnings.simplefilter("ignore", UserWarning)
+            t = torch.from_numpy(arr)
     if dtype is not None and t.dtype != dtype:
         t = t.to(dtype)
     return t.to(device(), non_blocking=True)
@@ -257,7 +268,13 @@ class DeviceGraph:
         """Fill the halo rows ``ext[rows_per:]`` of a [rows_per + n_halo, ld] state with the current
         values of their owners' rows (``ext[:rows_per]`` on the owning ranks)."""
         comm, rows_per = self.comm, self.rows_per
-        send = ext[:rows_per].index_select(0, self.send_idx)
+        # a persistent send buffer per state width: a fresh 10-200 MB tensor per step would be recorded on
+        # NCCL's stream and could not be recycled by the allocator until the collective has run
+        buf = getattr(self, "_send_buf", None)
+        if buf is None or buf.shape != (self.send_idx.numel(), ext.shape[1]) or buf.dtype != ext.dtype:
+            buf = self._send_buf = torch.empty((self.send_idx.numel(), ext.shape[1]), dtype=ext.dtype,
+                                               device=ext.device)
+        send = torch.index_select(ext[:rows_per], 0, self.send_idx, out=buf)
         recv = ext[rows_per:]
 
         def via_all_gather():  # backends without all_to_all (gloo in the tests)

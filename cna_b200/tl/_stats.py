@@ -63,11 +63,17 @@ class RedoWithHostDraw(Exception):
     stream: the call is repeated with the host engine.  numpy's generator is back in its prior state."""
 
 
-def _device_draw_enabled():
-    import os
+_DEVICE_DRAW = None
 
-    import torch
-    return torch.cuda.is_available() and not os.environ.get("CNA_B200_HOST_DRAW")
+
+def _device_draw_enabled():
+    global _DEVICE_DRAW
+    if _DEVICE_DRAW is None:
+        import os
+
+        import torch
+        _DEVICE_DRAW = bool(torch.cuda.is_available()) and not os.environ.get("CNA_B200_HOST_DRAW")
+    return _DEVICE_DRAW
 
 
 class PermutationDraw:

@@ -24,10 +24,15 @@ for _ in range(2):
     cna.tl.association(h, **kw)
 torch.cuda.synchronize()
 pr = cProfile.Profile()
-pr.enable()
-cna.tl.association(h, **kw)
-torch.cuda.synchronize()
-pr.disable()
+reps = 20
+for _ in range(reps):
+    torch.cuda.synchronize()
+    pr.enable()
+    cna.tl.association(h, **kw)
+    pr.disable()
 out = io.StringIO()
-pstats.Stats(pr, stream=out).sort_stats("cumulative").print_stats(45)
+st = pstats.Stats(pr, stream=out)
+print(f"{reps} calls profiled; divide by {reps}")
+st.sort_stats("cumulative").print_stats(60)
+st.sort_stats("tottime").print_stats(45)
 print(out.getvalue())
