@@ -42,6 +42,7 @@ CONFIGS = {
     "C": (1_000_000, 200, 30, 3, 10_000),
     "E": (10_000_000, 500, 30, 4, 10_000),
     "T": (200_000, 60, 15, 4, 500),  # smoke test of the row-block (config E) path at a size that takes seconds
+    "E1": (1_250_000, 500, 30, 4, 10_000),  # one rank's share of config E on one GPU (its own graph: no halo)
 }
 METRIC = "cells/sec through nam()+association(), 1M cells/200 samples/10k perms"
 # CPU sample: same samples / k / steps, cells and permutations scaled down by the same factor

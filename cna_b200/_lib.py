@@ -110,7 +110,8 @@ _SIGNATURES = {
 EXPORTS = sorted(list(_SIGNATURES) + ["cna_abi_version", "cna_last_error", "cna_launch_count",
                                       "cna_gram_tc_workspace", "cna_host_perm_blocks_async",
                                       "cna_median_workspace", "cna_sym_eig_workspace", "cna_tc_max_ctas",
-                                      "cna_perm_draw_workspace", "cna_perm_draw_device"])
+                                      "cna_perm_draw_workspace", "cna_perm_draw_device", "cna_host_upload",
+                                      "cna_host_upload_async", "cna_host_upload_wait"])
 
 
 
@@ -130,6 +131,12 @@ def _declare(lib):
     lib.cna_perm_draw_device.restype = ctypes.c_int
     lib.cna_perm_draw_device.argtypes = [_VP, _INT, _INT, _DBL, _INT, _VP, _VP, _I64, _VP, _I64, _VP, _VP, _VP,
                                          _VP, _I64, _VP]
+    lib.cna_host_upload.restype = ctypes.c_int
+    lib.cna_host_upload.argtypes = [_VP, _VP, _I64, _VP, _INT]
+    lib.cna_host_upload_async.restype = ctypes.c_void_p
+    lib.cna_host_upload_async.argtypes = [_VP, _VP, _I64, _VP, _INT]
+    lib.cna_host_upload_wait.restype = ctypes.c_int
+    lib.cna_host_upload_wait.argtypes = [_VP]
     lib.cna_tc_max_ctas.restype = ctypes.c_int
     lib.cna_tc_max_ctas.argtypes = [ctypes.c_int]
     lib.cna_sym_eig_workspace.restype = ctypes.c_int64
@@ -667,6 +674,42 @@ class HostPermJob:
             if getattr(self, "handle", None) is not None:
                 self.result()
         except Exception:
+            pass
+
+
+class HostUpload:
+    """A numpy array on its way to the device through ``cna_host_upload`` (staged by a few host threads when
+    the buffer is pageable).  ``background=True`` runs the upload on a library thread: the array must stay
+    untouched until ``wait()``; the destination tensor may be queued on right away (the copies are ordered
+    on the stream the upload was started on — callers on other streams wait for ``wait()`` first)."""
+
+    def __init__(self, arr, device, background=False, n_threads=0):
+        import numpy as np
+        self.arr = np.ascontiguousarray(arr)
+        self.tensor = torch.empty(self.arr.shape, dtype=getattr(torch, self.arr.dtype.name), device=device)
+        self.handle = None
+        args = (self.tensor.data_ptr(), self.arr.ctypes.data, self.arr.nbytes, _stream(), int(n_threads))
+        if background:
+            self.handle = load().cna_host_upload_async(*args)
+            if not self.handle:
+                raise CnaError(f"cna_host_upload_async failed: {load().cna_last_error().decode()}")
+        else:
+            rc = load().cna_host_upload(*args)
+            if rc != 0:
+                raise CnaError(f"cna_host_upload failed ({rc}): {load().cna_last_error().decode()}")
+
+    def wait(self):
+        if self.handle is not None:
+            rc = load().cna_host_upload_wait(self.handle)
+            self.handle = None
+            if rc != 0:
+                raise CnaError(f"cna_host_upload failed ({rc}): {load().cna_last_error().decode()}")
+        return self.tensor
+
+    def __del__(self):
+        try:
+            self.wait()
+        except Exception:  # noqa: BLE001
             pass
 
 

@@ -292,7 +292,7 @@ def _association(res, perms, Nnull=1000, local_test=True, show_progress=False, c
         # the leading max(ks) eigenpairs of the Gram follow on the device (one launch); only the full result
         # surface (and n > 512) decomposes the Gram with LAPACK on the host
         eig = None
-        if res.svd_top is not None and res.svd_top < n <= _nam.DEVICE_EIG_MAX_N:
+        if res.svd_top is not None and res.svd_top < n <= _nam.DEVICE_EIG_MAX_N and res.svd_top <= 64:
             # one CTA, ~1 ms: on a side stream, beside the null GEMM (which leaves it an SM, phase B)
             w_d = torch.empty(res.svd_top, dtype=torch.float64, device=dev)
             ut_d = torch.empty((res.svd_top, n), dtype=torch.float64, device=dev)

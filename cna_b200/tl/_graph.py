@@ -178,14 +178,20 @@ class DeviceGraph:
             # same cell order and cut its shard of the reordered graph.
             indptr, indices, data = self._gather_blocks(A, data, shard[0])
             main = side = torch.cuda.current_stream() if indptr.is_cuda else None
+            pending_data = None
         else:
             indptr = _to_dev(A.indptr, torch.int32)
-            indices = _to_dev(A.indices, torch.int32)
+            dev = indptr.device
+            big = A.indices.dtype == np.int32 and A.indices.nbytes >= (8 << 20)
+            # column indices: staged through the library's page-locked ring when the buffer is pageable
+            # (several host threads, 4 MB chunks: PCIe speed instead of the driver's single-threaded staging)
+            indices = _lib.HostUpload(A.indices, dev).wait() if big else _to_dev(A.indices, torch.int32)
             # the edge weights (2/3 of the bytes) are not needed by the ordering: they travel on a side
-            # stream while the breadth-first sweeps run (truly asynchronous when the host buffer is pinned)
-            main, side = torch.cuda.current_stream(), _upload_stream(indptr.device)
+            # stream, staged by a library thread, while the breadth-first sweeps run
+            main, side = torch.cuda.current_stream(), _upload_stream(dev)
             with torch.cuda.stream(side):
-                data = _to_dev(data)
+                pending_data = _lib.HostUpload(data, dev, background=True) if big else None
+                data = pending_data.tensor if big else _to_dev(data)
             data.record_stream(main)
         self.order = self.inv = None
         mark("graph: indices queued for upload")
@@ -198,10 +204,15 @@ class DeviceGraph:
                 new_indptr = torch.zeros(self.n_total + 1, dtype=torch.int32, device=indptr.device)
                 new_indptr[1:] = torch.cumsum(deg, 0)
                 new_indices, new_data = torch.empty_like(indices), torch.empty_like(data)
+                if pending_data is not None:
+                    pending_data.wait()  # every chunk of the edge weights is queued on the side stream
+                    pending_data = None
                 if main is not side:
                     main.wait_stream(side)
                 _lib.permute_csr(indptr, indices, data, self.order, self.inv, new_indptr, new_indices, new_data)
                 indptr, indices, data = new_indptr, new_indices, new_data
+        if pending_data is not None:
+            pending_data.wait()
         if main is not side:
             main.wait_stream(side)
         self.halo_ids = None

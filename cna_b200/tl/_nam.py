@@ -360,7 +360,12 @@ def planes_of(x, n):
     return _lib.split_f16(x, n)
 
 
-DEVICE_EIG_MAX_N = 512  # cna_sym_eig_top's limit; CNA_B200_HOST_EIG=1 forces the LAPACK route (cross-check)
+# cna_sym_eig_top is used while the packed Gram fits in one SM's shared memory (n <= 208: 1.2 ms at n = 200
+# against 2.1 ms + two PCIe hops for LAPACK); above that its matrix lives in L2 and LAPACK dsyevr with a few
+# BLAS threads wins (n = 500: 22 ms on the device, ~13 ms on the host; measured on config E's per-rank
+# share, 49.9 against 41.4 ms per call).  CNA_B200_HOST_EIG=1 forces the LAPACK route (cross-check),
+# CNA_B200_DEVICE_EIG_MAX_N overrides the limit (the kernel itself takes n <= 512).
+DEVICE_EIG_MAX_N = int(os.environ.get("CNA_B200_DEVICE_EIG_MAX_N", "208"))
 if os.environ.get("CNA_B200_HOST_EIG"):
     DEVICE_EIG_MAX_N = 0
 
@@ -384,15 +389,18 @@ _BLAS = None
 
 
 def _single_threaded_blas():
-    """Context manager pinning the BLAS/LAPACK thread pool to one thread.  The n x n decomposition is
-    a few ms of work on one core; with OpenBLAS's default (one spinning thread per core) it collapses
-    to 10x that when the permutation draw is using the same cores."""
+    """Context manager capping the BLAS/LAPACK thread pool for the n x n decomposition on the host (the
+    full-result surface and n > DEVICE_EIG_MAX_N): a few ms of work; with OpenBLAS's default (one spinning
+    thread per core) it collapses to 10x that when something else is using the same cores.  One thread
+    while the host permutation engine may be running, ``CNA_B200_BLAS_THREADS`` (default 4) otherwise."""
     global _BLAS
     try:
         if _BLAS is None:
             from threadpoolctl import ThreadpoolController
             _BLAS = ThreadpoolController()
-        return _BLAS.limit(limits=1, user_api="blas")
+        from . import _stats
+        limit = int(os.environ.get("CNA_B200_BLAS_THREADS", "4")) if _stats._device_draw_enabled() else 1
+        return _BLAS.limit(limits=max(1, limit), user_api="blas")
     except Exception:  # threadpoolctl missing: run with whatever the BLAS does by default
         import contextlib
         return contextlib.nullcontext()

@@ -413,6 +413,21 @@ int cna_host_perm_done(void *handle);
 int cna_host_perm_wait(void *handle);
 
 /* ------------------------------------------------------------------------------------------
+ * host -> device upload of pageable buffers (upload_host.cpp)
+ * ------------------------------------------------------------------------------------------ */
+
+/* dst (device) <- src (host), `bytes` bytes, ordered on `stream`.  Page-locked sources take one
+ * cudaMemcpyAsync; pageable sources are staged by `n_threads` (<= 0: 4) host threads through a ring of
+ * page-locked 4 MB slots owned by the library, one asynchronous copy per chunk, so that staging and DMA
+ * overlap (a pageable cudaMemcpyAsync stages on one thread at ~10 GB/s).  Returns once the last chunk
+ * has left `src` (the semantics of a pageable cudaMemcpyAsync).  The _async form runs on a thread of its
+ * own: `src` must stay untouched until cna_host_upload_wait, which joins it and returns the status.
+ * replaces: nothing in the reference (it never leaves the host); serves the graph read at _nam.py:12-19. */
+int cna_host_upload(void *dst, const void *src, int64_t bytes, void *stream, int n_threads);
+void *cna_host_upload_async(void *dst, const void *src, int64_t bytes, void *stream, int n_threads);
+int cna_host_upload_wait(void *handle);
+
+/* ------------------------------------------------------------------------------------------
  * kNN graph construction (cna_b200.pp.neighbors and the data generator; not on the timed path)
  * ------------------------------------------------------------------------------------------ */
 
