@@ -800,3 +800,27 @@ def test_ks_in_any_order_and_with_duplicates(cna):
         warnings.simplefilter("ignore")
         want = orc.association(d, return_full=True, **kw)
     assert b[0].p == want.p and int(b[0].k) == int(want.k)
+
+
+@pytest.mark.gpu
+def test_staged_host_upload_round_trips(cna):
+    """cna_host_upload: pageable buffers staged through the library's page-locked ring (several threads, 4 MB
+    chunks, a ring smaller than the buffer so that slots are recycled), page-locked buffers in one copy, the
+    background form, odd sizes — the device copy equals the source bit for bit."""
+    import torch
+    from cna_b200 import _lib
+    rng = np.random.default_rng(0)
+    for n, dtype in ((30_000_001, np.float64), (5_000_003, np.int32), (17, np.float64), (1 << 20, np.int32)):
+        a = rng.integers(-2 ** 31, 2 ** 31 - 1, n).astype(dtype) if dtype == np.int32 else rng.normal(size=n)
+        up = _lib.HostUpload(a, torch.device("cuda", 0))
+        torch.cuda.synchronize()
+        np.testing.assert_array_equal(up.wait().cpu().numpy(), a)
+        bg = _lib.HostUpload(a, torch.device("cuda", 0), background=True, n_threads=3)
+        t = bg.wait()
+        torch.cuda.synchronize()
+        np.testing.assert_array_equal(t.cpu().numpy(), a)
+    pinned = torch.empty(3_000_000, dtype=torch.float64, pin_memory=True)
+    pinned.copy_(torch.as_tensor(rng.normal(size=3_000_000)))
+    up = _lib.HostUpload(pinned.numpy(), torch.device("cuda", 0))
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(up.wait().cpu().numpy(), pinned.numpy())
