@@ -542,7 +542,8 @@ def association(data, y, sid_name, batches=None, covs=None, donorids=None, ks=No
     y_std = (y_f - y_f.mean()) / y_f.std()  # :22 (ndarray -> ddof=0)
     npcs = min(n, max([10] + [int(max_frac_pcs * n)] + [ks if ks is not None else []][0]))  # :207
     ks_eff = default_ks(n) if ks is None else ks
-    r = _nam.design_matrix(covs_f, batches_f, n)[0].shape[1]
+    design = _nam.design_matrix(covs_f, batches_f, n)
+    r = design[0].shape[1]
 
     if kwargs.get("seed") is not None:
         np.random.seed(kwargs["seed"])  # :15-16
@@ -571,7 +572,8 @@ def association(data, y, sid_name, batches=None, covs=None, donorids=None, ks=No
         _nam._qc_device(stn, batches, show_progress=show_progress)
         colmap = stn.labels.get_indexer(sids)  # NAM.reindex(y.index)[filter_samples], :178-181
         res = _nam.resid_nam_device(stn, colmap, covs_f, batches_f, y_std, ridges=ridges,
-                                    show_progress=show_progress, want_x=return_full, speculate=True)
+                                    show_progress=show_progress, want_x=return_full, speculate=True,
+                                    design=design)
         mark("resid pass launched")
         res.y_std = y_std
         res.ks = ks_eff

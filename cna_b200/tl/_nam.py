@@ -159,19 +159,43 @@ def _r2_p20(s, old, S):
     return np.percentile(r2, 20)
 
 
+_QC_PLANS = {}
+
+
+def _series_key(ser):
+    """Content key of a small pandas Series (values and index)."""
+    v, ix = ser.to_numpy(), ser.index.to_numpy()
+    return (v.tobytes() if v.dtype != object else tuple(v.tolist()), str(v.dtype),
+            ix.tobytes() if ix.dtype != object else tuple(ix.tolist()), str(ix.dtype))
+
+
 def _qc_plan(batches, labels, ld, dev):
     """Device tables for the QC statistic fused into the last diffusion step: batch of each sample
     column (int8, -1 for padding) and 1 / samples per batch; None when the fused kernel does not
     apply (one batch: no QC, _nam.py:89; more than 8 batches: separate kernel)."""
-    if batches is None or len(np.unique(batches)) == 1:
+    if batches is None:
         return None
-    ub, order, off = _batch_segments(batches.reindex(labels).to_numpy())  # _nam.py:79
-    if not 2 <= len(ub) <= 8 or ld // 4 > 128:  # the fused kernel's limits: <= 8 batches, <= 512 columns
-        return None
-    col_batch = np.full(ld, -1, dtype=np.int8)
-    for b in range(len(ub)):
-        col_batch[order[off[b]:off[b + 1]]] = b
-    return _to_dev(col_batch), _to_dev(1.0 / np.diff(off).astype(np.float64))
+    # the plan depends on the batch Series and the sample labels only: kept per (content, labels, device)
+    # — ~0.25 ms of pandas / numpy / two small uploads per call otherwise
+    try:
+        key = (_series_key(batches), id(labels), ld, dev.index)
+    except Exception:  # noqa: BLE001 - unhashable content: no caching
+        key = None
+    if key is not None and key in _QC_PLANS:
+        return _QC_PLANS[key][1]
+    plan = None
+    if len(np.unique(batches)) > 1:
+        ub, order, off = _batch_segments(batches.reindex(labels).to_numpy())  # _nam.py:79
+        if 2 <= len(ub) <= 8 and ld // 4 <= 128:  # the fused kernel's limits: <= 8 batches, <= 512 columns
+            col_batch = np.full(ld, -1, dtype=np.int8)
+            for b in range(len(ub)):
+                col_batch[order[off[b]:off[b + 1]]] = b
+            plan = _to_dev(col_batch), _to_dev(1.0 / np.diff(off).astype(np.float64))
+    if key is not None:
+        if len(_QC_PLANS) >= 8:
+            _QC_PLANS.clear()
+        _QC_PLANS[key] = (labels, plan)  # (the labels object is kept alive so that its id stays unique)
+    return plan
 
 
 def _nam_device(data, sid_name, nsteps=None, maxnsteps=15, self_weight=1, show_progress=False, codes=None,
@@ -493,7 +517,7 @@ def projector(C, nb, ridge):
 
 
 def resid_nam_device(st, colmap, covs, batches, y_std, ridges=None, show_progress=False, want_x=True,
-                     speculate=False):
+                     speculate=False, design=None):
     """``_nam.py:118-177`` + ``_association.py:178-185`` + ``:77`` on the device.
 
     colmap : int array, state column of each of the n selected samples (phenotype order)
@@ -510,7 +534,7 @@ def resid_nam_device(st, colmap, covs, batches, y_std, ridges=None, show_progres
     out = select_output(show_progress)
     n = len(colmap)
     dev = st.s.device
-    C, nb = design_matrix(covs, batches, n)
+    C, nb = design if design is not None else design_matrix(covs, batches, n)
     r = C.shape[1]
     ld = _round_up(n, 8)
     # the fp32 matrix is only needed for the full result surface and for the CUDA-core Gram that
