@@ -35,7 +35,7 @@ def load():
                 "Run `python -m cna_b200.build` on a machine with nvcc 12.9.") from exc
     lib = ctypes.CDLL(LIB_PATH)
     _declare(lib)
-    if lib.cna_abi_version() != 4:
+    if lib.cna_abi_version() != 5:
         raise ImportError("cna_b200: ABI version mismatch between _lib.py and libcna_b200.so")
     _lib = lib
     return lib
@@ -58,7 +58,7 @@ class ResidArgs(ctypes.Structure):
         ("y", _VP),
         ("x_out", _VP), ("ld_x", _I64), ("kurt", _VP), ("ncorr", _VP), ("row_valid", _VP),
         ("x16_hi", _VP), ("x16_lo", _VP), ("ld16", _I64),
-        ("qc_kurt", _VP), ("qc_median", _VP),
+        ("qc_kurt", _VP), ("qc_median", _VP), ("qc_out", _VP),
     ]
 
 
@@ -75,6 +75,7 @@ _SIGNATURES = {
     "cna_row_kurtosis": [_VP, _I64, _I64, _INT, _VP, _VP, _VP],
     "cna_batch_kurtosis": [_VP, _I64, _I64, _VP, _VP, _VP, _INT, _INT, _VP, _VP],
     "cna_resid_pass": [ctypes.POINTER(ResidArgs), _VP],
+    "cna_qc_fixup": [_VP, _VP, _I64, _VP, _I64, _VP, _VP, _I64, _VP, _VP, _VP, _VP],
     "cna_gram": [_VP, _I64, _I64, _INT, _VP, _VP],
     "cna_gram_simt": [_VP, _I64, _I64, _INT, _VP, _VP],
     "cna_right_multiply": [_VP, _I64, _I64, _INT, _VP, _I64, _INT, _VP, _I64, _VP],
@@ -300,10 +301,12 @@ def batch_kurtosis(s, inv_count, seg_order, seg_off, kurt):
 
 
 def resid_pass(s, inv_count, colmap, row_keep, C, Wt, seg_order, seg_off, y, x_out, kurt, ncorr, row_valid,
-               planes=None, qc_kurt=None, qc_median=None):
+               planes=None, qc_kurt=None, qc_median=None, qc_out=None):
     """``row_keep`` (uint8 mask) or ``qc_kurt`` + ``qc_median`` (device: keep iff kurt < max(6, 2 median))
-    decide which rows survive the QC; both None keeps every row."""
+    decide which rows survive the QC; both None keeps every row.  ``qc_out``: receives the QC statistic of
+    every row instead (the caller decides afterwards, ``qc_fixup``)."""
     a = ResidArgs()
+    a.qc_out = _ptr(qc_out, torch.float64, "qc_out", allow_none=True)
     a.qc_kurt = _ptr(qc_kurt, torch.float64, "qc_kurt", allow_none=True) if row_keep is None else None
     a.qc_median = _ptr(qc_median, torch.float64, "qc_median", allow_none=True) if a.qc_kurt else None
     a.s = _ptr(s, torch.float32, "s"); a.ld_s = s.shape[1]; a.n_rows = s.shape[0]
@@ -332,6 +335,16 @@ def resid_pass(s, inv_count, colmap, row_keep, C, Wt, seg_order, seg_off, y, x_o
     a.ncorr = _ptr(ncorr, torch.float64, "ncorr")
     a.row_valid = _ptr(row_valid, torch.uint8, "row_valid")
     _call("cna_resid_pass", ctypes.byref(a), _stream())
+
+
+def qc_fixup(qc, median, x, planes, kurt, ncorr, row_valid):
+    """Blank the rows whose QC statistic fails ``qc < max(6, 2 median)`` (after ``resid_pass(qc_out=...)``)."""
+    _call("cna_qc_fixup", _ptr(qc, torch.float64, "qc"), _ptr(median, torch.float64, "median"), qc.numel(),
+          _ptr(x, torch.float32, "x", allow_none=True), 0 if x is None else x.shape[1],
+          None if planes is None else _ptr(planes.hi, torch.float16, "x16_hi"),
+          None if planes is None else _ptr(planes.lo, torch.float16, "x16_lo"),
+          0 if planes is None else planes.ld, _ptr(kurt, torch.float64, "kurt", allow_none=True),
+          _ptr(ncorr, torch.float64, "ncorr"), _ptr(row_valid, torch.uint8, "row_valid"), _stream())
 
 
 def gram(x, n, out, simt=False):

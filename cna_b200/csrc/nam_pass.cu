@@ -515,6 +515,18 @@ __global__ void __launch_bounds__(256, 2) resid_lin_kernel(cna_resid_args a, Res
                 kurt = kurtosis_from_moments(mm, m2 / nbk, m4 / nbk, false);
             }
             if (a.kurt) a.kurt[row] = kurt;
+            if (a.qc_out) {  // the QC statistic of the raw row (_nam.py:78-82): kurtosis across its batch means
+                double mm = 0.0;
+                for (int b = 0; b < nbk; ++b) mm += t[2 + r + b];
+                mm /= nbk;
+                double m2 = 0.0, m4 = 0.0;
+                for (int b = 0; b < nbk; ++b) {
+                    const double d2 = (t[2 + r + b] - mm) * (t[2 + r + b] - mm);
+                    m2 += d2;
+                    m4 += d2 * d2;
+                }
+                a.qc_out[row] = kurtosis_from_moments(mm, m2 / nbk, m4 / nbk, false);
+            }
             // ddof=1 standardisation (_nam.py:159; pandas std is taken around the mean of x')
             const double s1 = t[m1p + 2] * inv_n;
             inv_std = rsqrt((t[m1p + 1] - dn * s1 * s1) * inv_nm1);
@@ -548,11 +560,49 @@ __global__ void __launch_bounds__(256, 2) resid_lin_kernel(cna_resid_args a, Res
     }
 }
 
+// Late QC decision (cna_resid_pass with qc_out): a warp per row, rows that pass cost one load.
+__global__ void __launch_bounds__(256) qc_fixup_kernel(const double *__restrict__ qc, const double *__restrict__ median,
+                                                       int64_t n_rows, float *x, int64_t ld_x, __half *hi, __half *lo,
+                                                       int64_t ld16, double *kurt, double *ncorr, uint8_t *row_valid) {
+    const double two_med = 2.0 * median[0];
+    const double thr = two_med > 6.0 ? two_med : 6.0;  // Python's max(6, 2 * median): NaN -> 6
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+    for (int64_t row = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; row < n_rows; row += warps) {
+        if (qc[row] < thr) continue;  // kept (NaN fails the comparison: dropped, _nam.py:96)
+        if (x)
+            for (int64_t c = lane; c < ld_x; c += 32) x[row * ld_x + c] = 0.f;
+        if (hi)
+            for (int64_t c = lane; c < ld16; c += 32) {
+                hi[row * ld16 + c] = __float2half_rn(0.f);
+                lo[row * ld16 + c] = __float2half_rn(0.f);
+            }
+        if (lane == 0) {
+            if (kurt) kurt[row] = nan("");
+            ncorr[row] = 0.0;
+            row_valid[row] = 0;
+        }
+    }
+}
+
 }  // namespace cna
 
 using namespace cna;
 
 extern "C" {
+
+int cna_qc_fixup(const double *qc, const double *median, int64_t n_rows, float *x, int64_t ld_x, void *x16_hi,
+                 void *x16_lo, int64_t ld16, double *kurt, double *ncorr, uint8_t *row_valid, void *stream) {
+    CNA_REQUIRE(qc && median && ncorr && row_valid && n_rows >= 0, "cna_qc_fixup: bad arguments");
+    CNA_REQUIRE((x16_hi == nullptr) == (x16_lo == nullptr), "cna_qc_fixup: both planes or none");
+    if (n_rows == 0) return CNA_OK;
+    int64_t blocks = (n_rows + 7) / 8, cap = int64_t(num_sms()) * 16;
+    qc_fixup_kernel<<<unsigned(blocks < cap ? blocks : cap), 256, 0, as_stream(stream)>>>(
+        qc, median, n_rows, x, ld_x, static_cast<__half *>(x16_hi), static_cast<__half *>(x16_lo), ld16, kurt, ncorr,
+        row_valid);
+    CNA_LAUNCHED("qc_fixup_kernel");
+    return CNA_OK;
+}
 
 int cna_batch_kurtosis(const float *s, int64_t ld, int64_t n_rows, const double *inv_count,
                        const int32_t *seg_order, const int32_t *seg_off, int n_batches, int n_sel,
@@ -590,6 +640,8 @@ int cna_resid_pass(const cna_resid_args *args, void *stream) {
     const bool want_kurt = a.kurt && a.n_batches > 1;
     CNA_REQUIRE(!want_kurt || (a.seg_order && a.seg_off), "cna_resid_pass: batch segments missing");
     CNA_REQUIRE(!a.qc_kurt || a.qc_median, "cna_resid_pass: qc_kurt needs qc_median");
+    CNA_REQUIRE(!a.qc_out || (want_kurt && !a.qc_kurt && !a.row_keep),
+                "cna_resid_pass: qc_out needs the batch segments and no other QC input");
     int nq = (a.n + 31) / 32;
     cudaStream_t st = as_stream(stream);
     {   // the linear-functional kernel whenever its tables fit in shared memory
@@ -629,6 +681,7 @@ int cna_resid_pass(const cna_resid_args *args, void *stream) {
             return CNA_OK;
         }
     }
+    CNA_REQUIRE(!a.qc_out, "cna_resid_pass: qc_out is produced by the linear-functional kernel only (tables too large)");
     const int R = nq <= 8 ? 4 : (nq <= 16 ? 2 : 1);  // rows per warp (register budget: R * NQ doubles)
     size_t smem = sizeof(double) * (2 * size_t(a.r) * a.n + 2 * size_t(a.n) + size_t(warps) * R * a.r +
                                     (want_kurt ? size_t(warps) * (a.n + a.n_batches) : 0)) +

@@ -4,6 +4,7 @@ Mirrors ``src/cna/tools/_association.py`` of the reference: same signature, side
 ``data.obs``, exceptions, warnings and result Namespace.  The NAM never leaves the GPU unless
 ``return_full=True`` asks for the big matrices.
 """
+import os
 import warnings
 from argparse import Namespace
 
@@ -148,6 +149,30 @@ def _adopt_column(obs, key, values):
         obs[key] = pd.Series(values, index=obs.index, copy=False)
     except Exception:  # noqa: BLE001 - an obs container that cannot adopt a Series gets the plain copy
         obs[key] = values
+
+
+def _all_samples_selected(labels, y, batches, covs):
+    """True when the call selects every sample of the data, in label order, with complete phenotype / batch /
+    covariate values and 2..16 batches (cheap numpy checks: this runs before the first kernel is queued)."""
+    try:
+        if batches is None or len(y) != len(labels) or len(labels) > 256:
+            return False
+        if not (y.index.equals(labels) and (batches.index is y.index or batches.index.equals(y.index))):
+            return False
+        yv, bv = y.to_numpy(), batches.to_numpy()
+        if yv.dtype.kind not in "fiub" or bv.dtype.kind not in "fiub":
+            return False
+        if (yv.dtype.kind == "f" and np.isnan(yv).any()) or (bv.dtype.kind == "f" and np.isnan(bv).any()):
+            return False
+        if covs is not None:
+            cv = covs.to_numpy()
+            if not (covs.index is y.index or covs.index.equals(y.index)) or cv.dtype.kind not in "fiub":
+                return False
+            if cv.dtype.kind == "f" and np.isnan(cv).any():
+                return False
+        return 2 <= len(np.unique(bv)) <= 16
+    except Exception:  # noqa: BLE001 - anything unusual takes the general route
+        return False
 
 
 def default_ks(n):
@@ -516,10 +541,16 @@ def association(data, y, sid_name, batches=None, covs=None, donorids=None, ks=No
     # data.obs).  A host graph is uploaded and reordered first (~10 ms): there the draw is started before.
     user_batches = batches
 
+    # Every sample of the data selected, in label order (the common call): the QC statistic of a cell is then
+    # a by-product of the residualisation pass (its batch-mean functionals are the QC's batch means), so the
+    # last diffusion step runs without its QC epilogue and the decision is applied afterwards (cna_qc_fixup)
+    qc_in_pass = (not show_progress and not os.environ.get("CNA_B200_QC_IN_SPMM")
+                  and _all_samples_selected(codes[0], y, batches, covs))
+
     def launch_nam():
         print("computing NAM", file=out)
         st = _nam._nam_device(data, sid_name, nsteps=nsteps, show_progress=show_progress, codes=codes,
-                              qc_batches=user_batches)
+                              qc_batches=None if qc_in_pass else user_batches)
         mark("diffusion launched")
         return st
 
@@ -569,11 +600,14 @@ def association(data, y, sid_name, batches=None, covs=None, donorids=None, ks=No
         if stn is None:
             stn = launch_nam()
         # ---- QC and residualisation: queued behind the diffusion, no host round trip ----
-        _nam._qc_device(stn, batches, show_progress=show_progress)
+        if qc_in_pass:
+            stn._keep, stn.qc_median, stn.qc_kurt = None, None, None
+        else:
+            _nam._qc_device(stn, batches, show_progress=show_progress)
         colmap = stn.labels.get_indexer(sids)  # NAM.reindex(y.index)[filter_samples], :178-181
         res = _nam.resid_nam_device(stn, colmap, covs_f, batches_f, y_std, ridges=ridges,
                                     show_progress=show_progress, want_x=return_full, speculate=True,
-                                    design=design)
+                                    design=design, qc_in_pass=qc_in_pass)
         mark("resid pass launched")
         res.y_std = y_std
         res.ks = ks_eff

@@ -517,7 +517,7 @@ def projector(C, nb, ridge):
 
 
 def resid_nam_device(st, colmap, covs, batches, y_std, ridges=None, show_progress=False, want_x=True,
-                     speculate=False, design=None):
+                     speculate=False, design=None, qc_in_pass=False):
     """``_nam.py:118-177`` + ``_association.py:178-185`` + ``:77`` on the device.
 
     colmap : int array, state column of each of the n selected samples (phenotype order)
@@ -550,13 +550,23 @@ def resid_nam_device(st, colmap, covs, batches, y_std, ridges=None, show_progres
                     ridge_median=None, settle=lambda med=None: True)
     C_d = _to_dev(C) if r else None
     row_keep = st._keep  # an explicit mask wins; otherwise the QC decision is taken inside the pass
-    qc_kurt = st.qc_kurt if (row_keep is None and st.qc_median is not None) else None
+    qc = Namespace(kurt=st.qc_kurt if (row_keep is None and st.qc_median is not None) else None,
+                   pending=bool(qc_in_pass) and nb > 1 and row_keep is None and st.qc_median is None)
 
     def run(Wcum, seg=None, kurt=None):
         W_d = _to_dev(np.ascontiguousarray(Wcum)) if r else None
+        qc_out = torch.empty(st.N, dtype=torch.float64, device=dev) if qc.pending else None
         _lib.resid_pass(st.s, st.inv_count, colmap_d, row_keep, C_d, W_d,
                         seg[0] if seg else None, seg[1] if seg else None, y_d, x, kurt, ncorr, valid,
-                        planes=planes, qc_kurt=qc_kurt, qc_median=st.qc_median if qc_kurt is not None else None)
+                        planes=planes, qc_kurt=qc.kurt, qc_median=st.qc_median if qc.kurt is not None else None,
+                        qc_out=qc_out)
+        if qc_out is not None:
+            # the QC statistic (_nam.py:78-82) came out of this pass: median, threshold and the late decision
+            # (_nam.py:94-99) follow on the device; later ridge stages reuse it as an input
+            qc.pending = False
+            st.qc_kurt = qc.kurt = qc_out
+            st.qc_median = median_device(qc_out, comm=st.comm, rows_per=st.rows_per)
+            _lib.qc_fixup(qc_out, st.qc_median, x, planes, kurt, ncorr, valid)
 
     if nb == 0:
         if r > 0:  # _nam.py:133

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define CNA_B200_ABI_VERSION 4
+#define CNA_B200_ABI_VERSION 5
 
 /* bit pattern (a signalling NaN) of vector entries cna_median_f64 ignores: padding of gathered shards */
 #define CNA_MEDIAN_SKIP_BITS 0x7FF4DEADBEEF0001ull
@@ -162,11 +162,24 @@ typedef struct cna_resid_args {
      * device, so no host round trip separates the QC from the residualisation).  Both NULL: keep all. */
     const double *qc_kurt;
     const double *qc_median;
+    /* Optional output (needs the batch segments and qc_kurt == row_keep == NULL): the QC statistic itself,
+     * qc_out[i] = Pearson kurtosis across the per-batch means of the selected, scaled raw row i (_nam.py:78-82) —
+     * a by-product of the pass when every sample of the state is selected.  The pass then keeps every row;
+     * the caller takes the median of qc_out and blanks the rows that fail with cna_qc_fixup, which saves the
+     * QC epilogue of the last diffusion step. */
+    double *qc_out;
 } cna_resid_args;
 
 /* replaces: _association.py:178-185 (reindex, filter, zero-variance drop), _nam.py:122 (centre),
  * :128-156 (M.NAM as a rank-r update), :159 (ddof=1 standardise), _association.py:77 (ncorrs). */
 int cna_resid_pass(const cna_resid_args *args, void *stream);
+
+/* Late QC decision for rows produced by cna_resid_pass with qc_out: rows with !(qc[i] < max(6, 2 * median[0]))
+ * (_nam.py:94-96) get zero operand planes / x rows, ncorr = 0, valid = 0, kurt = NaN — what the pass writes
+ * for a dropped cell.  Any of x, x16_hi / x16_lo, kurt may be NULL.
+ * replaces: _nam.py:96-99 `keep = kurtoses < threshold; NAM.iloc[:, keep]`. */
+int cna_qc_fixup(const double *qc, const double *median, int64_t n_rows, float *x, int64_t ld_x, void *x16_hi,
+                 void *x16_lo, int64_t ld16, double *kurt, double *ncorr, uint8_t *row_valid, void *stream);
 
 /* ------------------------------------------------------------------------------------------
  * kernel (iii): Gram matrix of the standardised NAM

@@ -824,3 +824,35 @@ def test_staged_host_upload_round_trips(cna):
     up = _lib.HostUpload(pinned.numpy(), torch.device("cuda", 0))
     torch.cuda.synchronize()
     np.testing.assert_array_equal(up.wait().cpu().numpy(), pinned.numpy())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["batchy_qc", "all_batchy_ridgewalk"])
+def test_qc_decided_after_the_residualisation_pass(cna, synth, name, monkeypatch):
+    """When every sample is selected the QC statistic is produced by cna_resid_pass (qc_out) and the decision
+    applied by cna_qc_fixup (the route the golden cases above take); with CNA_B200_QC_IN_SPMM=1 the statistic
+    comes from the last diffusion step's epilogue and the decision is taken inside the pass.  On the two golden
+    cases whose QC drops cells (one of them walks several ridges, so later stages reuse the statistic as an
+    input): the same kept set, coefficients, FDRs and p; in the first case cells are indeed dropped."""
+    from cna_b200.tl import _association as A_
+    arrays, scalars = synth
+    spec = cases.SYNTH_CASES[name]
+    res = {}
+    for mode in ("pass", "spmm"):
+        if mode == "spmm":
+            monkeypatch.setenv("CNA_B200_QC_IN_SPMM", "1")
+        data, kwargs = cases.build_synth_case(spec, helpers.synth_raw(arrays, name))
+        if mode == "pass":
+            assert A_._all_samples_selected(pd.Index(np.unique(data.obs["id"])), kwargs["y"], kwargs.get("batches"),
+                                            kwargs.get("covs"))
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            full = cna.tl.association(data, return_full=True, **kwargs)
+        res[mode] = (full, data.obs["coef"].to_numpy().copy(), data.obs["coef_fdr"].to_numpy().copy())
+    a, b = res["pass"], res["spmm"]
+    np.testing.assert_array_equal(a[0].kept, b[0].kept)
+    if name == "batchy_qc":
+        assert 0 < (~a[0].kept).sum() < len(a[0].kept)
+    assert a[0].p == b[0].p and int(a[0].k) == int(b[0].k)
+    np.testing.assert_allclose(a[1], b[1], rtol=1e-12, atol=1e-14, equal_nan=True)
+    np.testing.assert_allclose(a[2], b[2], rtol=1e-12, atol=1e-14, equal_nan=True)

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/cna_b200.h but not exported"
     assert declared == set(_lib.EXPORTS)
-    assert lib.cna_abi_version() == 4
+    assert lib.cna_abi_version() == 5
     assert isinstance(lib.cna_last_error(), bytes)
     # every entry point is documented: a "replaces:" citation in the header, a row in INTEGRATION.md
     integration = open(os.path.join(ROOT, "INTEGRATION.md")).read()
