@@ -772,7 +772,9 @@ class DevicePermJob:
         self._keep = (ws, key, src)
         side = _DRAW_STREAM.get(dev)
         if side is None:
-            side = _DRAW_STREAM[dev] = torch.cuda.Stream(device=dev)
+            # high priority: its single-CTA recurrence should start as soon as it is queued, beside the
+            # diffusion, instead of waiting for a free slot behind the grid of the running kernel
+            side = _DRAW_STREAM[dev] = torch.cuda.Stream(device=dev, priority=-1)
         with torch.cuda.stream(side):
             base = self.small.data_ptr()
             rc = load().cna_perm_draw_device(key.ctypes.data, int(pos), int(has_gauss), float(gauss), nb,

@@ -57,21 +57,20 @@ __global__ void __launch_bounds__(256) mt_stream_kernel(uint32_t *__restrict__ r
     for (int64_t b = 1; b <= n_blocks; ++b) {
         const uint32_t *o = st[cur];
         uint32_t *nw = st[cur ^ 1];
-        if (t < kN - kM) nw[t] = twist(o[t], o[t + 1], o[t + kM]);  // [0, 227): old words only
+        uint32_t *out = raw + b * kN;  // every word goes to global memory as it is produced
+        if (t < kN - kM) out[t] = nw[t] = twist(o[t], o[t + 1], o[t + kM]);  // [0, 227): old words only
         __syncthreads();
         {
             const int i = (kN - kM) + t;  // [227, 454): new words written one wave earlier
-            if (t < kN - kM) nw[i] = twist(o[i], o[i + 1], nw[i - (kN - kM)]);
+            if (t < kN - kM) out[i] = nw[i] = twist(o[i], o[i + 1], nw[i - (kN - kM)]);
         }
         __syncthreads();
         {
             const int i = 2 * (kN - kM) + t;  // [454, 623), and the wrap-around word 623
-            if (i < kN - 1) nw[i] = twist(o[i], o[i + 1], nw[i - (kN - kM)]);
-            else if (i == kN - 1) nw[i] = twist(o[kN - 1], nw[0], nw[kM - 1]);
+            if (i < kN - 1) out[i] = nw[i] = twist(o[i], o[i + 1], nw[i - (kN - kM)]);
+            else if (i == kN - 1) out[i] = nw[i] = twist(o[kN - 1], nw[0], nw[kM - 1]);
         }
         __syncthreads();
-        uint32_t *out = raw + b * kN;
-        for (int i = t; i < kN; i += 256) out[i] = nw[i];
         cur ^= 1;
     }
 }

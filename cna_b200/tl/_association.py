@@ -111,7 +111,7 @@ def _side_stream(dev, tag="copy"):
     kernels queued after the pass that produced them), "eig" for the single-CTA eigensolver."""
     key = (dev.type, dev.index, tag)
     if key not in _SIDE:
-        _SIDE[key] = torch.cuda.Stream(device=dev)
+        _SIDE[key] = torch.cuda.Stream(device=dev, priority=-1 if tag == "eig" else 0)
     return _SIDE[key]
 
 
