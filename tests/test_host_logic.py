@@ -338,3 +338,25 @@ def test_tile_plan_is_consistent():
     B = B.tocsr()
     with pytest.raises(_lib.CnaError):
         _graph.TilePlan(t(B.indptr.astype(np.int32)), t(B.indices.astype(np.int32)), t(B.data.astype(np.float32)), n)
+
+
+def test_namespace_mirrors_the_reference_package():
+    """``import cna_b200 as cna`` offers the reference's public names (src/cna/__init__.py:1-3,
+    tools/__init__.py, plotting/__init__.py, utils/__init__.py); the plotting helpers import their optional
+    stack on use and say so when it is missing."""
+    import inspect
+
+    import cna_b200 as cna
+    for name in ("association", "nam", "svd_nam", "diffuse", "diffuse_stepwise"):
+        assert callable(getattr(cna.tl, name))
+    assert callable(cna.ut.obs_to_sample)
+    for name, params in (("umap_ncorr", ["data", "fdr_thresh", "key"]),
+                         ("umap_overlay", ["data", "mask", "key", "scatter0", "scatter1", "ax", "noframe"]),
+                         ("violinplot", ["data", "stratification", "key", "ax", "cmap"])):
+        fn = getattr(cna.pl, name)
+        assert list(inspect.signature(fn).parameters)[:len(params)] == params
+    try:
+        import matplotlib  # noqa: F401
+    except ImportError:
+        with pytest.raises(ImportError, match="optional dependency 'matplotlib'"):
+            cna.pl.violinplot(None, "cluster")
