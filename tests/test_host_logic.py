@@ -360,3 +360,36 @@ def test_namespace_mirrors_the_reference_package():
     except ImportError:
         with pytest.raises(ImportError, match="optional dependency 'matplotlib'"):
             cna.pl.violinplot(None, "cluster")
+
+
+def test_all_samples_selected_predicate():
+    """The cheap eligibility test for taking the QC statistic out of the residualisation pass
+    (tl/_association.py:_all_samples_selected): every sample selected, in label order, complete inputs."""
+    from cna_b200.tl._association import _all_samples_selected as ok
+    labels = pd.Index(np.arange(12))
+    y = pd.Series(np.arange(12) % 2, index=labels, dtype=float)
+    b = pd.Series(np.arange(12) % 3, index=labels)
+    covs = pd.DataFrame({"age": np.linspace(0, 1, 12)}, index=labels)
+    assert ok(labels, y, b, covs) and ok(labels, y, b, None)
+    assert not ok(labels, y, None, covs)                                  # no batches: no QC at all
+    assert not ok(labels, y.iloc[::-1], b.iloc[::-1], None)               # phenotype in another order
+    assert not ok(labels, y.iloc[:-1], b.iloc[:-1], None)                 # a sample without phenotype
+    y_nan = y.copy()
+    y_nan.iloc[3] = np.nan
+    assert not ok(labels, y_nan, b, None)                                 # NaN phenotype filters a sample
+    c_nan = covs.copy()
+    c_nan.iloc[5, 0] = np.nan
+    assert not ok(labels, y, b, c_nan)
+    assert not ok(labels, y, pd.Series(np.zeros(12), index=labels), None)  # a single batch
+    assert not ok(labels, y, b.astype(str), None)                         # non-numeric batches take the general route
+    assert not ok(pd.Index(np.arange(13)), y, b, None)                    # data has a sample the phenotype lacks
+
+
+def test_series_key_tracks_content():
+    from cna_b200.tl._nam import _series_key
+    a = pd.Series([0, 1, 0, 2], index=[3, 1, 2, 0])
+    assert _series_key(a) == _series_key(a.copy())
+    assert _series_key(a) != _series_key(pd.Series([0, 1, 0, 3], index=[3, 1, 2, 0]))
+    assert _series_key(a) != _series_key(pd.Series([0, 1, 0, 2], index=[3, 1, 0, 2]))
+    s = pd.Series(["x", "y"], index=["a", "b"])
+    assert _series_key(s) == _series_key(s.copy()) and _series_key(s) != _series_key(s.iloc[::-1])
