@@ -151,9 +151,22 @@ def _adopt_column(obs, key, values):
         obs[key] = values
 
 
+def _resid_tables_fit(n, r, nbk):
+    """Mirror of the shared-memory budget of the linear-functional residualisation kernel
+    (csrc/nam_pass.cu:cna_resid_pass, the only kernel that emits ``qc_out``), for n <= 256 samples."""
+    nq = (n + 31) // 32
+    if nq > 8:
+        return False
+    rows, warps, ldn = 4, 8, 32 * nq
+    m1p = -(-(2 + r + nbk) // (16 // rows)) * (16 // rows)
+    doubles = (m1p + r + 1) * ldn + nbk * r + r + 1 + warps * rows * (m1p + 3)
+    return 8 * doubles + 4 * ldn <= 100 * 1024
+
+
 def _all_samples_selected(labels, y, batches, covs):
     """True when the call selects every sample of the data, in label order, with complete phenotype / batch /
-    covariate values and 2..16 batches (cheap numpy checks: this runs before the first kernel is queued)."""
+    covariate values, 2..16 batches, and a design small enough for the kernel that emits the statistic (cheap
+    numpy checks: this runs before the first kernel is queued)."""
     try:
         if batches is None or len(y) != len(labels) or len(labels) > 256:
             return False
@@ -168,9 +181,11 @@ def _all_samples_selected(labels, y, batches, covs):
             cv = covs.to_numpy()
             if not (covs.index is y.index or covs.index.equals(y.index)) or cv.dtype.kind not in "fiub":
                 return False
-            if cv.dtype.kind == "f" and np.isnan(cv).any():
+            if (cv.dtype.kind == "f" and np.isnan(cv).any()) or cv.ndim != 2:
                 return False
-        return 2 <= len(np.unique(bv)) <= 16
+        nb = len(np.unique(bv))
+        ncov = 0 if covs is None else cv.shape[1]
+        return 2 <= nb <= 16 and _resid_tables_fit(len(labels), nb + ncov, nb)
     except Exception:  # noqa: BLE001 - anything unusual takes the general route
         return False
 

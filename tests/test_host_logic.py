@@ -393,3 +393,14 @@ def test_series_key_tracks_content():
     assert _series_key(a) != _series_key(pd.Series([0, 1, 0, 2], index=[3, 1, 0, 2]))
     s = pd.Series(["x", "y"], index=["a", "b"])
     assert _series_key(s) == _series_key(s.copy()) and _series_key(s) != _series_key(s.iloc[::-1])
+
+
+def test_resid_tables_fit_mirrors_the_kernel_budget():
+    """tl/_association.py:_resid_tables_fit restates the shared-memory test of cna_resid_pass's
+    linear-functional kernel (csrc/nam_pass.cu: (m1p + r + 1) ldn + nbk r + r + 1 + warps R (m1p + 3) doubles
+    + ldn ints <= 100 KiB): the benchmark and golden shapes fit, large designs take the general route."""
+    from cna_b200.tl._association import _resid_tables_fit as fits
+    assert fits(200, 5, 4) and fits(100, 5, 4) and fits(40, 11, 10) and fits(50, 6, 5)
+    assert not fits(256, 40, 16) and not fits(300, 5, 4)
+    src = open(os.path.join(ROOT, "cna_b200", "csrc", "nam_pass.cu")).read()
+    assert "size_t(m1p + a.r + 1) * ldn + size_t(tb.nbk) * a.r + a.r + 1" in src and "smem <= 100 * 1024" in src
