@@ -115,3 +115,40 @@ def test_neighbors_writes_the_scanpy_fields_and_feeds_association():
     y = pd.Series((np.arange(S) % 2).astype(float), index=np.arange(S))
     p = cna.tl.association(d, y, "id", Nnull=100, seed=0, nsteps=3)
     assert 0 < p <= 1 and "coef" in d.obs
+
+
+def test_fuzzy_simplicial_set_properties_on_random_neighbour_lists():
+    """Symmetric, zero diagonal, weights in (0, 1], every stored kNN edge present, and the nearest neighbour of
+    every cell carries weight 1 (local_connectivity = 1: rho is the distance to it)."""
+    from sklearn.neighbors import NearestNeighbors
+
+    from cna_b200.pp import fuzzy_simplicial_set
+    rng = np.random.default_rng(2)
+    X = rng.normal(size=(1500, 8))
+    dist, idx = NearestNeighbors(n_neighbors=11).fit(X).kneighbors(X)
+    A = fuzzy_simplicial_set(idx[:, 1:], dist[:, 1:])
+    assert A.shape == (1500, 1500) and abs(A - A.T).max() < 1e-15 and A.diagonal().sum() == 0
+    assert 0 < A.data.min() and A.data.max() <= 1.0 + 1e-12  # p + q - p q of two ones, up to rounding
+    assert (np.asarray(A[np.repeat(np.arange(1500), 10), idx[:, 1:].ravel()]) > 0).all()
+    np.testing.assert_allclose(np.asarray(A[np.arange(1500), idx[:, 1]]).ravel(), 1.0, rtol=0, atol=1e-12)
+    with pytest.raises(ValueError):
+        fuzzy_simplicial_set(idx[:100, 1:], dist[:100, 1:], n_total=1500)
+
+
+def test_neighbors_argument_checks():
+    """pp.neighbors validates before touching the GPU: representation lookup and shape, n_neighbors range."""
+    from cna_b200 import pp, synth
+    import pandas as pd
+    d = synth.AnnDataLike(pd.DataFrame({"id": np.zeros(10, dtype=int)}), None)
+    with pytest.raises(ValueError, match="neither"):
+        pp.neighbors(d)
+    d.obsm = {"X_pca": np.zeros((10, 70))}
+    with pytest.raises(ValueError, match="d <= 64"):
+        pp.neighbors(d)
+    with pytest.raises(ValueError, match="no 'X_other'"):
+        pp.neighbors(d, use_rep="X_other")
+    d.obsm["X_pca"] = np.zeros((10, 5))
+    with pytest.raises(ValueError, match="n_neighbors"):
+        pp.neighbors(d, n_neighbors=11)
+    with pytest.raises(ValueError, match="n_neighbors"):
+        pp.neighbors(d, n_neighbors=1)
