@@ -47,9 +47,10 @@ CONFIGS = {
 METRIC = "cells/sec through nam()+association(), 1M cells/200 samples/10k perms"
 # CPU sample: same samples / k / steps, cells and permutations scaled down by the same factor
 CPU_SAMPLE_SCALE = 20
-# DRAM traffic of one SpMM launch at config C from the committed `ncu --set full` capture
-# (profiles/r01c_ncu_spmm_summary.txt: 2.600 GB read + 0.780 GB written; 31.6 GB before the reordering)
-SPMM_DRAM_TRAFFIC_GB = 3.380
+# DRAM traffic of one SpMM launch at config C from the committed `ncu --set full` captures
+# (profiles/r02c_ncu_full_summary.txt: 2.605 GB read + 0.788 GB written; profiles/r01c_ncu_spmm_summary.txt:
+# 2.600 + 0.780 GB for the plain step; 31.6 GB before the cell reordering)
+SPMM_DRAM_TRAFFIC_GB = 3.393
 
 
 def parse_args():
@@ -445,9 +446,8 @@ def run_ours(args):
         primary = {"kernel": "cna_diffuse_step_f32 (CSR SpMM diffusion step)", "bound": "hbm",
                    "achieved": spmm["achieved"], "peak": spmm["peak"], "unit": "GB/s", "frac": spmm["frac"],
                    "traffic": SPMM_DRAM_TRAFFIC_GB if (args.config == "C" and world == 1) else None,
-                   "traffic_unit": "GB per launch (dram__bytes_read.sum + dram__bytes_write.sum, "
-                                   "profiles/r01c_ncu_spmm_summary.txt; captured on the Cuthill-McKee order, "
-                                   "before its block-local refinement was enabled)",
+                   "traffic_unit": "GB per launch (dram__bytes_read.sum + dram__bytes_write.sum of one spmm_f32_kernel "
+                                   "launch, profiles/r02c_ncu_full_summary.txt)",
                    "algorithmic_gb": spmm["algorithmic_bytes"] / 1e9,
                    "peak_source": peaks["source"] + " (MEASURED_PEAKS.json hbm_gbs)"}
     line = {
